@@ -1,0 +1,259 @@
+"""Pin the oracle to the reference and write the committed fixtures under tests/golden/.
+
+Runs ONLY in the build container (needs /root/reference).  For every fixture it (1) executes the
+UNMODIFIED reference code (imported from /root/reference, with ``.to('cuda')`` redirected to CPU and
+``torch.randn_like`` fed from a noise tape), (2) asserts the oracle restatement agrees, (3) stores the
+reference's outputs.  tests/test_oracle_golden.py re-checks the oracle against these files everywhere;
+tests/test_gpu_*.py check the CUDA engine against them on the B200.
+
+    python -m oracle.gen_golden
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+from oracle import operators as O          # noqa: E402
+from oracle import sampler as S            # noqa: E402
+from oracle import schedule as SCH         # noqa: E402
+from oracle import unet_simple as U        # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def ns(**k):
+    return types.SimpleNamespace(**k)
+
+
+def ref_model(cfg, seed):
+    from guided_diffusion.models import Model
+    c = ns(model=ns(type="simple", ch=cfg.ch, out_ch=cfg.out_ch, ch_mult=list(cfg.ch_mult),
+                    num_res_blocks=cfg.num_res_blocks, attn_resolutions=list(cfg.attn_resolutions), dropout=0.0,
+                    in_channels=cfg.in_channels, resamp_with_conv=True),
+           data=ns(image_size=cfg.resolution), diffusion=ns(num_diffusion_timesteps=1000))
+    torch.manual_seed(seed)
+    return Model(c).eval()
+
+
+class cpu_shim:
+    """Redirect the reference's hard-coded device moves (svd_ddnm.py:45,72) and feed randn_like from a tape."""
+
+    def __init__(self, tape):
+        self.tape = list(tape)
+
+    def __enter__(self):
+        self._to, self._rl = torch.Tensor.to, torch.randn_like
+        orig_to = self._to
+
+        def to(t, *a, **k):
+            if a and isinstance(a[0], str) and a[0].startswith("cuda"):
+                return t
+            return orig_to(t, *a, **k)
+        tape = self.tape
+
+        def randn_like(x, *a, **k):
+            z = tape.pop(0)
+            assert z.shape == x.shape
+            return z
+        torch.Tensor.to = to
+        torch.randn_like = randn_like
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.to, torch.randn_like = self._to, self._rl
+
+
+def close(a, b, tol, what):
+    d = (a - b).abs().max().item()
+    assert d <= tol, f"{what}: oracle deviates from reference by {d}"
+    return d
+
+
+# --------------------------------------------------------------------------------------------------
+def unet_fixtures():
+    out = {}
+    for name, cfg, B in (("tiny", U.SimpleUNetConfig.tiny(), 2), ("celeba", U.SimpleUNetConfig.celeba_hq(), 1)):
+        m = ref_model(cfg, 1234)
+        sd = U.init_state_dict(cfg, 1234)
+        assert all(torch.equal(sd[k], v) for k, v in m.state_dict().items()), "weight init differs"
+        g = torch.Generator().manual_seed(99)
+        x = torch.randn(B, 3, cfg.resolution, cfg.resolution, generator=g)
+        t = torch.tensor([417.0, 3.0][:B])
+        with torch.no_grad():
+            r = m(x, t)
+            taps = {}
+            o = U.forward(sd, x, t, cfg, taps=taps)
+        close(o, r, 0.0, f"unet {name}")
+        out[f"{name}_t"] = t.numpy()
+        if name == "tiny":
+            out["tiny_x"] = x.numpy()
+            out["tiny_out"] = r.numpy()
+            for k in ("conv_in", "down.0.0", "down.0.ds", "down.1.0", "mid.attn_1", "up.1.us", "up.0.1"):
+                out["tiny_tap_" + k] = taps[k].numpy()
+        else:
+            # full 256x256 net: x is regenerated from the seed by the test; keep a strided sample of eps
+            out["celeba_out_s8"] = r[:, :, ::8, ::8].contiguous().numpy()
+            out["celeba_out_sum"] = np.array([r.double().sum().item(), r.double().abs().sum().item()])
+        print(f"unet {name}: ok, out std {r.std().item():.4f}")
+    np.savez_compressed(os.path.join(GOLD, "unet_simple.npz"), **out)
+
+
+# --------------------------------------------------------------------------------------------------
+def _ref_inpainting(R, channels, img_dim, mask_flat):
+    """The reference constructor's kept-index loop is O(N*missing) (svd_operators.py:330); build the
+    same object through a boolean complement (identical kept/missing index tensors)."""
+    mr = torch.nonzero(mask_flat == 0).long().reshape(-1) * 3          # diffusion.py:467-470
+    missing = torch.cat([mr, mr + 1, mr + 2], dim=0)
+    n = channels * img_dim ** 2
+    r = R.Inpainting.__new__(R.Inpainting)
+    r.channels, r.img_dim, r.missing_indices = channels, img_dim, missing
+    r._singulars = torch.ones(n - missing.shape[0])
+    keep = torch.ones(n, dtype=torch.bool)
+    keep[missing] = False
+    r.kept_indices = torch.nonzero(keep).reshape(-1)
+    if img_dim <= 32:                                                     # small enough for the real loop
+        rr = R.Inpainting(channels, img_dim, missing, "cpu")
+        assert torch.equal(rr.kept_indices, r.kept_indices)
+    return r
+
+
+def gauss_kernel():
+    # diffusion.py:504-509
+    sigma = 10
+    pdf = lambda z: torch.exp(torch.Tensor([-0.5 * (z / sigma) ** 2]))   # noqa: E731
+    k = torch.Tensor([pdf(-2), pdf(-1), pdf(0), pdf(1), pdf(2)])
+    return k / k.sum()
+
+
+def build_ops(dim, rng):
+    """(name, reference object, oracle object, artefact dict) for the six north-star operators at image size dim."""
+    from functions import svd_operators as R
+    ops = []
+    r = R.SuperResolution(3, dim, 4, "cpu")
+    ops.append(("sr4", r, O.SuperResolution(3, dim, 4, r.U_small, r.singulars_small, r.V_small),
+                dict(U_small=r.U_small, singulars_small=r.singulars_small, V_small=r.V_small)))
+    r = R.Colorization(dim, "cpu")
+    ops.append(("color", r, O.Colorization(dim, r.U_small, r.singulars_small, r.V_small),
+                dict(U_small=r.U_small, singulars_small=r.singulars_small, V_small=r.V_small)))
+    if dim == 256:
+        mask = np.load(os.path.join(REF, "exp/inp_masks/mask.npy"))
+    else:
+        mask = (torch.rand(dim, dim, generator=rng) > 0.3).long().numpy()
+    r = _ref_inpainting(R, 3, dim, torch.from_numpy(mask).reshape(-1))
+    ops.append(("inpaint", r, O.Inpainting(3, dim, mask), dict(mask=torch.from_numpy(mask))))
+    perm = torch.randperm(dim ** 2, generator=rng)
+    r = R.WalshHadamardCS(3, dim, 4, perm, "cpu")
+    ops.append(("wh", r, O.WalshHadamardCS(3, dim, 4, perm), dict(perm=perm)))
+    r = R.Deblurring(gauss_kernel(), 3, dim, "cpu")
+    ops.append(("deblur", r, O.Deblurring(3, dim, r.U_small, r.V_small, r._singulars, r._singulars_orig, r._perm),
+                dict(U_small=r.U_small, V_small=r.V_small, singulars=r._singulars, singulars_orig=r._singulars_orig,
+                     perm=r._perm)))
+    k = O.SRConv.bicubic_kernel(4)
+    r = R.SRConv(k, 3, dim, "cpu", stride=4)
+    ops.append(("bicubic", r, O.SRConv(3, dim, 4, r.U_small, r.singulars_small, r.V_small),
+                dict(U_small=r.U_small, singulars_small=r.singulars_small, V_small=r.V_small)))
+    return ops
+
+
+LAMBDA_CASES = [(0.9, 0.1, 0.3), (0.99, 0.1, 0.02), (1.0, 0.1, 0.0), (0.5, 0.0, 0.4)]   # (a, sigma_y, sigma_t)
+
+
+def operator_fixtures():
+    out = {}
+    for dim, B in ((32, 2), (256, 1)):
+        rng = torch.Generator().manual_seed(4321)
+        x = torch.rand(B, 3, dim, dim, generator=rng) * 2 - 1
+        v = torch.randn(B, 3 * dim * dim, generator=rng)
+        e = torch.randn(B, 3 * dim * dim, generator=rng)
+        tag = f"d{dim}"
+        if dim == 32:
+            out[f"{tag}_x"], out[f"{tag}_v"], out[f"{tag}_e"] = x.numpy(), v.numpy(), e.numpy()
+        sub = (lambda z: z) if dim == 32 else (lambda z: z.reshape(B, -1)[:, ::61].contiguous())
+        for name, r, o, art in build_ops(dim, rng):
+            if dim == 32 or name in ("wh",):
+                for k, a in art.items():
+                    out[f"{tag}_{name}_art_{k}"] = a.numpy()
+            y = r.A(x)
+            close(o.A(x.reshape(B, -1)), y, 2e-6, f"{name} A")
+            yq = y * 0.9 + 0.05
+            pin = r.A_pinv(yq.clone())
+            close(o.A_pinv(yq.clone()), pin, 2e-6, f"{name} A_pinv")
+            proj = x - r.A_pinv(r.A(x.reshape(B, -1)) - yq.reshape(B, -1)).reshape(x.shape)
+            close(o.project(x, yq), proj, 4e-6, f"{name} project")
+            out[f"{tag}_{name}_A"] = sub(y).numpy()
+            out[f"{tag}_{name}_Apinv"] = sub(pin).numpy()
+            out[f"{tag}_{name}_proj"] = sub(proj).numpy()
+            if name != "bicubic":
+                for ci, (a, sy, st) in enumerate(LAMBDA_CASES):
+                    at, stt = torch.tensor(a), torch.tensor(st)
+                    L = r.Lambda(v.clone(), at, sy, stt, 0.85)
+                    Ln = r.Lambda_noise(v.clone(), at, sy, stt, 0.85, e.clone())
+                    close(o.Lambda(v.clone(), at, sy, stt, 0.85), L, 4e-6, f"{name} Lambda{ci}")
+                    close(o.Lambda_noise(v.clone(), at, sy, stt, 0.85, e.clone()), Ln, 4e-6, f"{name} Lnoise{ci}")
+                    out[f"{tag}_{name}_L{ci}"] = sub(L).numpy()
+                    out[f"{tag}_{name}_Ln{ci}"] = sub(Ln).numpy()
+            print(f"operator {name}@{dim}: ok")
+    np.savez_compressed(os.path.join(GOLD, "operators.npz"), **out)
+
+
+# --------------------------------------------------------------------------------------------------
+def sampler_fixtures():
+    from functions.svd_ddnm import ddnm_diffusion, ddnm_plus_diffusion, get_schedule_jump
+    for T, l, r in ((20, 1, 1), (100, 1, 1), (100, 3, 3), (100, 2, 2), (250, 1, 1), (10, 3, 2)):
+        assert get_schedule_jump(T, l, r) == SCH.jump_schedule(T, l, r)
+    cfg = U.SimpleUNetConfig.tiny()
+    m = ref_model(cfg, 1234)
+    sd = U.init_state_dict(cfg, 1234)
+    betas = SCH.linear_betas()
+    dim, B = cfg.resolution, 2
+    out = {"betas": betas.numpy()}
+    rng = torch.Generator().manual_seed(777)
+    x_orig = torch.rand(B, 3, dim, dim, generator=rng) * 2 - 1
+    x_T = torch.randn(B, 3, dim, dim, generator=rng)
+    out["x_orig"], out["x_T"] = x_orig.numpy(), x_T.numpy()
+    opsets = {n: (r_, o_) for n, r_, o_, _ in build_ops(dim, torch.Generator().manual_seed(4321))}
+    cases = [("sr4", 10, 1, 1, 0.0), ("sr4", 10, 3, 2, 0.0), ("sr4", 10, 1, 1, 0.1), ("color", 10, 1, 1, 0.0),
+             ("inpaint", 10, 2, 2, 0.1), ("wh", 10, 1, 1, 0.0), ("deblur", 10, 1, 1, 0.1), ("bicubic", 10, 1, 1, 0.0)]
+    for name, T, tl, tr, sy in cases:
+        rop, oop = opsets[name]
+        conf = ns(diffusion=ns(num_diffusion_timesteps=1000), time_travel=ns(T_sampling=T, travel_length=tl, travel_repeat=tr))
+        npairs = len(SCH.time_pairs(1000, T, tl, tr))
+        nrng = torch.Generator().manual_seed(555)
+        tape = [torch.randn(B, 3, dim, dim, generator=nrng) for _ in range(npairs)]
+        y = rop.A(x_orig)
+        if sy > 0:
+            y = y + sy * torch.randn(y.shape, generator=nrng)
+        with torch.no_grad(), cpu_shim(tape):
+            if sy == 0.0:
+                xs, x0s = ddnm_diffusion(x_T, m, betas, 0.85, rop, y, config=conf)
+            else:
+                xs, x0s = ddnm_plus_diffusion(x_T, m, betas, 0.85, rop, y, sy, config=conf)
+        with torch.no_grad():
+            ox, ox0 = S.ddnm_sample(x_T, lambda a, b: U.forward(sd, a, b, cfg), betas, 0.85, oop, y, tape,
+                                    t_sampling=T, travel_length=tl, travel_repeat=tr, sigma_y=sy)
+        d = close(ox, xs[0], 5e-4, f"sampler {name}")
+        close(ox0, x0s[0], 5e-4, f"sampler {name} x0")
+        key = f"{name}_T{T}_l{tl}_r{tr}_s{sy}"
+        out[key + "_y"], out[key + "_x0"], out[key + "_x0pred"] = y.numpy(), xs[0].numpy(), x0s[0].numpy()
+        print(f"sampler {key}: ok (oracle-ref {d:.2e}), npairs {npairs}")
+    out["noise_seed"] = np.array([555])
+    np.savez_compressed(os.path.join(GOLD, "sampler_tiny.npz"), **out)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    which = sys.argv[1:] or ["unet", "ops", "sampler"]
+    if "unet" in which:
+        unet_fixtures()
+    if "ops" in which:
+        operator_fixtures()
+    if "sampler" in which:
+        sampler_fixtures()
+    print("golden fixtures written to", GOLD)
