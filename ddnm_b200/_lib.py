@@ -1,0 +1,94 @@
+"""ctypes binding of libddnm_b200.so (include/ddnm_b200.h).  There is NO fallback: if the CUDA library is
+missing or fails to load, importing the product path raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libddnm_b200.so")
+
+
+class DDNMError(RuntimeError):
+    pass
+
+
+class SimpleCfg(C.Structure):
+    _fields_ = [("ch", C.c_int), ("out_ch", C.c_int), ("n_levels", C.c_int), ("ch_mult", C.c_int * 8),
+                ("num_res_blocks", C.c_int), ("n_attn_res", C.c_int), ("attn_res", C.c_int * 4),
+                ("in_channels", C.c_int), ("resolution", C.c_int), ("groups", C.c_int), ("eps", C.c_float)]
+
+
+class OperatorDesc(C.Structure):
+    _fields_ = [("kind", C.c_int), ("channels", C.c_int), ("img_dim", C.c_int), ("ratio", C.c_int),
+                ("v_small", C.c_void_p), ("u_small", C.c_void_p), ("singulars", C.c_void_p),
+                ("singulars_orig", C.c_void_p), ("perm", C.c_void_p), ("mask", C.c_void_p)]
+
+
+class Schedule(C.Structure):
+    _fields_ = [("n_pairs", C.c_int), ("t_i", C.c_void_p), ("t_j", C.c_void_p), ("abar", C.c_void_p),
+                ("num_timesteps", C.c_int), ("eta", C.c_float), ("sigma_y", C.c_float)]
+
+
+_lib = None
+
+_P, _I, _LL, _F, _D = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+_SIGS = {
+    "ddnm_version": (C.c_int, []),
+    "ddnm_unet_simple_create": (C.c_int, [C.POINTER(SimpleCfg), _I, C.POINTER(_P)]),
+    "ddnm_unet_set_param": (C.c_int, [_P, C.c_char_p, _P, _LL]),
+    "ddnm_unet_finalize": (C.c_int, [_P]),
+    "ddnm_unet_forward": (C.c_int, [_P, _P, _P, _P, _P]),
+    "ddnm_unet_set_graph": (C.c_int, [_P, _I]),
+    "ddnm_unet_read_tap": (C.c_int, [_P, C.c_char_p, _P, _LL, _P]),
+    "ddnm_unet_info": (C.c_int, [_P, C.POINTER(_LL), C.POINTER(_I), C.POINTER(_D)]),
+    "ddnm_unet_profile": (C.c_int, [_P, _P, _P, _P, _P, C.c_char_p, _LL]),
+    "ddnm_unet_destroy": (C.c_int, [_P]),
+    "ddnm_operator_create": (C.c_int, [C.POINTER(OperatorDesc), C.POINTER(_P)]),
+    "ddnm_operator_y_dim": (_LL, [_P]),
+    "ddnm_operator_A": (C.c_int, [_P, _P, _I, _P, _P]),
+    "ddnm_operator_A_pinv": (C.c_int, [_P, _P, _I, _P, _P]),
+    "ddnm_operator_project": (C.c_int, [_P, _P, _P, _I, _P, _P]),
+    "ddnm_operator_lambda": (C.c_int, [_P, _P, _I, _F, _F, _F, _F, _P, _P]),
+    "ddnm_operator_lambda_noise": (C.c_int, [_P, _P, _P, _I, _F, _F, _F, _F, _P, _P]),
+    "ddnm_operator_destroy": (C.c_int, [_P]),
+    "ddnm_sample": (C.c_int, [_P, _P, C.POINTER(Schedule), _P, _P, _P, _I, _P, _P, _P]),
+    "ddnm_conv_tc": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P]),
+    "ddnm_conv_direct": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
+    "ddnm_conv_tc_bench": (C.c_int, [_I, _I, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_D)]),
+    "ddnm_groupnorm": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P]),
+    "ddnm_tc_debug_override": (C.c_int, [C.c_uint, C.c_uint]),
+}
+EXPORTS = ["ddnm_last_error"] + list(_SIGS)
+
+
+def lib():
+    """Load the library once; raise DDNMError if it is absent (no CPU / eager fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DDNMError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` first")
+        L = C.CDLL(LIB_PATH)
+        L.ddnm_last_error.restype = C.c_char_p
+        L.ddnm_last_error.argtypes = []
+        missing = [n for n in _SIGS if not hasattr(L, n)]
+        if missing:
+            raise DDNMError(f"{LIB_PATH} lacks symbols {missing}: stale build?")
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DDNMError(lib().ddnm_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Raw data pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def cur_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

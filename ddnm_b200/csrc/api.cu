@@ -1,0 +1,219 @@
+// C ABI (include/ddnm_b200.h): denoiser handle + op-level entry points.  Operators and the sampler loop
+// are exported from operators.cu / sampler.cu.
+#include "../../include/ddnm_b200.h"
+
+#include <cstring>
+#include <vector>
+
+#include "api_util.cuh"
+#include "engine.cuh"
+#include "kernels.cuh"
+#include "tc_gemm.cuh"
+
+using namespace ddnm;
+
+namespace ddnm {
+thread_local std::string g_last_error;
+}
+
+extern "C" {
+
+const char* ddnm_last_error(void) { return g_last_error.c_str(); }
+int ddnm_version(void) { return 100; }
+
+int ddnm_unet_simple_create(const ddnm_simple_cfg* c, int batch, void** handle) {
+  DDNM_API_BEGIN
+  DDNM_CHECK(c && handle, "null argument");
+  SimpleCfg cfg;
+  cfg.ch = c->ch; cfg.out_ch = c->out_ch; cfg.n_levels = c->n_levels;
+  DDNM_CHECK(c->n_levels >= 1 && c->n_levels <= 8 && c->n_attn_res >= 0 && c->n_attn_res <= 4, "bad config");
+  for (int i = 0; i < 8; ++i) cfg.ch_mult[i] = c->ch_mult[i];
+  cfg.num_res_blocks = c->num_res_blocks;
+  cfg.n_attn_res = c->n_attn_res;
+  for (int i = 0; i < 4; ++i) cfg.attn_res[i] = c->attn_res[i];
+  cfg.in_channels = c->in_channels; cfg.resolution = c->resolution; cfg.groups = c->groups; cfg.eps = c->eps;
+  *handle = new UNetSimple(cfg, batch);
+  DDNM_API_END
+}
+
+int ddnm_unet_set_param(void* h, const char* name, const float* data, long long numel) {
+  DDNM_API_BEGIN
+  static_cast<UNetSimple*>(h)->set_param(name, data, numel);
+  DDNM_API_END
+}
+int ddnm_unet_finalize(void* h) {
+  DDNM_API_BEGIN
+  static_cast<UNetSimple*>(h)->finalize();
+  DDNM_API_END
+}
+int ddnm_unet_forward(void* h, const float* x, const float* t, float* out, void* stream) {
+  DDNM_API_BEGIN
+  static_cast<UNetSimple*>(h)->forward(x, t, out, (cudaStream_t)stream);
+  DDNM_API_END
+}
+int ddnm_unet_set_graph(void* h, int on) {
+  DDNM_API_BEGIN
+  static_cast<UNetSimple*>(h)->set_use_graph(on != 0);
+  DDNM_API_END
+}
+int ddnm_unet_read_tap(void* h, const char* name, float* dst, long long cap, void* stream) {
+  DDNM_API_BEGIN
+  DDNM_CHECK(static_cast<UNetSimple*>(h)->read_tap(name, dst, cap, (cudaStream_t)stream), std::string("unknown tap ") + name);
+  DDNM_API_END
+}
+int ddnm_unet_info(void* h, long long* ws, int* launches, double* flops) {
+  DDNM_API_BEGIN
+  UNetSimple* u = static_cast<UNetSimple*>(h);
+  if (ws) *ws = (long long)u->workspace_bytes();
+  if (launches) *launches = u->num_launches();
+  if (flops) *flops = u->flops_per_forward();
+  DDNM_API_END
+}
+int ddnm_unet_profile(void* h, const float* x, const float* t, float* out, void* stream, char* json, long long cap) {
+  DDNM_API_BEGIN
+  std::string s = static_cast<UNetSimple*>(h)->profile(x, t, out, (cudaStream_t)stream);
+  DDNM_CHECK((long long)s.size() + 1 <= cap, "json buffer too small");
+  std::memcpy(json, s.c_str(), s.size() + 1);
+  DDNM_API_END
+}
+int ddnm_unet_destroy(void* h) {
+  DDNM_API_BEGIN
+  delete static_cast<UNetSimple*>(h);
+  DDNM_API_END
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// op-level entry points
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+struct Tmp {
+  std::vector<void*> ptrs;
+  ~Tmp() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  template <class T>
+  T* get(size_t n) {
+    void* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    ptrs.push_back(p);
+    return (T*)p;
+  }
+};
+int sm_count() {
+  int dev = 0, n = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  return n;
+}
+View mkview(float* p, int N, int H, int W, int C) {
+  View v;
+  v.p = p; v.N = N; v.H = H; v.W = W; v.C = C; v.ld = C;
+  return v;
+}
+}  // namespace
+
+extern "C" {
+
+int ddnm_conv_tc(const float* x, int N, int H, int W, int Cin, const float* w, const float* bias, int Cout, int mode, int up2,
+                 const float* side_x, int CinSide, const float* side_w, const float* residual, float* out, void* stream) {
+  DDNM_API_BEGIN
+  cudaStream_t s = (cudaStream_t)stream;
+  Tmp tmp;
+  const int taps = mode == TAPS_1X1 ? 1 : 9;
+  int oH = H, oW = W;
+  int smode = SPLIT_SAME;
+  if (mode == TAPS_3X3_S2) { oH = H / 2; oW = W / 2; smode = SPLIT_S2D; DDNM_CHECK(!up2, "stride 2 with upsample"); }
+  if (up2) { oH = 2 * H; oW = 2 * W; smode = SPLIT_UP2; }
+  const size_t pe = (size_t)N * H * W * Cin * (up2 ? 4 : 1);
+  SplitView A;
+  A.hi = tmp.get<__half>(pe); A.lo = tmp.get<__half>(pe); A.C = Cin;
+  if (smode == SPLIT_S2D) { A.N = 4 * N; A.H = oH; A.W = oW; } else { A.N = N; A.H = oH; A.W = oW; }
+  View xv = mkview(const_cast<float*>(x), N, H, W, Cin);
+  gn_apply_split(xv, 1, nullptr, nullptr, nullptr, 0.f, false, smode, A.hi, A.lo, s);
+  SplitView S;
+  if (side_x) {
+    const size_t se = (size_t)N * oH * oW * CinSide;
+    S.hi = tmp.get<__half>(se); S.lo = tmp.get<__half>(se); S.N = N; S.H = oH; S.W = oW; S.C = CinSide;
+    gn_apply_split(mkview(const_cast<float*>(side_x), N, oH, oW, CinSide), 1, nullptr, nullptr, nullptr, 0.f, false, SPLIT_SAME,
+                   S.hi, S.lo, s);
+  }
+  const int ktot = taps * Cin + (side_x ? CinSide : 0);
+  __half* wh = tmp.get<__half>((size_t)Cout * ktot);
+  __half* wl = tmp.get<__half>((size_t)Cout * ktot);
+  split_conv_weight(w, Cout, Cin, taps, wh, wl, ktot, 0, s);
+  if (side_x) split_conv_weight(side_w, Cout, CinSide, 1, wh, wl, ktot, taps * Cin, s);
+  View ov = mkview(out, N, oH, oW, Cout);
+  TcLaunch L = tc_make_launch(A, mode, side_x ? &S : nullptr, wh, wl, 1, Cout, ov, bias, 0, residual, Cout, 1.0f, sm_count());
+  tc_run(L, s);
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  DDNM_API_END
+}
+
+int ddnm_conv_direct(const float* x, int N, int H, int W, int Cin, const float* w, const float* bias, int Cout, int mode, int up2,
+                     float* out, void* stream) {
+  DDNM_API_BEGIN
+  int oH = H, oW = W;
+  if (mode == TAPS_3X3_S2) { oH = H / 2; oW = W / 2; }
+  if (up2) { oH = 2 * H; oW = 2 * W; }
+  conv_direct_ref(mkview(const_cast<float*>(x), N, H, W, Cin), w, bias, mode, up2 != 0, mkview(out, N, oH, oW, Cout),
+                  (cudaStream_t)stream);
+  DDNM_API_END
+}
+
+int ddnm_conv_tc_bench(int N, int H, int W, int Cin, int Cout, int mode, int iters, float* ms_per_iter, double* flops) {
+  DDNM_API_BEGIN
+  Tmp tmp;
+  const int taps = mode == TAPS_1X1 ? 1 : 9;
+  const size_t pe = (size_t)N * H * W * Cin;
+  SplitView A;
+  A.hi = tmp.get<__half>(pe); A.lo = tmp.get<__half>(pe); A.N = N; A.H = H; A.W = W; A.C = Cin;
+  float* xf = tmp.get<float>(pe);
+  CUDA_CHECK(cudaMemset(xf, 0, pe * 4));
+  gn_apply_split(mkview(xf, N, H, W, Cin), 1, nullptr, nullptr, nullptr, 0.f, false, SPLIT_SAME, A.hi, A.lo, 0);
+  const int ktot = taps * Cin;
+  __half* wh = tmp.get<__half>((size_t)Cout * ktot);
+  __half* wl = tmp.get<__half>((size_t)Cout * ktot);
+  CUDA_CHECK(cudaMemset(wh, 0, (size_t)Cout * ktot * 2));
+  CUDA_CHECK(cudaMemset(wl, 0, (size_t)Cout * ktot * 2));
+  float* o = tmp.get<float>((size_t)N * H * W * Cout);
+  TcLaunch L = tc_make_launch(A, mode, nullptr, wh, wl, 1, Cout, mkview(o, N, H, W, Cout), nullptr, 0, nullptr, 0, 1.0f, sm_count());
+  for (int i = 0; i < 3; ++i) tc_run(L, 0);
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, 0));
+  for (int i = 0; i < iters; ++i) tc_run(L, 0);
+  CUDA_CHECK(cudaEventRecord(e1, 0));
+  CUDA_CHECK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_iter = ms / iters;
+  *flops = L.flops;
+  DDNM_API_END
+}
+
+int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const float* gamma, const float* beta, float eps,
+                   int silu, float* out, void* stream) {
+  DDNM_API_BEGIN
+  cudaStream_t s = (cudaStream_t)stream;
+  Tmp tmp;
+  double* st = tmp.get<double>((size_t)N * groups * 2);
+  CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)N * groups * 2 * sizeof(double), s));
+  View xv = mkview(const_cast<float*>(x), N, H, W, C);
+  gn_stats(xv, groups, st, s);
+  gn_apply_f32(xv, groups, st, gamma, beta, eps, silu != 0, out, s);
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  DDNM_API_END
+}
+
+int ddnm_tc_debug_override(unsigned desc_hi, unsigned idesc_xor) {
+  DDNM_API_BEGIN
+  tc_debug_override(desc_hi, idesc_xor);
+  DDNM_API_END
+}
+
+}  // extern "C"

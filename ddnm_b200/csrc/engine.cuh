@@ -1,0 +1,109 @@
+// The denoiser engine: a static launch program for the "simple" DDPM UNet (guided_diffusion/models.py Model),
+// built once per (config, batch) and replayed as a CUDA graph.
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace ddnm {
+
+struct SimpleCfg {
+  int ch = 128, out_ch = 3, n_levels = 6;
+  int ch_mult[8] = {1, 1, 2, 2, 4, 4, 0, 0};
+  int num_res_blocks = 2;
+  int n_attn_res = 1;
+  int attn_res[4] = {16, 0, 0, 0};
+  int in_channels = 3, resolution = 256, groups = 32;
+  float eps = 1e-6f;
+};
+
+class Arena {
+ public:
+  ~Arena();
+  void* alloc(size_t bytes);
+  size_t used() const { return total_; }
+
+ private:
+  std::vector<void*> blocks_;
+  size_t total_ = 0;
+};
+
+struct OpRecord {
+  std::string name;
+  std::string kind;   // "tc", "gn_stats", "gn_apply", ...
+  double flops = 0;   // algorithmic
+  double bytes = 0;   // algorithmic HBM bytes (in + out)
+  std::function<void(cudaStream_t)> run;
+};
+
+class UNetSimple {
+ public:
+  UNetSimple(const SimpleCfg& cfg, int batch);
+  ~UNetSimple();
+  void set_param(const std::string& name, const float* data, long long numel);
+  void finalize();
+  // x: [B,3,R,R] NCHW fp32, t: [B] fp32 (device), out: [B,out_ch,R,R] NCHW fp32 (device)
+  void forward(const float* x, const float* t, float* out, cudaStream_t stream);
+  // tests: copy an internal activation (by oracle tap name) as NCHW fp32
+  bool read_tap(const std::string& name, float* dst_nchw, long long capacity, cudaStream_t stream);
+  // per-op timing of one eager (non-graph) forward; returns JSON
+  std::string profile(const float* x, const float* t, float* out, cudaStream_t stream);
+  int batch() const { return B_; }
+  const SimpleCfg& cfg() const { return cfg_; }
+  void set_use_graph(bool on) { use_graph_ = on; }
+  size_t workspace_bytes() const { return arena_.used(); }
+  int num_launches() const { return (int)ops_.size(); }
+  double flops_per_forward() const;
+
+ private:
+  struct Param { float* p; long long n; };
+  const float* P(const std::string& name, long long expect = -1) const;
+  View new_view(int H, int W, int C);
+  double* new_stats();
+  struct TcWeights { __half *hi, *lo; int ktot; };
+  TcWeights prep_weights(const std::string& main, int Cout, int Cin, int taps, const std::string& side, int CinSide);
+  TcWeights prep_qkv(const std::string& p, int C);
+  const float* bias_sum(const std::string& a, const std::string& b, int C);
+
+  void add_op(const std::string& name, const std::string& kind, double flops, double bytes, std::function<void(cudaStream_t)> f);
+  void emit_gn_split(const std::string& name, const View& x, const std::string& norm, bool silu, int mode, SplitView& dst);
+  void emit_tc(const std::string& name, const SplitView& a, int mode, const SplitView* side, const TcWeights& w, int Cout,
+               const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr);
+  void emit_resblock(const std::string& p, const View& x, const View& out);
+  void emit_attn(const std::string& p, const View& x, const View& out);
+  void emit_downsample(const std::string& p, const View& x, const View& out);
+  void emit_upsample(const std::string& p, const View& x, const View& out);
+  void build_program();
+  void run_ops(cudaStream_t s);
+
+  SimpleCfg cfg_;
+  int B_, num_sms_ = 148;
+  bool finalized_ = false, use_graph_ = true;
+  Arena arena_;
+  std::map<std::string, Param> params_;
+  std::vector<OpRecord> ops_;
+  std::map<std::string, View> taps_;
+  // fixed I/O staging (graph replays need stable addresses)
+  float *x_in_ = nullptr, *t_in_ = nullptr, *out_ = nullptr;
+  // scratch
+  __half *splitA_hi_ = nullptr, *splitA_lo_ = nullptr, *splitB_hi_ = nullptr, *splitB_lo_ = nullptr;
+  size_t split_elems_ = 0;
+  float* hbuf_ = nullptr;      // resblock intermediate
+  size_t hbuf_elems_ = 0;
+  float *qkv_ = nullptr, *attS_ = nullptr, *attO_ = nullptr, *headact_ = nullptr;
+  double* stats_base_ = nullptr;
+  size_t stats_count_ = 0, stats_cap_ = 0;
+  float *emb_ = nullptr, *temb0_ = nullptr, *temb_ = nullptr, *ca_all_ = nullptr, *freq_ = nullptr;
+  int ca_total_ = 0;
+  std::map<std::string, int> ca_off_;
+  float *tembW_all_ = nullptr, *tembB_all_ = nullptr;
+  cudaGraph_t graph_ = nullptr;
+  cudaGraphExec_t graph_exec_ = nullptr;
+};
+
+}  // namespace ddnm

@@ -1,0 +1,572 @@
+// SIMT kernels (see kernels.cuh).  Reference semantics cited per kernel.
+#include "kernels.cuh"
+#include "tc_gemm.cuh"
+
+namespace ddnm {
+
+static constexpr int MAX_C = 2048;  // widest concat in either UNet
+
+__device__ __forceinline__ float swishf(float x) { return x / (1.0f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm statistics (torch.nn.GroupNorm(32, C): models.py:32-33 / nn.py:17-19).  One CTA = one image x one
+// pixel chunk; every thread owns 4 fixed channels (float4 loads along the contiguous NHWC channel axis), partial
+// sums meet in shared memory per channel, then per group, then one double atomicAdd pair per (CTA, group).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int ld, int groups, int pix_per_cta,
+                                double* __restrict__ stats) {
+  __shared__ float csum[MAX_C], csq[MAX_C];
+  const int n = blockIdx.y;
+  const int C4 = C >> 2;
+  const int rows = blockDim.x / C4;
+  const int c4 = threadIdx.x % C4;
+  const int prow = threadIdx.x / C4;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    csum[i] = 0.f;
+    csq[i] = 0.f;
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (prow < rows) {
+    const float* base = x + (long long)n * HW * ld + c4 * 4;
+    for (int p = p0 + prow; p < p1; p += rows) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + (long long)p * ld));
+      s[0] += v.x; q[0] += v.x * v.x;
+      s[1] += v.y; q[1] += v.y * v.y;
+      s[2] += v.z; q[2] += v.z * v.z;
+      s[3] += v.w; q[3] += v.w * v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&csum[c4 * 4 + j], s[j]);
+      atomicAdd(&csq[c4 * 4 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double a = 0, b = 0;
+    for (int j = 0; j < cpg; ++j) {
+      a += (double)csum[g * cpg + j];
+      b += (double)csq[g * cpg + j];
+    }
+    atomicAdd(&stats[((long long)n * groups + g) * 2 + 0], a);
+    atomicAdd(&stats[((long long)n * groups + g) * 2 + 1], b);
+  }
+}
+
+void gn_stats(const View& x, int groups, double* stats, cudaStream_t st) {
+  DDNM_CHECK(x.C % 4 == 0 && x.C <= MAX_C && x.C % groups == 0 && x.ld % 4 == 0, "gn_stats: unsupported channel count");
+  const int C4 = x.C / 4;
+  const int rows = std::max(1, 256 / C4);
+  const int threads = C4 * rows;
+  const int HW = x.H * x.W;
+  long long want = cdivll((long long)HW * x.N, 592);
+  int ppc = (int)std::max<long long>(rows * 4, cdivll(want, rows) * rows);
+  dim3 grid(cdiv(HW, ppc), x.N);
+  gn_stats_kernel<<<grid, threads, 0, st>>>(x.p, HW, x.C, x.ld, groups, ppc, stats);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Normalise (+ SiLU) and split to fp16 hi/lo.  Produces the A operand of the tensor-core convolution, i.e. fuses
+//   h = nonlinearity(norm(x))            models.py:117-118,124-125   (x * sigmoid(x), GN eps 1e-6)
+//   F.interpolate(x, 2, 'nearest')       models.py:48-49   (SPLIT_UP2)
+//   F.pad(x, (0,1,0,1)) + stride 2       models.py:67-71   (SPLIT_S2D: parity phases; pad = TMA zero fill)
+// Each thread converts 8 channels of one pixel: 2 x float4 in, 16 B out per plane.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool F32OUT>
+__global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C, int ld, int N, int groups,
+                                const double* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int silu, int mode, int pix_per_cta,
+                                __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ out32) {
+  __shared__ float sc[MAX_C], sh[MAX_C];
+  const int n = blockIdx.y;
+  const int HW = H * W;
+  if (stats) {
+    const int cpg = C / groups;
+    const double cnt = (double)HW * cpg;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / cpg;
+      const double mean = stats[((long long)n * groups + g) * 2] / cnt;
+      double var = stats[((long long)n * groups + g) * 2 + 1] / cnt - mean * mean;
+      var = var < 0 ? 0 : var;
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float a = rstd * gamma[c];
+      sc[c] = a;
+      sh[c] = beta[c] - (float)mean * a;
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      sc[c] = 1.f;
+      sh[c] = 0.f;
+    }
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  const long long total = (long long)(p1 - p0) * C8;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    const int p = p0 + (int)(i / C8);
+    const int c = (int)(i % C8) * 8;
+    const float* src = x + ((long long)n * HW + p) * ld + c;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = v[j] * sc[c + j] + sh[c + j];
+      if (silu) v[j] = swishf(v[j]);
+    }
+    if (F32OUT) {
+      float* d = out32 + ((long long)n * HW + p) * C + c;
+      *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      __align__(16) __half h8[8];
+      __align__(16) __half l8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_f16(v[j], h8[j], l8[j]);
+      const uint4 hv = *reinterpret_cast<const uint4*>(h8);
+      const uint4 lv = *reinterpret_cast<const uint4*>(l8);
+      const int y = p / W, xx = p % W;
+      if (mode == SPLIT_SAME) {
+        const long long o = ((long long)n * HW + p) * C + c;
+        *reinterpret_cast<uint4*>(hi + o) = hv;
+        *reinterpret_cast<uint4*>(lo + o) = lv;
+      } else if (mode == SPLIT_UP2) {
+        const int W2 = 2 * W;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const long long o = (((long long)n * 2 * H + (2 * y + (d >> 1))) * W2 + (2 * xx + (d & 1))) * C + c;
+          *reinterpret_cast<uint4*>(hi + o) = hv;
+          *reinterpret_cast<uint4*>(lo + o) = lv;
+        }
+      } else {  // SPLIT_S2D
+        const int ph = (y & 1) * 2 + (xx & 1);
+        const int Hh = H >> 1, Wh = W >> 1;
+        const long long o = ((((long long)ph * N + n) * Hh + (y >> 1)) * Wh + (xx >> 1)) * C + c;
+        *reinterpret_cast<uint4*>(hi + o) = hv;
+        *reinterpret_cast<uint4*>(lo + o) = lv;
+      }
+    }
+  }
+}
+
+static void gn_apply_launch(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
+                            bool silu, int mode, __half* hi, __half* lo, float* out32, cudaStream_t st) {
+  DDNM_CHECK(x.C % 8 == 0 && x.C <= MAX_C && x.ld % 4 == 0, "gn_apply: unsupported channel count");
+  if (mode == SPLIT_S2D) DDNM_CHECK(x.H % 2 == 0 && x.W % 2 == 0, "space-to-depth needs even dims");
+  const int HW = x.H * x.W;
+  long long want = cdivll((long long)HW * x.N, 148 * 8);
+  int ppc = (int)std::max<long long>(8, want);
+  dim3 grid(cdiv(HW, ppc), x.N);
+  if (out32)
+    gn_apply_kernel<true><<<grid, 256, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, gamma, beta, eps, silu, mode,
+                                                 ppc, nullptr, nullptr, out32);
+  else
+    gn_apply_kernel<false><<<grid, 256, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, gamma, beta, eps, silu, mode,
+                                                  ppc, hi, lo, nullptr);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void gn_apply_split(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
+                    bool silu, int mode, __half* hi, __half* lo, cudaStream_t s) {
+  gn_apply_launch(x, groups, stats, gamma, beta, eps, silu, mode, hi, lo, nullptr, s);
+}
+void gn_apply_f32(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
+                  bool silu, float* out, cudaStream_t s) {
+  gn_apply_launch(x, groups, stats, gamma, beta, eps, silu, SPLIT_SAME, nullptr, nullptr, out, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stem: conv_in = Conv2d(3, ch, 3, padding=1) (models.py:228-232, 311) on the caller's NCHW tensor, NHWC result.
+// Lane <-> 4 output channels (weights live in registers), warp walks over pixels; output rows are written as
+// full 512-byte segments.  blockIdx.z selects a 128-channel slab of Cout.
+// ---------------------------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(256) conv_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ out,
+                                                             int H, int W, int Cout, int ld) {
+  constexpr int KT = CIN * 9;
+  constexpr int TW = 64;  // pixels per CTA (one row segment)
+  __shared__ float tile[CIN][3][TW + 2];
+  const int n = blockIdx.z / ((Cout + 127) / 128);
+  const int slab = blockIdx.z % ((Cout + 127) / 128);
+  const int y = blockIdx.y;
+  const int x0 = blockIdx.x * TW;
+  for (int i = threadIdx.x; i < CIN * 3 * (TW + 2); i += blockDim.x) {
+    const int xx = i % (TW + 2), r = (i / (TW + 2)) % 3, c = i / (3 * (TW + 2));
+    const int gy = y + r - 1, gx = x0 + xx - 1;
+    tile[c][r][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[(((long long)n * CIN + c) * H + gy) * W + gx] : 0.f;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int co = slab * 128 + lane * 4;
+  const bool active = co < Cout;
+  float wr[KT][4];
+  float b4[4] = {0, 0, 0, 0};
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wr[k][j] = w[(long long)(co + j) * KT + k];  // OIHW: k = ci*9 + ky*3 + kx
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b4[j] = bias[co + j];
+  }
+  __syncthreads();
+  if (!active) return;
+  for (int px = warp; px < TW && x0 + px < W; px += 8) {
+    float acc[4] = {b4[0], b4[1], b4[2], b4[3]};
+#pragma unroll
+    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float v = tile[c][r][px + d];
+          const int k = c * 9 + r * 3 + d;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fmaf(v, wr[k][j], acc[j]);
+        }
+    float* o = out + (((long long)n * H + y) * W + x0 + px) * ld + co;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
+void conv3x3_small_cin(const float* x, int Cin, const float* w, const float* bias, const View& out, cudaStream_t st) {
+  DDNM_CHECK(Cin == 3, "stem convolution expects 3 input channels");
+  DDNM_CHECK(out.C % 4 == 0, "stem Cout % 4");
+  dim3 grid(cdiv(out.W, 64), out.H, out.N * cdiv(out.C, 128));
+  conv_small_cin_kernel<3><<<grid, 256, 0, st>>>(x, w, bias, out.p, out.H, out.W, out.C, out.ld);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Head: conv_out = Conv2d(ch, out_ch, 3, padding=1) (models.py:294-299, 340) on the activated NHWC tensor, NCHW
+// result.  Warp <-> strip of 8 output pixels in a row, lane <-> channel slices of 4; each loaded input vector is
+// reused by the 3 horizontal taps; weights sit in shared memory as [tap][co][ci].
+// ---------------------------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256) conv_small_cout_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ out,
+                                                              int N, int H, int W, int Cin) {
+  extern __shared__ float ws[];  // [9][COUT][Cin]
+  for (int i = threadIdx.x; i < 9 * COUT * Cin; i += blockDim.x) {
+    const int ci = i % Cin, co = (i / Cin) % COUT, tap = i / (Cin * COUT);
+    ws[i] = w[((long long)co * Cin + ci) * 9 + tap];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int strips_per_row = W / 8;
+  const long long strip = (long long)blockIdx.x * 8 + warp;
+  if (strip >= (long long)N * H * strips_per_row) return;
+  const int sx = (int)(strip % strips_per_row) * 8;
+  const int y = (int)((strip / strips_per_row) % H);
+  const int n = (int)(strip / ((long long)strips_per_row * H));
+  float acc[8][COUT];
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[p][c] = 0.f;
+  for (int cb = lane * 4; cb < Cin; cb += 128) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int gy = y + r - 1;
+      if (gy < 0 || gy >= H) continue;
+      float4 wv[3][COUT];
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) wv[d][c] = *reinterpret_cast<const float4*>(&ws[((r * 3 + d) * COUT + c) * Cin + cb]);
+      const float* rowp = x + (((long long)n * H + gy) * W) * Cin + cb;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {  // input columns sx-1 .. sx+8
+        const int gx = sx + i - 1;
+        if (gx < 0 || gx >= W) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(rowp + (long long)gx * Cin));
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int p = i - d;  // output pixel that sees this column through horizontal tap d
+          if (p < 0 || p > 7) continue;
+#pragma unroll
+          for (int c = 0; c < COUT; ++c)
+            acc[p][c] += v.x * wv[d][c].x + v.y * wv[d][c].y + v.z * wv[d][c].z + v.w * wv[d][c].w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+      float v = acc[p][c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[p][c] = v;
+    }
+  if (lane < 8) {
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+      float v = 0.f;
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+        if (p == lane) v = acc[p][c];
+      out[(((long long)n * COUT + c) * H + y) * W + sx + lane] = v + bias[c];
+    }
+  }
+}
+
+void conv3x3_small_cout(const float* x, int N, int H, int W, int Cin, const float* w, const float* bias, int Cout, float* out,
+                        cudaStream_t st) {
+  DDNM_CHECK(W % 8 == 0 && Cin % 4 == 0, "head convolution: W % 8, Cin % 4");
+  const long long strips = (long long)N * H * (W / 8);
+  const int grid = (int)cdivll(strips, 8);
+  const size_t smem = (size_t)9 * Cout * Cin * sizeof(float);
+  static size_t smem_set[2] = {0, 0};
+  if (Cout == 3) {
+    if (smem > smem_set[0]) {
+      CUDA_CHECK(cudaFuncSetAttribute(conv_small_cout_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set[0] = smem;
+    }
+    conv_small_cout_kernel<3><<<grid, 256, smem, st>>>(x, w, bias, out, N, H, W, Cin);
+  } else if (Cout == 6) {
+    if (smem > smem_set[1]) {
+      CUDA_CHECK(cudaFuncSetAttribute(conv_small_cout_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set[1] = smem;
+    }
+    conv_small_cout_kernel<6><<<grid, 256, smem, st>>>(x, w, bias, out, N, H, W, Cin);
+  } else {
+    throw Error("head convolution supports Cout 3 or 6");
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Timestep MLP pieces (models.py:6-24, 305-308, 121).  One warp per output element.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void linear_kernel(const float* __restrict__ in, int N, int K, const float* __restrict__ W,
+                              const float* __restrict__ bias, int O, float* __restrict__ out, int ldo, int act_in, int act_out) {
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= (long long)N * O) return;
+  const int n = (int)(gw / O), o = (int)(gw % O);
+  const float* a = in + (long long)n * K;
+  const float* w = W + (long long)o * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float v = a[k];
+    if (act_in) v = swishf(v);
+    acc = fmaf(v, w[k], acc);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    float r = acc + (bias ? bias[o] : 0.f);
+    if (act_out) r = swishf(r);
+    out[(long long)n * ldo + o] = r;
+  }
+}
+void linear(const float* in, int N, int K, const float* W, const float* bias, int O, float* out, int ldo, int act_in,
+            int act_out, cudaStream_t st) {
+  const long long warps = (long long)N * O;
+  linear_kernel<<<(int)cdivll(warps * 32, 256), 256, 0, st>>>(in, N, K, W, bias, O, out, ldo, act_in, act_out);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void sinusoid_kernel(const float* __restrict__ t, int N, const float* __restrict__ freq, int dim, int sin_first,
+                                float* __restrict__ emb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= N * half) return;
+  const int n = i / half, k = i % half;
+  const float a = t[n] * freq[k];
+  const float s = sinf(a), c = cosf(a);
+  emb[(long long)n * dim + k] = sin_first ? s : c;
+  emb[(long long)n * dim + half + k] = sin_first ? c : s;
+}
+void sinusoid(const float* t, int N, const float* freq, int dim, bool sin_first, float* emb, cudaStream_t st) {
+  sinusoid_kernel<<<cdiv(N * (dim / 2), 128), 128, 0, st>>>(t, N, freq, dim, sin_first ? 1 : 0, emb);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Batched fp32 GEMM, 64x64x16 tiles, 4x4 per thread (torch.bmm in AttnBlock, models.py:177,185).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool BT>
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
+                                                    long long sa, const float* __restrict__ B, int ldb, long long sb,
+                                                    float* __restrict__ C, int ldc, long long sc) {
+  __shared__ float As[16][64 + 4], Bs[16][64 + 4];
+  const int b = blockIdx.z;
+  A += b * sa; B += b * sb; C += b * sc;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int kk = i % 16, mm = i / 16;
+      As[kk][mm] = (m0 + mm < M && k0 + kk < K) ? A[(long long)(m0 + mm) * lda + k0 + kk] : 0.f;
+    }
+    if (BT) {
+      for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+        const int kk = i % 16, nn = i / 16;
+        Bs[kk][nn] = (n0 + nn < N && k0 + kk < K) ? B[(long long)(n0 + nn) * ldb + k0 + kk] : 0.f;
+      }
+    } else {
+      for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+        const int nn = i % 64, kk = i / 64;
+        Bs[kk][nn] = (n0 + nn < N && k0 + kk < K) ? B[(long long)(k0 + kk) * ldb + n0 + nn] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < M && n < N) C[(long long)m * ldc + n] = alpha * acc[i][j];
+    }
+}
+void sgemm_batched(bool bt, int batches, int M, int N, int K, float alpha, const float* A, int lda, long long sa,
+                   const float* B, int ldb, long long sb, float* C, int ldc, long long sc, cudaStream_t st) {
+  dim3 grid(cdiv(N, 64), cdiv(M, 64), batches);
+  if (bt)
+    sgemm_kernel<true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sa, B, ldb, sb, C, ldc, sc);
+  else
+    sgemm_kernel<false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sa, B, ldb, sb, C, ldc, sc);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// softmax over the last dim, one warp per row (F.softmax(w_, dim=2), models.py:179)
+__global__ void softmax_kernel(float* __restrict__ x, long long rows, int cols) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* r = x + row * cols;
+  float m = -INFINITY;
+  for (int i = lane; i < cols; i += 32) m = fmaxf(m, r[i]);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  float sum = 0.f;
+  for (int i = lane; i < cols; i += 32) {
+    const float e = expf(r[i] - m);
+    r[i] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  const float inv = 1.0f / sum;
+  for (int i = lane; i < cols; i += 32) r[i] *= inv;
+}
+void softmax_rows(float* x, long long rows, int cols, cudaStream_t st) {
+  softmax_kernel<<<(int)cdivll(rows * 32, 256), 256, 0, st>>>(x, rows, cols);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight preparation (once per model load)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void split_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, __half* __restrict__ hi,
+                                    __half* __restrict__ lo, int ktot, int koff) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)Cout * Cin * taps;
+  if (i >= total) return;
+  const int ci = (int)(i % Cin);
+  const int tap = (int)((i / Cin) % taps);
+  const int co = (int)(i / ((long long)Cin * taps));
+  const float v = w[((long long)co * Cin + ci) * taps + tap];
+  __half h, l;
+  split_f16(v, h, l);
+  const long long o = (long long)co * ktot + koff + (long long)tap * Cin + ci;
+  hi[o] = h;
+  lo[o] = l;
+}
+void split_conv_weight(const float* w, int Cout, int Cin, int taps, __half* hi, __half* lo, int ktot, int koff, cudaStream_t st) {
+  const long long total = (long long)Cout * Cin * taps;
+  split_weight_kernel<<<(int)cdivll(total, 256), 256, 0, st>>>(w, Cout, Cin, taps, hi, lo, ktot, koff);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Direct convolution, one thread per output element (validation only).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void conv_direct_kernel(const float* __restrict__ x, int xH, int xW, int Cin, int xld, const float* __restrict__ w,
+                                   const float* __restrict__ bias, int mode, int up2, float* __restrict__ out, int N, int H,
+                                   int W, int Cout, int old) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * H * W * Cout;
+  if (i >= total) return;
+  const int co = (int)(i % Cout);
+  const long long pix = i / Cout;
+  const int ox = (int)(pix % W), oy = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+  const int taps = mode == TAPS_1X1 ? 1 : 9;
+  const int inH = up2 ? 2 * xH : xH, inW = up2 ? 2 * xW : xW;  // logical (post-upsample) input size
+  float acc = bias ? bias[co] : 0.f;
+  for (int tap = 0; tap < taps; ++tap) {
+    int iy, ix;
+    if (mode == TAPS_1X1) { iy = oy; ix = ox; }
+    else if (mode == TAPS_3X3) { iy = oy + tap / 3 - 1; ix = ox + tap % 3 - 1; }
+    else { iy = 2 * oy + tap / 3; ix = 2 * ox + tap % 3; }
+    if (iy < 0 || iy >= inH || ix < 0 || ix >= inW) continue;
+    if (up2) { iy >>= 1; ix >>= 1; }
+    const float* xp = x + (((long long)n * xH + iy) * xW + ix) * xld;
+    const float* wp = w + (long long)co * Cin * taps + tap;
+    for (int ci = 0; ci < Cin; ++ci) acc = fmaf(xp[ci], wp[(long long)ci * taps], acc);
+  }
+  out[pix * old + co] = acc;
+}
+void conv_direct_ref(const View& x, const float* w, const float* bias, int mode, bool up2, const View& out, cudaStream_t st) {
+  const long long total = out.pixels() * out.C;
+  conv_direct_kernel<<<(int)cdivll(total, 256), 256, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, w, bias, mode, up2 ? 1 : 0, out.p, out.N,
+                                                             out.H, out.W, out.C, out.ld);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ s, int N, int C, int H, int W, float* __restrict__ d, int ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * C * H * W;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const long long pix = i / C;
+  const long long hw = pix % ((long long)H * W);
+  const int n = (int)(pix / ((long long)H * W));
+  d[pix * ld + c] = s[((long long)n * C + c) * H * W + hw];
+}
+void nchw_to_nhwc(const float* src, int N, int C, int H, int W, const View& dst, cudaStream_t st) {
+  const long long total = (long long)N * C * H * W;
+  nchw_to_nhwc_kernel<<<(int)cdivll(total, 256), 256, 0, st>>>(src, N, C, H, W, dst.p, dst.ld);
+  CUDA_CHECK(cudaGetLastError());
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ s, int N, int C, int H, int W, int ld, float* __restrict__ d) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * C * H * W;
+  if (i >= total) return;
+  const long long hw = i % ((long long)H * W);
+  const int c = (int)((i / ((long long)H * W)) % C);
+  const int n = (int)(i / ((long long)H * W * C));
+  d[i] = s[((long long)n * H * W + hw) * ld + c];
+}
+void nhwc_to_nchw(const View& src, float* dst, cudaStream_t st) {
+  const long long total = src.pixels() * src.C;
+  nhwc_to_nchw_kernel<<<(int)cdivll(total, 256), 256, 0, st>>>(src.p, src.N, src.C, src.H, src.W, src.ld, dst);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace ddnm

@@ -1,0 +1,53 @@
+// SIMT (CUDA-core) kernels of the ddnm_b200 library: normalisation, fp16 splitting, small convolutions,
+// timestep MLP, attention helpers, weight preparation.  All are HBM- or latency-bound; the FLOP-heavy
+// contractions live in tc_gemm.cu.
+#pragma once
+#include "common.cuh"
+
+namespace ddnm {
+
+enum SplitMode : int { SPLIT_SAME = 0, SPLIT_UP2 = 1, SPLIT_S2D = 2 };
+
+// GroupNorm statistics: stats[(n*G + g)*2 + {0,1}] += {sum, sum of squares} (double).  Caller zeroes stats.
+void gn_stats(const View& x, int groups, double* stats, cudaStream_t s);
+
+// y = [GN affine](x) -> [SiLU] -> fp16 (hi, lo) planes.  stats == nullptr: no normalisation (raw split).
+// mode SPLIT_UP2 writes a nearest-neighbour 2x upsampled plane, SPLIT_S2D writes 4 parity phases
+// (plane index = phase*N + n, phase = (y&1)*2 + (x&1)) for the stride-2 convolution.
+void gn_apply_split(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
+                    bool silu, int mode, __half* hi, __half* lo, cudaStream_t s);
+// same normalisation, fp32 contiguous NHWC output (feeds the small-Cout output convolution)
+void gn_apply_f32(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
+                  bool silu, float* out, cudaStream_t s);
+
+// 3x3 pad-1 convolution with tiny Cin (the network stem): x NCHW [N,Cin,H,W] fp32, w OIHW, out NHWC view.
+void conv3x3_small_cin(const float* x_nchw, int Cin, const float* w_oihw, const float* bias, const View& out, cudaStream_t s);
+// 3x3 pad-1 convolution with tiny Cout (the network head): x NHWC contiguous fp32, out NCHW [N,Cout,H,W].
+void conv3x3_small_cout(const float* x_nhwc, int N, int H, int W, int Cin, const float* w_oihw, const float* bias, int Cout,
+                        float* out_nchw, cudaStream_t s);
+
+// out[n][o] = act_out( sum_k act_in(in[n][k]) * W[o][k] + bias[o] );  act: 0 none, 1 swish
+void linear(const float* in, int N, int K, const float* W, const float* bias, int O, float* out, int ldo, int act_in,
+            int act_out, cudaStream_t s);
+// emb[n][:] = [sin(t*f) | cos(t*f)] (sin_first) or [cos | sin]; f has dim/2 entries
+void sinusoid(const float* t, int N, const float* freq, int dim, bool sin_first, float* emb, cudaStream_t s);
+
+// batched fp32 GEMM on CUDA cores (attention at small token counts).
+//   NT: C[b][m][n] = alpha * sum_k A[b][m][k] * B[b][n][k];   NN: ... * B[b][k][n]
+void sgemm_batched(bool b_transposed, int batches, int M, int N, int K, float alpha, const float* A, int lda, long long sa,
+                   const float* B, int ldb, long long sb, float* C, int ldc, long long sc, cudaStream_t s);
+void softmax_rows(float* x, long long rows, int cols, cudaStream_t s);
+
+// OIHW fp32 conv weight -> K-major fp16 (hi, lo) rows: dst[co*ktot + koff + tap*Cin + ci]
+void split_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, __half* hi, __half* lo, int ktot, int koff,
+                       cudaStream_t s);
+
+// Reference-quality direct convolution on CUDA cores (tests / validation of the tensor-core path only).
+//   mode: TcTapMode; up2: input is nearest-upsampled 2x on the fly.  x, out: NHWC views; w: OIHW.
+void conv_direct_ref(const View& x, const float* w_oihw, const float* bias, int taps_mode, bool up2, const View& out,
+                     cudaStream_t s);
+
+void nchw_to_nhwc(const float* src, int N, int C, int H, int W, const View& dst, cudaStream_t s);
+void nhwc_to_nchw(const View& src, float* dst, cudaStream_t s);
+
+}  // namespace ddnm

@@ -1,0 +1,363 @@
+// tcgen05 implicit-GEMM convolution for sm_100a.
+//
+//   out[pixel, co] = alpha * sum_k A[pixel, k] * Wt[co, k] + chanadd[image, co] + residual[pixel, co]
+//
+// A is never materialised: for k-block (tap, 64-channel slice) the TMA engine copies the shifted NHWC window
+// [bn images x bh rows x bw cols] x 64 channels straight into 128B-swizzled shared memory; halo / padding pixels
+// come from TMA out-of-bounds zero fill (no im2col, no padded copy).  Products are "fp32-grade": every fp32
+// operand is pre-split into fp16 hi + lo and each k-slice issues hi*hi + hi*lo + lo*hi into one fp32 TMEM
+// accumulator (the dropped lo*lo term is ~2^-22 relative).
+//
+// Replaces, on the reference path, every torch.nn.Conv2d / 1x1 conv / bmm inside
+//   guided_diffusion/models.py:77-189 (ResnetBlock, AttnBlock), :36-74 (Up/Downsample)
+// which the reference dispatches to cuDNN / cuBLAS.
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 UMMA issuer (+TMEM owner), warps 2-5 epilogue (TMEM -> regs -> HBM).
+// Persistent over output tiles; two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "tc_gemm.cuh"
+
+namespace ddnm {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;                      // fp16 elements = 128 bytes = one swizzle row
+static constexpr int A_PLANE_BYTES = BM * BK * 2;  // 16 KiB
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int B_PLANE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant__ CUtensorMap tm_a0l,
+               const __grid_constant__ CUtensorMap tm_a1h, const __grid_constant__ CUtensorMap tm_a1l,
+               const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bl, const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int KB = p.kb0 + p.kb1;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a0h);
+    tma_prefetch_desc(&tm_a0l);
+    tma_prefetch_desc(&tm_bh);
+    tma_prefetch_desc(&tm_bl);
+    if (p.kb1) {
+      tma_prefetch_desc(&tm_a1h);
+      tma_prefetch_desc(&tm_a1l);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto decode = [&](int tile, int& n_idx, int& x0, int& y0, int& n0) {
+    n_idx = tile % p.n_tiles;
+    int m = tile / p.n_tiles;
+    int tx = m % p.tiles_x;
+    int t2 = m / p.tiles_x;
+    int ty = t2 % p.tiles_y;
+    int tn = t2 / p.tiles_y;
+    x0 = tx * p.bw;
+    y0 = ty * p.bh;
+    n0 = tn * p.bn;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n_idx, x0, y0, n0;
+        decode(tile, n_idx, x0, y0, n0);
+        const int bz = p.b_batched ? n0 : 0;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t fb = full_bar(stage);
+          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+          if (kb < p.kb0) {
+            const int tap = kb / p.cb0;
+            const int c = (kb - tap * p.cb0) * BK;
+            int cx = x0, cy = y0, cn = n0;
+            if (p.mode0 == TAPS_3X3) {
+              cy += tap / 3 - 1;
+              cx += tap % 3 - 1;
+            } else if (p.mode0 == TAPS_3X3_S2) {
+              const int dy = tap / 3, dx = tap % 3;
+              cy += dy >> 1;
+              cx += dx >> 1;
+              cn += ((dy & 1) * 2 + (dx & 1)) * p.phase_stride;
+            }
+            tma_load_4d(sa, &tm_a0h, fb, c, cx, cy, cn);
+            tma_load_4d(sa + A_PLANE_BYTES, &tm_a0l, fb, c, cx, cy, cn);
+          } else {
+            const int c = (kb - p.kb0) * BK;
+            tma_load_4d(sa, &tm_a1h, fb, c, x0, y0, n0);
+            tma_load_4d(sa + A_PLANE_BYTES, &tm_a1l, fb, c, x0, y0, n0);
+          }
+          tma_load_3d(sa + 2 * A_PLANE_BYTES, &tm_bh, fb, kb * BK, n_idx * BN, bz);
+          tma_load_3d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tm_bl, fb, kb * BK, n_idx * BN, bz);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ UMMA issuer -------------------------------------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const uint64_t hi = (uint64_t)p.desc_hi << 32;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          // descriptor low word: start address >> 4 | LBO (unused for swizzled K-major, canonical value 1) << 16
+          const uint32_t ah = ((sa & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t al = (((sa + A_PLANE_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t bh = (((sa + 2 * A_PLANE_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t bl = (((sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t adv = 2u * k;  // 16 fp16 = 32 bytes = 2 x 16-byte units inside the swizzle row
+            umma_f16(d_tmem, hi | (ah + adv), hi | (bh + adv), p.idesc, (uint32_t)((kb | k) != 0));
+            umma_f16(d_tmem, hi | (ah + adv), hi | (bl + adv), p.idesc, 1u);
+            umma_f16(d_tmem, hi | (al + adv), hi | (bh + adv), p.idesc, 1u);
+          }
+          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue ----------------------------------------------------
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = ew * 32 + lane;
+    const int xi = r % p.bw;
+    const int yi = (r / p.bw) % p.bh;
+    const int ni = r / (p.bw * p.bh);
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int n_idx, x0, y0, n0;
+      decode(tile, n_idx, x0, y0, n0);
+      const int n = n0 + ni;
+      const bool valid = n < p.N;
+      const long long pix = ((long long)n * p.H + (y0 + yi)) * p.W + (x0 + xi);
+      float* orow = p.out + pix * p.ldc + n_idx * BN;
+      const float* rrow = p.residual ? p.residual + pix * p.ldr + n_idx * BN : nullptr;
+      const float* crow = p.chanadd ? p.chanadd + (long long)n * p.ca_ld + n_idx * BN : nullptr;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t0 + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = p.alpha * __uint_as_float(v[j + 0]);
+            o.y = p.alpha * __uint_as_float(v[j + 1]);
+            o.z = p.alpha * __uint_as_float(v[j + 2]);
+            o.w = p.alpha * __uint_as_float(v[j + 3]);
+            if (crow) {
+              const float4 c = __ldg(reinterpret_cast<const float4*>(crow + c0 + j));
+              o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+            }
+            if (rrow) {
+              const float4 q = *reinterpret_cast<const float4*>(rrow + c0 + j);
+              o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+            }
+            *reinterpret_cast<float4*>(orow + c0 + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+    DDNM_CHECK(f != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+static CUtensorMap make_map_f16(const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+  CUtensorMap m;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t b[5], es[5];
+  uint64_t stride = 2;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    b[i] = box[i];
+    es[i] = 1;
+    stride *= dims[i];
+    if (i < rank - 1) gstr[i] = stride;
+  }
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, b, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DDNM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return m;
+}
+
+static uint32_t g_desc_hi_override = 0, g_idesc_xor = 0;
+void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor) {
+  g_desc_hi_override = desc_hi;
+  g_idesc_xor = idesc_xor;
+}
+
+TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1, const __half* w_hi, const __half* w_lo,
+                        int w_batches, int Cout, const View& out, const float* chanadd, int ca_ld, const float* residual,
+                        int ldr, float alpha, int num_sms) {
+  TcLaunch L;
+  TcParams& p = L.p;
+  const int taps = (mode0 == TAPS_1X1) ? 1 : 9;
+  DDNM_CHECK(src0.C % BK == 0, "tensor-core conv needs Cin % 64 == 0");
+  DDNM_CHECK(Cout % 64 == 0, "tensor-core conv needs Cout % 64 == 0");
+  L.BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  p.H = out.H; p.W = out.W; p.N = out.N;
+  // M tile: 128 consecutive pixels as [bn][bh][bw]
+  p.bw = out.W >= 128 ? 128 : out.W;
+  DDNM_CHECK(128 % p.bw == 0 && out.W % p.bw == 0, "unsupported width for the 128-pixel tile");
+  p.bh = std::min(out.H, 128 / p.bw);
+  DDNM_CHECK(out.H % p.bh == 0 && 128 % (p.bw * p.bh) == 0, "unsupported height for the 128-pixel tile");
+  p.bn = 128 / (p.bw * p.bh);
+  p.tiles_x = out.W / p.bw;
+  p.tiles_y = out.H / p.bh;
+  p.tiles_n = cdiv(out.N, p.bn);
+  p.n_tiles = Cout / L.BN;
+  p.mode0 = mode0;
+  p.cb0 = src0.C / BK;
+  p.kb0 = taps * p.cb0;
+  p.kb1 = src1 ? src1->C / BK : 0;
+  if (src1) DDNM_CHECK(src1->C % BK == 0 && src1->H == out.H && src1->W == out.W && src1->N == out.N, "bad 1x1 side input");
+  p.phase_stride = 0;
+  p.b_batched = w_batches > 1 ? 1 : 0;
+  if (p.b_batched) DDNM_CHECK(p.bn == 1 && w_batches == out.N, "batched B operand needs one image per tile");
+  if (mode0 == TAPS_3X3_S2) {
+    DDNM_CHECK(src0.H == out.H && src0.W == out.W && src0.N == 4 * out.N, "stride-2 source must be 4 parity phases");
+    p.phase_stride = out.N;
+  } else {
+    DDNM_CHECK(src0.H == out.H && src0.W == out.W && src0.N == out.N, "source/output shape mismatch");
+  }
+  p.Cout = Cout; p.ldc = out.ld; p.out = out.p;
+  DDNM_CHECK(out.C == Cout && out.ld % 4 == 0 && ((uintptr_t)out.p & 15) == 0, "output view misaligned");
+  p.chanadd = chanadd; p.ca_ld = ca_ld; p.residual = residual; p.ldr = ldr; p.alpha = alpha;
+  if (residual) DDNM_CHECK(ldr % 4 == 0 && ((uintptr_t)residual & 15) == 0, "residual misaligned");
+  // UMMA shared-memory descriptor, high word: SBO = 1024 B (8 rows x 128 B) >> 4 at bits [32,46), version = 1 at
+  // [46,48), layout SWIZZLE_128B (= 2) at [61,64).  (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+  p.desc_hi = g_desc_hi_override ? g_desc_hi_override : (64u | (1u << 14) | (2u << 29));
+  // Instruction descriptor: D = f32 (1 << 4), A = B = f16 (0), K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
+  p.idesc = ((1u << 4) | ((uint32_t)(L.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24)) ^ g_idesc_xor;
+
+  const uint64_t ad[4] = {(uint64_t)src0.C, (uint64_t)src0.W, (uint64_t)src0.H, (uint64_t)src0.N};
+  const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+  L.a0h = make_map_f16(src0.hi, 4, ad, abox);
+  L.a0l = make_map_f16(src0.lo, 4, ad, abox);
+  if (src1) {
+    const uint64_t ad1[4] = {(uint64_t)src1->C, (uint64_t)src1->W, (uint64_t)src1->H, (uint64_t)src1->N};
+    L.a1h = make_map_f16(src1->hi, 4, ad1, abox);
+    L.a1l = make_map_f16(src1->lo, 4, ad1, abox);
+  } else {
+    L.a1h = L.a0h;
+    L.a1l = L.a0l;
+  }
+  const int Ktot = (p.kb0 + p.kb1) * BK;
+  const uint64_t bd[3] = {(uint64_t)Ktot, (uint64_t)Cout, (uint64_t)w_batches};
+  const uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)L.BN, 1u};
+  L.bh = make_map_f16(w_hi, 3, bd, bbox);
+  L.bl = make_map_f16(w_lo, 3, bd, bbox);
+  const int total = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
+  L.grid = std::min(total, num_sms);
+  L.flops = 2.0 * (double)out.pixels() * Cout * Ktot;
+  return L;
+}
+
+template <int BN>
+static void launch_bn(const TcLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  conv_tc_kernel<BN><<<L.grid, 192, TcCfg<BN>::SMEM_BYTES, stream>>>(L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.p);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void tc_run(const TcLaunch& L, cudaStream_t stream) {
+  switch (L.BN) {
+    case 256: launch_bn<256>(L, stream); break;
+    case 128: launch_bn<128>(L, stream); break;
+    case 64: launch_bn<64>(L, stream); break;
+    default: throw Error("bad BN");
+  }
+}
+
+}  // namespace ddnm

@@ -1,0 +1,53 @@
+// tcgen05 implicit-GEMM convolution / GEMM with 3x fp16 split ("fp32-grade" products on the
+// 5th-gen tensor cores).  See tc_gemm.cu for the kernel; this header is the host-side launch record.
+#pragma once
+#include "common.cuh"
+
+namespace ddnm {
+
+enum TcTapMode : int {
+  TAPS_3X3 = 0,     // 3x3, stride 1, zero pad 1 (pad comes from TMA out-of-bounds zero fill)
+  TAPS_1X1 = 1,     // 1x1 / plain GEMM rows
+  TAPS_3X3_S2 = 2,  // 3x3, stride 2, pad (0,1,0,1): source is stored as 4 parity phases (space-to-depth)
+};
+
+struct TcParams {
+  int H, W, N;                 // OUTPUT spatial size and number of images
+  int bw, bh, bn;              // 128-row M tile = bn images x bh rows x bw columns
+  int tiles_x, tiles_y, tiles_n;
+  int n_tiles;                 // Cout / BN
+  int mode0;                   // TcTapMode of source 0
+  int cb0, kb0;                // source 0: 64-channel blocks per tap, total k-blocks (= taps * cb0)
+  int kb1;                     // source 1 (always 1x1, e.g. the nin_shortcut input): k-blocks, 0 = absent
+  int phase_stride;            // TAPS_3X3_S2: images per parity phase in the source's outer dim
+  int b_batched;               // 1: B operand has one matrix per image (attention), z coordinate = image
+  int Cout, ldc;
+  float* out;                  // out[pixel*ldc + co]
+  const float* chanadd;        // chanadd[image*ca_ld + co] added per (image, channel): bias (+ timestep projection); may be null
+  int ca_ld;                   // 0 = one row broadcast over images
+  const float* residual;       // residual[pixel*ldr + co]; may be null
+  int ldr;
+  float alpha;                 // out = alpha*acc + chanadd + residual
+  uint32_t desc_hi;            // UMMA smem descriptor high word (SW128 K-major), see tc_gemm.cu
+  uint32_t idesc;              // UMMA instruction descriptor
+};
+
+struct TcLaunch {
+  CUtensorMap a0h, a0l, a1h, a1l, bh, bl;
+  TcParams p;
+  int BN = 128;
+  int grid = 0;
+  double flops = 0;            // algorithmic flops (2*M*N*K, counted once)
+};
+
+// Build the launch record.  src0/src1: fp16 split activations; w_hi/w_lo: [batch][Cout][Ktot] fp16 K-major with
+// Ktot = taps*C0 + C1 (k index = tap*C0 + ci, then source-1 channels).
+TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1, const __half* w_hi, const __half* w_lo,
+                        int w_batches, int Cout, const View& out, const float* chanadd, int ca_ld, const float* residual,
+                        int ldr, float alpha, int num_sms);
+void tc_run(const TcLaunch& L, cudaStream_t stream);
+
+// debug knobs (tests only): override descriptor words for the NEXT launches built
+void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor);
+
+}  // namespace ddnm

@@ -1,0 +1,117 @@
+/* ddnm_b200 — C ABI of the B200-native DDNM sampling engine (libddnm_b200.so).
+ *
+ * The reference (wyhuai/DDNM) has no FFI: its hot path is reached through three Python call conventions
+ * (SURVEY.md §8b).  Each entry point below names the reference interface it stands behind; the Python
+ * shims in ddnm_b200/{model,operators,sampler}.py keep those signatures and forward to these symbols
+ * via ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions: every pointer is a raw CUDA device pointer unless a comment says "host"; `stream` is a
+ * cudaStream_t (NULL = default stream); work is enqueued asynchronously on it; tensors are borrowed
+ * for the duration of the call, workspaces belong to the handle.  Return value 0 = ok, non-zero =
+ * failure with a message available from ddnm_last_error() (thread-local).  Handles are per device and
+ * not re-entrant.
+ */
+#ifndef DDNM_B200_H
+#define DDNM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* ddnm_last_error(void);
+int ddnm_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Denoiser: guided_diffusion/models.py::Model ("simple" DDPM UNet of configs/celeba_hq.yml).
+ * Replaces `et = model(xt, t)` at functions/svd_ddnm.py:47,108 (Model.forward, models.py:301-341).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int ch, out_ch, n_levels;
+  int ch_mult[8];
+  int num_res_blocks;
+  int n_attn_res;
+  int attn_res[4];
+  int in_channels, resolution, groups;
+  float eps;
+} ddnm_simple_cfg;   /* mirrors config.model.* / config.data.image_size read at models.py:195-204 */
+
+int ddnm_unet_simple_create(const ddnm_simple_cfg* cfg, int batch, void** handle);
+/* name = key of Model.state_dict() (models.py:216-299), data = fp32 host or device, reference layout (OIHW);
+ * plus the pseudo-parameter "__freq" = exp(arange(ch/2) * -log(1e4)/(ch/2-1)) (models.py:16-18). */
+int ddnm_unet_set_param(void* handle, const char* name, const float* data, long long numel);
+int ddnm_unet_finalize(void* handle);
+/* x [B,3,R,R] NCHW fp32, t [B] fp32 holding integer timesteps, out [B,out_ch,R,R] NCHW fp32 */
+int ddnm_unet_forward(void* handle, const float* x, const float* t, float* out, void* stream);
+int ddnm_unet_set_graph(void* handle, int use_cuda_graph);
+int ddnm_unet_read_tap(void* handle, const char* name, float* dst_nchw, long long capacity, void* stream);
+int ddnm_unet_info(void* handle, long long* workspace_bytes, int* launches, double* flops_per_forward);
+/* per-launch CUDA-event timing of one eager forward, JSON array into json (host) */
+int ddnm_unet_profile(void* handle, const float* x, const float* t, float* out, void* stream, char* json, long long capacity);
+int ddnm_unet_destroy(void* handle);
+
+/* ------------------------------------------------------------------------------------------------
+ * Degradation operators: functions/svd_operators.py A_functions contract (:52-97):
+ * A, A_pinv, Lambda, Lambda_noise, plus the fused projection x0 - A^+(A x0 - y) of svd_ddnm.py:59-61.
+ * kind: 0 SuperResolution(:479) 1 Colorization(:627) 2 Inpainting(:324) 3 WalshHadamardCS(:211)
+ *       4 Deblurring(:934) 5 SRConv(:851).  Artefacts (V_small, perm, mask, singular tables) are inputs.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int kind, channels, img_dim, ratio;
+  const float* v_small;       /* SR: [r*r, r*r]; Colorization: [3,3]; Deblurring/SRConv: V_small [dim,dim] */
+  const float* u_small;       /* SR/Colorization: [1,1]; Deblurring: [dim,dim]; SRConv: [small,small] */
+  const float* singulars;     /* SR/Colorization: [1]; Deblurring: sorted big singulars [dim*dim]; SRConv: small [small] */
+  const float* singulars_orig;/* Deblurring: un-thresholded, sorted [dim*dim] */
+  const long long* perm;      /* WalshHadamardCS: [dim*dim]; Deblurring: [dim*dim] */
+  const long long* mask;      /* Inpainting: [dim*dim], 0 = missing (exp/inp_masks/mask.npy) */
+} ddnm_operator_desc;         /* all pointers: host memory, copied at creation */
+
+int ddnm_operator_create(const ddnm_operator_desc* desc, void** handle);
+long long ddnm_operator_y_dim(void* handle);                       /* M = length of A(x) per image */
+int ddnm_operator_A(void* handle, const float* x, int B, float* y, void* stream);
+int ddnm_operator_A_pinv(void* handle, const float* y, int B, float* x, void* stream);
+int ddnm_operator_project(void* handle, const float* x0, const float* y, int B, float* x0_hat, void* stream);
+/* Lambda / Lambda_noise (svd_operators.py:91-97 and per class, coefficient rule e.g. :568-604); a = sqrt(alpha-bar_next),
+ * sigma_t = sqrt(1 - alpha-bar_next) as fp32 scalars, sigma_y and eta as the reference's python floats */
+int ddnm_operator_lambda(void* handle, const float* v, int B, float a, float sigma_y, float sigma_t, float eta, float* out,
+                         void* stream);
+int ddnm_operator_lambda_noise(void* handle, const float* v, const float* eps, int B, float a, float sigma_y, float sigma_t,
+                               float eta, float* out, void* stream);
+int ddnm_operator_destroy(void* handle);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampler: functions/svd_ddnm.py ddnm_diffusion (:19-78) / ddnm_plus_diffusion (:80-164).
+ * One fused kernel per time pair does x0_t, the null-space projection (and Lambda / Lambda_noise for DDNM+)
+ * and the re-noising; the whole loop is enqueued without host synchronisation.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n_pairs;
+  const int* t_i;             /* host [n_pairs]: model time of the pair's source */
+  const int* t_j;             /* host [n_pairs]: target time (-1 = final) ; j > i = travel-back step */
+  const float* abar;          /* host [num_timesteps+1]: cumprod table, abar[t+1] = alpha-bar(t), abar[0] = 1 */
+  int num_timesteps;
+  float eta;
+  float sigma_y;              /* 0 -> DDNM; > 0 (already doubled, diffusion.py:524) -> DDNM+ */
+} ddnm_schedule;
+
+/* x_T [B,3,R,R]; y [B,M]; noise [n_pairs,B,3,R,R] (the randn_like draws of svd_ddnm.py:65,74 in order);
+ * out_x0 [B,3,R,R] = xs[-1]; out_x0_pred [B,3,R,R] = x0_preds[-1] (may be NULL). */
+int ddnm_sample(void* unet, void* op, const ddnm_schedule* sched, const float* x_T, const float* y, const float* noise, int B,
+                float* out_x0, float* out_x0_pred, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Op-level entry points (unit tests, micro-benchmarks).  NHWC fp32 tensors, OIHW weights.
+ * mode: 0 = 3x3 pad 1, 1 = 1x1, 2 = 3x3 stride 2 pad (0,1,0,1); up2: nearest x2 before the conv.
+ * ---------------------------------------------------------------------------------------------- */
+int ddnm_conv_tc(const float* x, int N, int H, int W, int Cin, const float* w, const float* bias, int Cout, int mode, int up2,
+                 const float* side_x, int CinSide, const float* side_w, const float* residual, float* out, void* stream);
+int ddnm_conv_direct(const float* x, int N, int H, int W, int Cin, const float* w, const float* bias, int Cout, int mode, int up2,
+                     float* out, void* stream);
+int ddnm_conv_tc_bench(int N, int H, int W, int Cin, int Cout, int mode, int iters, float* ms_per_iter, double* flops);
+int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const float* gamma, const float* beta, float eps,
+                   int silu, float* out, void* stream);
+int ddnm_tc_debug_override(unsigned desc_hi, unsigned idesc_xor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDNM_B200_H */

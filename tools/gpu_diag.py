@@ -1,0 +1,221 @@
+"""GPU diagnostics for the tensor-core path (run on the B200 box; each group in its own process)."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ddnm_b200 import _lib  # noqa: E402
+
+L = _lib.lib()
+dev = "cuda"
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def conv_tc(x, w, b, mode=0, up2=False, side=None, side_w=None, res=None):
+    N, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    oH, oW = (H // 2, W // 2) if mode == 2 else ((2 * H, 2 * W) if up2 else (H, W))
+    out = torch.empty(N, oH, oW, Cout, device=dev)
+    xs = nhwc(x)
+    sx = nhwc(side) if side is not None else None
+    rs = nhwc(res) if res is not None else None
+    _lib.check(L.ddnm_conv_tc(_lib.ptr(xs), N, H, W, Cin, _lib.ptr(w.contiguous()), _lib.ptr(b), Cout, mode, int(up2),
+                              _lib.ptr(sx), 0 if side is None else side.shape[1],
+                              _lib.ptr(side_w.contiguous()) if side_w is not None else None, _lib.ptr(rs), _lib.ptr(out), None))
+    torch.cuda.synchronize()
+    return out.permute(0, 3, 1, 2)
+
+
+def ref_conv(x, w, b, mode=0, up2=False, side=None, side_w=None, res=None):
+    x, w, b = x.double().cpu(), w.double().cpu(), b.double().cpu()
+    if up2:
+        x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+    if mode == 0:
+        o = F.conv2d(x, w, b, padding=1)
+    elif mode == 1:
+        o = F.conv2d(x, w, b)
+    else:
+        o = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2)
+    if side is not None:
+        o = o + F.conv2d(side.double().cpu(), side_w.double().cpu())
+    if res is not None:
+        o = o + res.double().cpu()
+    return o
+
+
+def report(name, got, ref):
+    got = got.double().cpu()
+    err = (got - ref).abs()
+    scale = ref.abs().max().item()
+    print(f"[{name}] max_abs_err {err.max().item():.3e}  ref_absmax {scale:.3e}  rel {err.max().item() / max(scale, 1e-30):.3e}"
+          f"  mean_err {err.mean().item():.3e}", flush=True)
+    bad = err.max().item() > 1e-4 * max(scale, 1.0)
+    if bad:
+        e = err[0]
+        print("   err by out-channel block of 8 (first 8):", [f"{e[c*8:(c+1)*8].max().item():.2e}" for c in range(min(8, e.shape[0] // 8))])
+        print("   err by row (first 8):", [f"{e[:, r].max().item():.2e}" for r in range(min(8, e.shape[1]))])
+        print("   err by col (first 16):", [f"{e[:, :, c].max().item():.2e}" for c in range(min(16, e.shape[2]))])
+        print("   sample got/ref [0,0,0,:6]:", got[0, 0, 0, :6].tolist(), ref[0, 0, 0, :6].tolist())
+    return not bad
+
+
+def group_gemm():
+    torch.manual_seed(0)
+    ok = True
+    for (N, H, W, Cin, Cout) in [(1, 1, 128, 64, 64), (1, 2, 128, 64, 128), (1, 4, 128, 128, 256), (2, 8, 16, 192, 128),
+                                 (3, 8, 8, 64, 64), (1, 16, 16, 512, 1536)]:
+        x = torch.randn(N, Cin, H, W, device=dev)
+        w = torch.randn(Cout, Cin, 1, 1, device=dev) / Cin ** 0.5
+        b = torch.randn(Cout, device=dev)
+        ok &= report(f"gemm1x1 N{N} {H}x{W} {Cin}->{Cout}", conv_tc(x, w, b, mode=1), ref_conv(x, w, b, mode=1))
+    print("GROUP gemm:", "PASS" if ok else "FAIL")
+
+
+def group_conv():
+    torch.manual_seed(1)
+    ok = True
+    for (N, H, W, Cin, Cout) in [(1, 16, 16, 64, 64), (2, 32, 32, 128, 128), (1, 64, 64, 128, 256), (1, 256, 256, 64, 128),
+                                 (3, 8, 8, 128, 64), (1, 128, 128, 192, 128)]:
+        x = torch.randn(N, Cin, H, W, device=dev)
+        w = torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5
+        b = torch.randn(Cout, device=dev)
+        ok &= report(f"conv3x3 N{N} {H}x{W} {Cin}->{Cout}", conv_tc(x, w, b, mode=0), ref_conv(x, w, b, mode=0))
+    print("GROUP conv3x3:", "PASS" if ok else "FAIL")
+
+
+def group_variants():
+    torch.manual_seed(2)
+    ok = True
+    N, H, W, Cin, Cout = 2, 32, 32, 128, 128
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    ok &= report("stride2", conv_tc(x, w, b, mode=2), ref_conv(x, w, b, mode=2))
+    ok &= report("up2", conv_tc(x, w, b, up2=True), ref_conv(x, w, b, up2=True))
+    res = torch.randn(N, Cout, H, W, device=dev)
+    ok &= report("residual", conv_tc(x, w, b, res=res), ref_conv(x, w, b, res=res))
+    side = torch.randn(N, 192, H, W, device=dev)
+    sw = torch.randn(Cout, 192, 1, 1, device=dev) / 192 ** 0.5
+    ok &= report("side1x1", conv_tc(x, w, b, side=side, side_w=sw), ref_conv(x, w, b, side=side, side_w=sw))
+    x8 = torch.randn(3, 64, 16, 16, device=dev)
+    w8 = torch.randn(64, 64, 3, 3, device=dev) / 24.0
+    b8 = torch.randn(64, device=dev)
+    ok &= report("stride2->8x8 N3", conv_tc(x8, w8, b8, mode=2), ref_conv(x8, w8, b8, mode=2))
+    # dynamic range: large and tiny magnitudes through the fp16 split
+    xl = torch.randn(1, 64, 16, 16, device=dev) * torch.logspace(-6, 3, 64, device=dev).view(1, 64, 1, 1)
+    ok &= report("range", conv_tc(xl, w8, b8), ref_conv(xl, w8, b8))
+    print("GROUP variants:", "PASS" if ok else "FAIL")
+
+
+def group_bench():
+    ms, fl = C.c_float(), C.c_double()
+    for (N, H, W, Cin, Cout, mode) in [(16, 256, 256, 128, 128, 0), (16, 256, 256, 256, 128, 0), (16, 128, 128, 256, 256, 0),
+                                       (16, 64, 64, 256, 256, 0), (16, 32, 32, 512, 512, 0), (16, 16, 16, 512, 512, 0),
+                                       (16, 8, 8, 512, 512, 0), (16, 256, 256, 256, 128, 1), (4, 256, 256, 128, 128, 0)]:
+        _lib.check(L.ddnm_conv_tc_bench(N, H, W, Cin, Cout, mode, 10, C.byref(ms), C.byref(fl)))
+        print(f"[bench] N{N} {H}x{W} {Cin}->{Cout} mode{mode}: {ms.value:.3f} ms  {fl.value / ms.value / 1e9:.1f} TFLOP/s (algorithmic)", flush=True)
+
+
+def _cfg_ns(cfg):
+    import types
+    ns = types.SimpleNamespace
+    return ns(model=ns(type="simple", ch=cfg.ch, out_ch=cfg.out_ch, ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks,
+                       attn_resolutions=list(cfg.attn_resolutions), dropout=0.0, in_channels=cfg.in_channels, resamp_with_conv=True),
+              data=ns(image_size=cfg.resolution), diffusion=ns(num_diffusion_timesteps=1000))
+
+
+def group_unet(which="tiny", B=2, graph=1):
+    from oracle import unet_simple as U
+    from ddnm_b200.model import Model
+    cfg = U.SimpleUNetConfig.tiny() if which == "tiny" else U.SimpleUNetConfig.celeba_hq()
+    sd = U.init_state_dict(cfg, 1234)
+    m = Model(_cfg_ns(cfg))
+    m.use_cuda_graph = bool(int(graph))
+    m.load_state_dict(sd)
+    B = int(B)
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(B, 3, cfg.resolution, cfg.resolution, generator=g)
+    t = torch.tensor([417.0, 3.0, 999.0, 0.0][:B] if B <= 4 else [float((37 * i) % 1000) for i in range(B)])
+    taps = {}
+    with torch.no_grad():
+        ref = U.forward(sd, x, t, cfg, taps=taps)
+    t0 = time.time()
+    out = m(x.to(dev), t.to(dev))
+    torch.cuda.synchronize()
+    print(f"engine build+first forward {time.time() - t0:.2f}s; info {m.info(B)}")
+    out2 = m(x.to(dev), t.to(dev))
+    torch.cuda.synchronize()
+    print("replay identical:", torch.equal(out, out2))
+    order = ["conv_in"]
+    nlev = len(cfg.ch_mult)
+    for lv in range(nlev):
+        order += [f"down.{lv}.{ib}" for ib in range(cfg.num_res_blocks)]
+        if lv != nlev - 1:
+            order.append(f"down.{lv}.ds")
+    order += ["mid.block_1", "mid.attn_1", "mid.block_2"]
+    for lv in reversed(range(nlev)):
+        order += [f"up.{lv}.{ib}" for ib in range(cfg.num_res_blocks + 1)]
+        if lv != 0:
+            order.append(f"up.{lv}.us")
+    for name in order:
+        r = taps[name]
+        got = m.read_tap(B, name, tuple(r.shape)).cpu()
+        err = (got - r).abs().max().item()
+        print(f"   tap {name:14s} shape {tuple(r.shape)} max_err {err:.3e} ref_absmax {r.abs().max().item():.3e}")
+    err = (out.cpu() - ref).abs()
+    tol = 1e-4 + 1e-3 * ref.abs()
+    viol = (err > tol).float().mean().item()
+    print(f"[unet {which} B{B}] max_abs_err {err.max().item():.3e} ref_absmax {ref.abs().max().item():.3e} "
+          f"violations(rtol1e-3,atol1e-4) {viol * 100:.4f}%  ->", "PASS" if viol == 0 else "FAIL", flush=True)
+    return m, x, t
+
+
+def group_unet_bench(which="celeba", B=16, iters=5):
+    from oracle import unet_simple as U
+    from ddnm_b200.model import Model
+    B, iters = int(B), int(iters)
+    cfg = U.SimpleUNetConfig.tiny() if which == "tiny" else U.SimpleUNetConfig.celeba_hq()
+    sd = U.init_state_dict(cfg, 1234)
+    m = Model(_cfg_ns(cfg))
+    m.load_state_dict(sd)
+    x = torch.randn(B, 3, cfg.resolution, cfg.resolution, device=dev)
+    t = torch.full((B,), 500.0, device=dev)
+    for _ in range(3):
+        m(x, t)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        m(x, t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    info = m.info(B)
+    print(f"[unet bench {which} B{B}] {ms:.2f} ms/forward  {B / ms * 1e3:.1f} img-fwd/s  "
+          f"{info['flops_per_forward'] / ms / 1e9:.1f} TFLOP/s algorithmic; workspace {info['workspace_bytes'] / 2**30:.2f} GiB; launches {info['launches']}")
+    prof = m.profile(x, t)
+    agg = {}
+    for p in prof:
+        a = agg.setdefault(p["kind"], [0.0, 0.0, 0.0, 0])
+        a[0] += p["ms"]; a[1] += p["flops"]; a[2] += p["bytes"]; a[3] += 1
+    tot = sum(a[0] for a in agg.values())
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        print(f"   {k:10s} n={a[3]:4d} {a[0]:8.3f} ms ({a[0] / tot * 100:5.1f}%)  {a[1] / max(a[0], 1e-9) / 1e9:8.1f} TFLOP/s  {a[2] / max(a[0], 1e-9) / 1e6:8.1f} GB/s")
+    top = sorted(prof, key=lambda p: -p["ms"])[:12]
+    for p in top:
+        print(f"   top {p['name']:28s} {p['ms']:.3f} ms  {p['flops'] / max(p['ms'], 1e-9) / 1e9:.1f} TF/s  {p['bytes'] / max(p['ms'], 1e-9) / 1e6:.1f} GB/s")
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(prof, open(f"gpurun_out/unet_profile_{which}_B{B}.json", "w"))
+
+
+if __name__ == "__main__":
+    print("device:", torch.cuda.get_device_name(0), flush=True)
+    globals()["group_" + sys.argv[1]](*sys.argv[2:])
