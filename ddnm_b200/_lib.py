@@ -25,7 +25,7 @@ class OperatorDesc(C.Structure):
 
 class Schedule(C.Structure):
     _fields_ = [("n_pairs", C.c_int), ("t_i", C.c_void_p), ("t_j", C.c_void_p), ("abar", C.c_void_p),
-                ("num_timesteps", C.c_int), ("eta", C.c_float), ("sigma_y", C.c_float)]
+                ("num_timesteps", C.c_int), ("eta", C.c_float), ("sigma_y", C.c_float), ("plus", C.c_int)]
 
 
 _lib = None

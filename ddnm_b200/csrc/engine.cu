@@ -485,20 +485,26 @@ void UNetSimple::forward(const float* x, const float* t, float* out, cudaStream_
   if (t != t_in_) CUDA_CHECK(cudaMemcpyAsync(t_in_, t, (size_t)B_ * 4, cudaMemcpyDeviceToDevice, stream));
   if (use_graph_) {
     if (!graph_exec_) {
-      // warm-up outside capture (first-use attribute setting is not capturable), then capture the program once
-      run_ops(stream);
+      // Capture once on a private stream (the caller's may be the legacy default stream, which cannot capture).
+      // A warm-up pass runs first: one-time cudaFuncSetAttribute calls are not capturable.
+      cudaStream_t cs = nullptr;
+      CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
       CUDA_CHECK(cudaStreamSynchronize(stream));
-      CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      run_ops(cs);
+      CUDA_CHECK(cudaStreamSynchronize(cs));
+      CUDA_CHECK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
       try {
-        run_ops(stream);
+        run_ops(cs);
       } catch (...) {
         cudaGraph_t g = nullptr;
-        cudaStreamEndCapture(stream, &g);
+        cudaStreamEndCapture(cs, &g);
         if (g) cudaGraphDestroy(g);
+        cudaStreamDestroy(cs);
         throw;
       }
-      CUDA_CHECK(cudaStreamEndCapture(stream, &graph_));
+      CUDA_CHECK(cudaStreamEndCapture(cs, &graph_));
       CUDA_CHECK(cudaGraphInstantiate(&graph_exec_, graph_, 0));
+      CUDA_CHECK(cudaStreamDestroy(cs));
     }
     CUDA_CHECK(cudaGraphLaunch(graph_exec_, stream));
   } else {

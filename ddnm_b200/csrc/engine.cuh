@@ -54,6 +54,9 @@ class UNetSimple {
   // per-op timing of one eager (non-graph) forward; returns JSON
   std::string profile(const float* x, const float* t, float* out, cudaStream_t stream);
   int batch() const { return B_; }
+  float* x_in() const { return x_in_; }
+  float* t_in() const { return t_in_; }
+  float* out_buf() const { return out_; }
   const SimpleCfg& cfg() const { return cfg_; }
   void set_use_graph(bool on) { use_graph_ = on; }
   size_t workspace_bytes() const { return arena_.used(); }

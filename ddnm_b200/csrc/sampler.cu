@@ -1,0 +1,86 @@
+// The DDNM / DDNM+ reverse-diffusion loop (functions/svd_ddnm.py:19-78 and :80-164) enqueued on one stream with
+// no host synchronisation: per denoising pair one UNet graph launch + one fused update; travel-back pairs are one
+// elementwise kernel.  The reference instead bounces xt / x0_t through host memory every step (:67-68, :45).
+#include <cmath>
+#include <vector>
+
+#include "../../include/ddnm_b200.h"
+#include "api_util.cuh"
+#include "engine.cuh"
+#include "operators.cuh"
+
+namespace ddnm {
+
+__global__ void fill_kernel(float* p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+// xt_next = at_next.sqrt() * x0_t + randn * (1 - at_next).sqrt()      (svd_ddnm.py:74)
+__global__ void travel_back_kernel(const float* __restrict__ x0, const float* __restrict__ z, float sa, float s1, float* __restrict__ xn,
+                                   long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) xn[i] = __fadd_rn(__fmul_rn(sa, x0[i]), __fmul_rn(z[i], s1));
+}
+
+static void sample(UNetSimple* unet, Operator* op, const ddnm_schedule* sc, const float* x_T, const float* y, const float* noise,
+                   int B, float* out_x0, float* out_x0_pred, cudaStream_t st) {
+  DDNM_CHECK(unet && op && sc && x_T && y && noise && out_x0, "null argument");
+  DDNM_CHECK(unet->batch() == B, "engine was built for a different batch size");
+  const SimpleCfg& cfg = unet->cfg();
+  DDNM_CHECK(op->x_dim() == (long long)cfg.in_channels * cfg.resolution * cfg.resolution, "operator / denoiser image size mismatch");
+  DDNM_CHECK(cfg.out_ch == 3 || cfg.out_ch == 6, "denoiser must predict 3 (eps) or 6 (eps, sigma) channels");
+  const long long img = op->x_dim();
+  const long long n = (long long)B * img;
+  const long long et_stride = (long long)cfg.out_ch * cfg.resolution * cfg.resolution;  // 6-channel nets: keep channels 0..2 (:54-55)
+  float* xt = unet->x_in();      // the denoiser reads its input here
+  float* et = unet->out_buf();   // and leaves eps here
+  float *x0t = nullptr, *xn = nullptr;
+  CUDA_CHECK(cudaMallocAsync((void**)&x0t, n * sizeof(float), st));
+  CUDA_CHECK(cudaMallocAsync((void**)&xn, n * sizeof(float), st));
+  CUDA_CHECK(cudaMemcpyAsync(xt, x_T, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const float eta = sc->eta;
+  const float c_eta = (float)std::sqrt(1.0 - (double)eta * (double)eta);  // (1 - eta ** 2) ** 0.5 as the fp32 scalar torch sees
+  bool have_x0 = false;
+  for (int k = 0; k < sc->n_pairs; ++k) {
+    const int i = sc->t_i[k], j = sc->t_j[k];
+    DDNM_CHECK(i >= 0 && i < sc->num_timesteps && j >= -1 && j < sc->num_timesteps, "time index out of range");
+    const float at_next = sc->abar[j + 1];
+    const float* z = noise + (long long)k * n;
+    if (j < i) {
+      const float at = sc->abar[i + 1];
+      fill_kernel<<<cdiv(B, 128), 128, 0, st>>>(unet->t_in(), B, (float)i);
+      unet->forward(xt, unet->t_in(), et, st);
+      StepScalars s{};
+      s.sqrt_at = std::sqrt(at);
+      s.sqrt_1m_at = std::sqrt(1.0f - at);
+      s.sqrt_atn = std::sqrt(at_next);
+      const float s1n = std::sqrt(1.0f - at_next);
+      s.c1 = s1n * eta;
+      s.c2 = s1n * c_eta;
+      s.use_plus = sc->plus ? 1 : 0;
+      if (s.use_plus) s.plus = Operator::make_plus(s.sqrt_atn, sc->sigma_y, s1n, eta);
+      op->step(xt, et, et_stride, z, y, B, s, x0t, xn, st);
+      have_x0 = true;
+    } else {
+      DDNM_CHECK(have_x0, "schedule starts with a travel-back step");
+      travel_back_kernel<<<(int)cdivll(n, 256), 256, 0, st>>>(x0t, z, std::sqrt(at_next), std::sqrt(1.0f - at_next), xn, n);
+      CUDA_CHECK(cudaGetLastError());
+    }
+    CUDA_CHECK(cudaMemcpyAsync(xt, xn, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(out_x0, xt, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (out_x0_pred) CUDA_CHECK(cudaMemcpyAsync(out_x0_pred, x0t, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CUDA_CHECK(cudaFreeAsync(x0t, st));
+  CUDA_CHECK(cudaFreeAsync(xn, st));
+}
+
+}  // namespace ddnm
+
+using namespace ddnm;
+extern "C" int ddnm_sample(void* unet, void* op, const ddnm_schedule* sched, const float* x_T, const float* y, const float* noise,
+                           int B, float* out_x0, float* out_x0_pred, void* stream) {
+  DDNM_API_BEGIN
+  sample(static_cast<UNetSimple*>(unet), static_cast<Operator*>(op), sched, x_T, y, noise, B, out_x0, out_x0_pred,
+         (cudaStream_t)stream);
+  DDNM_API_END
+}

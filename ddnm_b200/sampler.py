@@ -1,0 +1,62 @@
+"""Drop-in for ``functions/svd_ddnm.py``: ``ddnm_diffusion`` (:19-78) and ``ddnm_plus_diffusion`` (:80-164) with the
+reference's signatures and return convention (``([x_0.cpu()], [x0_pred.cpu()])``).
+
+The whole loop runs inside libddnm_b200.so on the current CUDA stream without host round trips.  The Gaussian draws
+are taken from torch's generator in the reference's order (one ``randn_like`` per time pair, :65/:74) into a tape
+before the loop starts, so a run is seed-for-seed comparable with the reference on the same device.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import Model
+from .operators import _Operator
+from .schedule import alpha_bar_table, time_pairs
+
+class_num = 951
+
+
+def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, noise=None):
+    if cls_fn is not None:
+        raise NotImplementedError("classifier guidance (imagenet_256_cc.yml) is outside the ddnm_b200 hot path")
+    if not isinstance(model, Model):
+        model = getattr(model, "module", model)          # tolerate nn.DataParallel-style wrappers
+    if not isinstance(model, Model) or not isinstance(A_funcs, _Operator):
+        raise TypeError("ddnm_b200.sampler needs a ddnm_b200.model.Model and a ddnm_b200.operators operator")
+    with torch.no_grad():
+        assert x.is_cuda, "x must live on the GPU"
+        n = x.size(0)
+        pairs = time_pairs(config.diffusion.num_diffusion_timesteps, config.time_travel.T_sampling,
+                           config.time_travel.travel_length, config.time_travel.travel_repeat)
+        abar = np.ascontiguousarray(alpha_bar_table(b).numpy())
+        ti = np.ascontiguousarray(np.array([p[0] for p in pairs], dtype=np.int32))
+        tj = np.ascontiguousarray(np.array([p[1] for p in pairs], dtype=np.int32))
+        x = x.float().contiguous()
+        if noise is None:
+            noise = torch.empty((len(pairs),) + tuple(x.shape), device=x.device, dtype=torch.float32)
+            for k in range(len(pairs)):
+                noise[k] = torch.randn_like(x)              # same generator consumption as the reference loop
+        else:
+            assert noise.shape == (len(pairs),) + tuple(x.shape)
+            noise = noise.to(x.device).float().contiguous()
+        yv = y.reshape(n, -1).to(x.device).float().contiguous()
+        assert yv.shape[1] == A_funcs.y_dim, f"y has {yv.shape[1]} entries per image, operator expects {A_funcs.y_dim}"
+        s = _lib.Schedule()
+        s.n_pairs, s.t_i, s.t_j, s.abar = len(pairs), ti.ctypes.data, tj.ctypes.data, abar.ctypes.data
+        s.num_timesteps, s.eta, s.sigma_y = int(config.diffusion.num_diffusion_timesteps), float(eta), float(sigma_y)
+        s.plus = 1 if plus else 0
+        out = torch.empty_like(x)
+        x0p = torch.empty_like(x)
+        _lib.check(_lib.lib().ddnm_sample(model.engine(n), A_funcs._h, C.byref(s), _lib.ptr(x), _lib.ptr(yv), _lib.ptr(noise), n,
+                                         _lib.ptr(out), _lib.ptr(x0p), _lib.cur_stream()))
+        return [out.to("cpu")], [x0p.to("cpu")]
+
+
+def ddnm_diffusion(x, model, b, eta, A_funcs, y, cls_fn=None, classes=None, config=None, noise=None):
+    return _run(x, model, b, eta, A_funcs, y, 0.0, False, cls_fn, classes, config, noise)
+
+
+def ddnm_plus_diffusion(x, model, b, eta, A_funcs, y, sigma_y, cls_fn=None, classes=None, config=None, noise=None):
+    return _run(x, model, b, eta, A_funcs, y, sigma_y, True, cls_fn, classes, config, noise)

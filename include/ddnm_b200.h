@@ -62,7 +62,8 @@ typedef struct {
   const float* singulars;     /* SR/Colorization: [1]; Deblurring: sorted big singulars [dim*dim]; SRConv: small [small] */
   const float* singulars_orig;/* Deblurring: un-thresholded, sorted [dim*dim] */
   const long long* perm;      /* WalshHadamardCS: [dim*dim]; Deblurring: [dim*dim] */
-  const long long* mask;      /* Inpainting: [dim*dim], 0 = missing (exp/inp_masks/mask.npy) */
+  const long long* mask;      /* Inpainting: [dim*dim*channels] keep flags over the (pixel, channel)-interleaved vector the
+                                 reference's missing_indices address (diffusion.py:466-470); 0 = missing */
 } ddnm_operator_desc;         /* all pointers: host memory, copied at creation */
 
 int ddnm_operator_create(const ddnm_operator_desc* desc, void** handle);
@@ -90,7 +91,8 @@ typedef struct {
   const float* abar;          /* host [num_timesteps+1]: cumprod table, abar[t+1] = alpha-bar(t), abar[0] = 1 */
   int num_timesteps;
   float eta;
-  float sigma_y;              /* 0 -> DDNM; > 0 (already doubled, diffusion.py:524) -> DDNM+ */
+  float sigma_y;              /* DDNM+: measurement noise level (already doubled, diffusion.py:524) */
+  int plus;                   /* 0 = ddnm_diffusion update (:57-65), 1 = ddnm_plus_diffusion update (:114-131) */
 } ddnm_schedule;
 
 /* x_T [B,3,R,R]; y [B,M]; noise [n_pairs,B,3,R,R] (the randn_like draws of svd_ddnm.py:65,74 in order);

@@ -218,7 +218,10 @@ def sampler_fixtures():
     x_orig = torch.rand(B, 3, dim, dim, generator=rng) * 2 - 1
     x_T = torch.randn(B, 3, dim, dim, generator=rng)
     out["x_orig"], out["x_T"] = x_orig.numpy(), x_T.numpy()
-    opsets = {n: (r_, o_) for n, r_, o_, _ in build_ops(dim, torch.Generator().manual_seed(4321))}
+    # same RNG protocol as operator_fixtures (x, v, e drawn first) so mask / perm equal the stored artefacts
+    orng = torch.Generator().manual_seed(4321)
+    torch.rand(B, 3, dim, dim, generator=orng), torch.randn(B, 3 * dim * dim, generator=orng), torch.randn(B, 3 * dim * dim, generator=orng)
+    opsets = {n: (r_, o_) for n, r_, o_, _ in build_ops(dim, orng)}
     cases = [("sr4", 10, 1, 1, 0.0), ("sr4", 10, 3, 2, 0.0), ("sr4", 10, 1, 1, 0.1), ("color", 10, 1, 1, 0.0),
              ("inpaint", 10, 2, 2, 0.1), ("wh", 10, 1, 1, 0.0), ("deblur", 10, 1, 1, 0.1), ("bicubic", 10, 1, 1, 0.0)]
     for name, T, tl, tr, sy in cases:
