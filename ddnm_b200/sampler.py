@@ -18,7 +18,12 @@ from .schedule import alpha_bar_table, time_pairs
 class_num = 951
 
 
-def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, noise=None):
+def sample_device(x, model, b, eta, A_funcs, y, sigma_y, plus, config, noise=None):
+    """The loop with device-resident inputs and outputs (no host copies): returns (x_0, x0_pred) CUDA tensors."""
+    return _run(x, model, b, eta, A_funcs, y, sigma_y, plus, None, None, config, noise, to_host=False)
+
+
+def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, noise=None, to_host=True):
     if cls_fn is not None:
         raise NotImplementedError("classifier guidance (imagenet_256_cc.yml) is outside the ddnm_b200 hot path")
     if not isinstance(model, Model):
@@ -26,7 +31,8 @@ def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, n
     if not isinstance(model, Model) or not isinstance(A_funcs, _Operator):
         raise TypeError("ddnm_b200.sampler needs a ddnm_b200.model.Model and a ddnm_b200.operators operator")
     with torch.no_grad():
-        assert x.is_cuda, "x must live on the GPU"
+        if not x.is_cuda:
+            x = x.to("cuda", non_blocking=True)            # the reference moves xs[-1] to 'cuda' itself (svd_ddnm.py:45)
         n = x.size(0)
         pairs = time_pairs(config.diffusion.num_diffusion_timesteps, config.time_travel.T_sampling,
                            config.time_travel.travel_length, config.time_travel.travel_repeat)
@@ -41,7 +47,7 @@ def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, n
         else:
             assert noise.shape == (len(pairs),) + tuple(x.shape)
             noise = noise.to(x.device).float().contiguous()
-        yv = y.reshape(n, -1).to(x.device).float().contiguous()
+        yv = y.reshape(n, -1).to(x.device, non_blocking=True).float().contiguous()
         assert yv.shape[1] == A_funcs.y_dim, f"y has {yv.shape[1]} entries per image, operator expects {A_funcs.y_dim}"
         s = _lib.Schedule()
         s.n_pairs, s.t_i, s.t_j, s.abar = len(pairs), ti.ctypes.data, tj.ctypes.data, abar.ctypes.data
@@ -51,6 +57,8 @@ def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, n
         x0p = torch.empty_like(x)
         _lib.check(_lib.lib().ddnm_sample(model.engine(n), A_funcs._h, C.byref(s), _lib.ptr(x), _lib.ptr(yv), _lib.ptr(noise), n,
                                          _lib.ptr(out), _lib.ptr(x0p), _lib.cur_stream()))
+        if not to_host:
+            return out, x0p
         return [out.to("cpu")], [x0p.to("cpu")]
 
 
