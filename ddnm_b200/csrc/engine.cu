@@ -334,7 +334,6 @@ void UNetSimple::build_program() {
   x_in_ = (float*)arena_.alloc((size_t)B_ * c.in_channels * R * R * 4);
   t_in_ = (float*)arena_.alloc((size_t)B_ * 4);
   out_ = (float*)arena_.alloc((size_t)B_ * c.out_ch * R * R * 4);
-  headact_ = (float*)arena_.alloc((size_t)B_ * R * R * c.ch * 4);
 
   // ---- timestep embedding MLP + all per-block projections as one matrix (models.py:305-308, :121) ----
   const int tch = c.ch * 4;
@@ -460,16 +459,14 @@ void UNetSimple::build_program() {
     const float *g = P("norm_out.weight", final_h.C), *b = P("norm_out.bias", final_h.C);
     const int groups = c.groups;
     const float eps = c.eps;
-    float* act = headact_;
     const View fh = final_h;
     const double ab = (double)fh.pixels() * fh.C * 4;
     add_op("norm_out.gn_stats", "gn_stats", 0, ab, [=](cudaStream_t s) { gn_stats(fh, groups, st, s); });
-    add_op("norm_out.apply", "gn_split", 0, 2 * ab, [=](cudaStream_t s) { gn_apply_f32(fh, groups, st, g, b, eps, true, act, s); });
     const float *w = P("conv_out.weight", (long long)c.out_ch * fh.C * 9), *bo = P("conv_out.bias", c.out_ch);
     float* o = out_;
     const int Bn = B_, oc = c.out_ch, Cin = fh.C, Rr = R;
-    add_op("conv_out", "head", 2.0 * Bn * Rr * Rr * (double)oc * Cin * 9, ab + (double)Bn * Rr * Rr * oc * 4,
-           [=](cudaStream_t s) { conv3x3_small_cout(act, Bn, Rr, Rr, Cin, w, bo, oc, o, s); });
+    add_op("norm_out+conv_out", "head", 2.0 * Bn * Rr * Rr * (double)oc * Cin * 9, ab + (double)Bn * Rr * Rr * oc * 4,
+           [=](cudaStream_t s) { head_conv_gn_silu(fh, groups, st, g, b, eps, w, bo, oc, o, s); });
   }
 }
 

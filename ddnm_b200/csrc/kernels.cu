@@ -31,8 +31,22 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int 
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   if (prow < rows) {
     const float* base = x + (long long)n * HW * ld + c4 * 4;
-    for (int p = p0 + prow; p < p1; p += rows) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(base + (long long)p * ld));
+    const size_t step = (size_t)rows * ld;
+    int p = p0 + prow;
+    const float* ptr = base + (size_t)p * ld;
+    // 4 independent 16-byte loads in flight per thread (the compiler does not unroll this loop on its own)
+    for (; p + 3 * rows < p1; p += 4 * rows, ptr += 4 * step) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(ptr));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(ptr + step));
+      const float4 v2 = __ldg(reinterpret_cast<const float4*>(ptr + 2 * step));
+      const float4 v3 = __ldg(reinterpret_cast<const float4*>(ptr + 3 * step));
+      s[0] += (v0.x + v1.x) + (v2.x + v3.x); q[0] += (v0.x * v0.x + v1.x * v1.x) + (v2.x * v2.x + v3.x * v3.x);
+      s[1] += (v0.y + v1.y) + (v2.y + v3.y); q[1] += (v0.y * v0.y + v1.y * v1.y) + (v2.y * v2.y + v3.y * v3.y);
+      s[2] += (v0.z + v1.z) + (v2.z + v3.z); q[2] += (v0.z * v0.z + v1.z * v1.z) + (v2.z * v2.z + v3.z * v3.z);
+      s[3] += (v0.w + v1.w) + (v2.w + v3.w); q[3] += (v0.w * v0.w + v1.w * v1.w) + (v2.w * v2.w + v3.w * v3.w);
+    }
+    for (; p < p1; p += rows, ptr += step) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ptr));
       s[0] += v.x; q[0] += v.x * v.x;
       s[1] += v.y; q[1] += v.y * v.y;
       s[2] += v.z; q[2] += v.z * v.z;
@@ -106,23 +120,28 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
   }
   __syncthreads();
   const int C8 = C >> 3;
+  const int rows = blockDim.x / C8;
+  const int c8 = threadIdx.x % C8, prow = threadIdx.x / C8;
+  if (prow >= rows) return;
+  const int c = c8 * 8;
+  float a8[8], b8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a8[j] = sc[c + j]; b8[j] = sh[c + j]; }
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
-  const long long total = (long long)(p1 - p0) * C8;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    const int p = p0 + (int)(i / C8);
-    const int c = (int)(i % C8) * 8;
-    const float* src = x + ((long long)n * HW + p) * ld + c;
+  const float* src = x + ((size_t)n * HW + p0 + prow) * ld + c;
+  const size_t step = (size_t)rows * ld;
+  for (int p = p0 + prow; p < p1; p += rows, src += step) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src));
     const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
     float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v[j] = v[j] * sc[c + j] + sh[c + j];
+      v[j] = fmaf(v[j], a8[j], b8[j]);
       if (silu) v[j] = swishf(v[j]);
     }
     if (F32OUT) {
-      float* d = out32 + ((long long)n * HW + p) * C + c;
+      float* d = out32 + ((size_t)n * HW + p) * C + c;
       *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
     } else {
@@ -132,25 +151,27 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
       for (int j = 0; j < 8; ++j) split_f16(v[j], h8[j], l8[j]);
       const uint4 hv = *reinterpret_cast<const uint4*>(h8);
       const uint4 lv = *reinterpret_cast<const uint4*>(l8);
-      const int y = p / W, xx = p % W;
       if (mode == SPLIT_SAME) {
-        const long long o = ((long long)n * HW + p) * C + c;
+        const size_t o = ((size_t)n * HW + p) * C + c;
         *reinterpret_cast<uint4*>(hi + o) = hv;
         *reinterpret_cast<uint4*>(lo + o) = lv;
-      } else if (mode == SPLIT_UP2) {
-        const int W2 = 2 * W;
+      } else {
+        const int y = p / W, xx = p - y * W;
+        if (mode == SPLIT_UP2) {
+          const int W2 = 2 * W;
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          const long long o = (((long long)n * 2 * H + (2 * y + (d >> 1))) * W2 + (2 * xx + (d & 1))) * C + c;
+          for (int d = 0; d < 4; ++d) {
+            const size_t o = (((size_t)n * 2 * H + (2 * y + (d >> 1))) * W2 + (2 * xx + (d & 1))) * C + c;
+            *reinterpret_cast<uint4*>(hi + o) = hv;
+            *reinterpret_cast<uint4*>(lo + o) = lv;
+          }
+        } else {  // SPLIT_S2D
+          const int ph = (y & 1) * 2 + (xx & 1);
+          const int Hh = H >> 1, Wh = W >> 1;
+          const size_t o = ((((size_t)ph * N + n) * Hh + (y >> 1)) * Wh + (xx >> 1)) * C + c;
           *reinterpret_cast<uint4*>(hi + o) = hv;
           *reinterpret_cast<uint4*>(lo + o) = lv;
         }
-      } else {  // SPLIT_S2D
-        const int ph = (y & 1) * 2 + (xx & 1);
-        const int Hh = H >> 1, Wh = W >> 1;
-        const long long o = ((((long long)ph * N + n) * Hh + (y >> 1)) * Wh + (xx >> 1)) * C + c;
-        *reinterpret_cast<uint4*>(hi + o) = hv;
-        *reinterpret_cast<uint4*>(lo + o) = lv;
       }
     }
   }
@@ -161,14 +182,17 @@ static void gn_apply_launch(const View& x, int groups, const double* stats, cons
   DDNM_CHECK(x.C % 8 == 0 && x.C <= MAX_C && x.ld % 4 == 0, "gn_apply: unsupported channel count");
   if (mode == SPLIT_S2D) DDNM_CHECK(x.H % 2 == 0 && x.W % 2 == 0, "space-to-depth needs even dims");
   const int HW = x.H * x.W;
+  const int C8 = x.C / 8;
+  const int rows = std::max(1, 256 / C8);
+  const int threads = C8 * rows;
   long long want = cdivll((long long)HW * x.N, 148 * 8);
-  int ppc = (int)std::max<long long>(8, want);
+  int ppc = (int)std::max<long long>(rows, cdivll(want, rows) * rows);
   dim3 grid(cdiv(HW, ppc), x.N);
   if (out32)
-    gn_apply_kernel<true><<<grid, 256, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, gamma, beta, eps, silu, mode,
+    gn_apply_kernel<true><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, gamma, beta, eps, silu, mode,
                                                  ppc, nullptr, nullptr, out32);
   else
-    gn_apply_kernel<false><<<grid, 256, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, gamma, beta, eps, silu, mode,
+    gn_apply_kernel<false><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, gamma, beta, eps, silu, mode,
                                                   ppc, hi, lo, nullptr);
   CUDA_CHECK(cudaGetLastError());
 }
@@ -192,16 +216,17 @@ __global__ void __launch_bounds__(256) conv_small_cin_kernel(const float* __rest
                                                              const float* __restrict__ bias, float* __restrict__ out,
                                                              int H, int W, int Cout, int ld) {
   constexpr int KT = CIN * 9;
-  constexpr int TW = 64;  // pixels per CTA (one row segment)
-  __shared__ float tile[CIN][3][TW + 2];
-  const int n = blockIdx.z / ((Cout + 127) / 128);
-  const int slab = blockIdx.z % ((Cout + 127) / 128);
-  const int y = blockIdx.y;
+  constexpr int TW = 64, TH = 8;  // output tile per CTA: one warp per row
+  __shared__ float tile[CIN][TH + 2][TW + 2];
+  const int slabs = (Cout + 127) / 128;
+  const int n = blockIdx.z / slabs;
+  const int slab = blockIdx.z % slabs;
+  const int y0 = blockIdx.y * TH;
   const int x0 = blockIdx.x * TW;
-  for (int i = threadIdx.x; i < CIN * 3 * (TW + 2); i += blockDim.x) {
-    const int xx = i % (TW + 2), r = (i / (TW + 2)) % 3, c = i / (3 * (TW + 2));
-    const int gy = y + r - 1, gx = x0 + xx - 1;
-    tile[c][r][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[(((long long)n * CIN + c) * H + gy) * W + gx] : 0.f;
+  for (int i = threadIdx.x; i < CIN * (TH + 2) * (TW + 2); i += blockDim.x) {
+    const int xx = i % (TW + 2), r = (i / (TW + 2)) % (TH + 2), c = i / ((TH + 2) * (TW + 2));
+    const int gy = y0 + r - 1, gx = x0 + xx - 1;
+    tile[c][r][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(&x[(((size_t)n * CIN + c) * H + gy) * W + gx]) : 0.f;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int co = slab * 128 + lane * 4;
@@ -212,13 +237,15 @@ __global__ void __launch_bounds__(256) conv_small_cin_kernel(const float* __rest
 #pragma unroll
     for (int k = 0; k < KT; ++k)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) wr[k][j] = w[(long long)(co + j) * KT + k];  // OIHW: k = ci*9 + ky*3 + kx
+      for (int j = 0; j < 4; ++j) wr[k][j] = __ldg(&w[(size_t)(co + j) * KT + k]);  // OIHW: k = ci*9 + ky*3 + kx
 #pragma unroll
-    for (int j = 0; j < 4; ++j) b4[j] = bias[co + j];
+    for (int j = 0; j < 4; ++j) b4[j] = __ldg(&bias[co + j]);
   }
   __syncthreads();
-  if (!active) return;
-  for (int px = warp; px < TW && x0 + px < W; px += 8) {
+  const int y = y0 + warp;
+  if (!active || y >= H) return;
+  float* orow = out + (((size_t)n * H + y) * W + x0) * ld + co;
+  for (int px = 0; px < TW && x0 + px < W; ++px) {
     float acc[4] = {b4[0], b4[1], b4[2], b4[3]};
 #pragma unroll
     for (int c = 0; c < CIN; ++c)
@@ -226,118 +253,132 @@ __global__ void __launch_bounds__(256) conv_small_cin_kernel(const float* __rest
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const float v = tile[c][r][px + d];
+          const float v = tile[c][warp + r][px + d];
           const int k = c * 9 + r * 3 + d;
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[j] = fmaf(v, wr[k][j], acc[j]);
         }
-    float* o = out + (((long long)n * H + y) * W + x0 + px) * ld + co;
-    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(orow + (size_t)px * ld) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
 
 void conv3x3_small_cin(const float* x, int Cin, const float* w, const float* bias, const View& out, cudaStream_t st) {
   DDNM_CHECK(Cin == 3, "stem convolution expects 3 input channels");
   DDNM_CHECK(out.C % 4 == 0, "stem Cout % 4");
-  dim3 grid(cdiv(out.W, 64), out.H, out.N * cdiv(out.C, 128));
+  dim3 grid(cdiv(out.W, 64), cdiv(out.H, 8), out.N * cdiv(out.C, 128));
   conv_small_cin_kernel<3><<<grid, 256, 0, st>>>(x, w, bias, out.p, out.H, out.W, out.C, out.ld);
   CUDA_CHECK(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Head: conv_out = Conv2d(ch, out_ch, 3, padding=1) (models.py:294-299, 340) on the activated NHWC tensor, NCHW
-// result.  Warp <-> strip of 8 output pixels in a row, lane <-> channel slices of 4; each loaded input vector is
-// reused by the 3 horizontal taps; weights sit in shared memory as [tap][co][ci].
+// Head: h = nonlinearity(norm_out(h)); conv_out = Conv2d(ch, out_ch, 3, padding=1)  (models.py:338-340), fused:
+// the CTA stages a (2+2) x (32+2) pixel halo tile of the NHWC input in shared memory, applying GroupNorm affine +
+// SiLU on the way in, then 64 pixels x 4 channel-quarters accumulate the 3x3xCin dot products; NCHW result.
+// The input tensor is read from HBM once (halo rows come from L2); no activated copy is ever written.
 // ---------------------------------------------------------------------------------------------------------------
 template <int COUT>
-__global__ void __launch_bounds__(256) conv_small_cout_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                              const float* __restrict__ bias, float* __restrict__ out,
-                                                              int N, int H, int W, int Cin) {
-  extern __shared__ float ws[];  // [9][COUT][Cin]
+__global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ x, int ld, int N, int H, int W, int Cin,
+                                                        int groups, const double* __restrict__ stats,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, const float* __restrict__ w, const float* __restrict__ bias,
+                                                        float* __restrict__ out) {
+  constexpr int TW = 32, TH = 2;
+  extern __shared__ float smem[];
+  const int PS = Cin + 4;                                  // padded pixel stride (floats): conflict-free LDS.128
+  float* tile = smem;                                      // [(TH+2)*(TW+2)][PS]
+  float* ws = tile + (TH + 2) * (TW + 2) * PS;             // [9][COUT][Cin]
+  float* sc = ws + 9 * COUT * Cin;                         // [Cin]
+  float* sh = sc + Cin;                                    // [Cin]
+  float* red = sh + Cin;                                   // [4][64][COUT]
+  const int n = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+  const int HW = H * W;
   for (int i = threadIdx.x; i < 9 * COUT * Cin; i += blockDim.x) {
     const int ci = i % Cin, co = (i / Cin) % COUT, tap = i / (Cin * COUT);
-    ws[i] = w[((long long)co * Cin + ci) * 9 + tap];
+    ws[i] = __ldg(&w[((size_t)co * Cin + ci) * 9 + tap]);
+  }
+  {
+    const int cpg = Cin / groups;
+    const double cnt = (double)HW * cpg;
+    for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+      const int g = c / cpg;
+      const double mean = stats[((size_t)n * groups + g) * 2] / cnt;
+      double var = stats[((size_t)n * groups + g) * 2 + 1] / cnt - mean * mean;
+      var = var < 0 ? 0 : var;
+      const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
+      sc[c] = a;
+      sh[c] = beta[c] - (float)mean * a;
+    }
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int strips_per_row = W / 8;
-  const long long strip = (long long)blockIdx.x * 8 + warp;
-  if (strip >= (long long)N * H * strips_per_row) return;
-  const int sx = (int)(strip % strips_per_row) * 8;
-  const int y = (int)((strip / strips_per_row) % H);
-  const int n = (int)(strip / ((long long)strips_per_row * H));
-  float acc[8][COUT];
+  const int C4 = Cin >> 2;
+  for (int i = threadIdx.x; i < (TH + 2) * (TW + 2) * C4; i += blockDim.x) {
+    const int c4 = i % C4, pp = i / C4;
+    const int tx = pp % (TW + 2), ty = pp / (TW + 2);
+    const int gy = y0 + ty - 1, gx = x0 + tx - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);            // zero padding applies AFTER the activation (conv pads its input)
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + gy) * W + gx) * ld + c4 * 4));
+      const int c = c4 * 4;
+      v.x = swishf(fmaf(v.x, sc[c + 0], sh[c + 0]));
+      v.y = swishf(fmaf(v.y, sc[c + 1], sh[c + 1]));
+      v.z = swishf(fmaf(v.z, sc[c + 2], sh[c + 2]));
+      v.w = swishf(fmaf(v.w, sc[c + 3], sh[c + 3]));
+    }
+    *reinterpret_cast<float4*>(tile + (size_t)pp * PS + c4 * 4) = v;
+  }
+  __syncthreads();
+  const int pix = threadIdx.x & 63, quarter = threadIdx.x >> 6;
+  const int py = pix >> 5, px = pix & 31;
+  const int cq = Cin >> 2;                                 // channels per quarter
+  float acc[COUT];
 #pragma unroll
-  for (int p = 0; p < 8; ++p)
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[p][c] = 0.f;
-  for (int cb = lane * 4; cb < Cin; cb += 128) {
+  for (int tap = 0; tap < 9; ++tap) {
+    const float* tp = tile + (size_t)((py + tap / 3) * (TW + 2) + px + tap % 3) * PS + quarter * cq;
+    const float* wp = ws + (size_t)tap * COUT * Cin + quarter * cq;
+    for (int c = 0; c < cq; c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(tp + c);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int gy = y + r - 1;
-      if (gy < 0 || gy >= H) continue;
-      float4 wv[3][COUT];
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int c = 0; c < COUT; ++c) wv[d][c] = *reinterpret_cast<const float4*>(&ws[((r * 3 + d) * COUT + c) * Cin + cb]);
-      const float* rowp = x + (((long long)n * H + gy) * W) * Cin + cb;
-#pragma unroll
-      for (int i = 0; i < 10; ++i) {  // input columns sx-1 .. sx+8
-        const int gx = sx + i - 1;
-        if (gx < 0 || gx >= W) continue;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(rowp + (long long)gx * Cin));
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const int p = i - d;  // output pixel that sees this column through horizontal tap d
-          if (p < 0 || p > 7) continue;
-#pragma unroll
-          for (int c = 0; c < COUT; ++c)
-            acc[p][c] += v.x * wv[d][c].x + v.y * wv[d][c].y + v.z * wv[d][c].z + v.w * wv[d][c].w;
-        }
+      for (int co = 0; co < COUT; ++co) {
+        const float4 ww = *reinterpret_cast<const float4*>(wp + (size_t)co * Cin + c);
+        acc[co] = fmaf(v.x, ww.x, fmaf(v.y, ww.y, fmaf(v.z, ww.z, fmaf(v.w, ww.w, acc[co]))));
       }
     }
   }
 #pragma unroll
-  for (int p = 0; p < 8; ++p)
-#pragma unroll
-    for (int c = 0; c < COUT; ++c) {
-      float v = acc[p][c];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      acc[p][c] = v;
-    }
-  if (lane < 8) {
-#pragma unroll
-    for (int c = 0; c < COUT; ++c) {
-      float v = 0.f;
-#pragma unroll
-      for (int p = 0; p < 8; ++p)
-        if (p == lane) v = acc[p][c];
-      out[(((long long)n * COUT + c) * H + y) * W + sx + lane] = v + bias[c];
+  for (int co = 0; co < COUT; ++co) red[(quarter * 64 + pix) * COUT + co] = acc[co];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * COUT; i += blockDim.x) {
+    const int p = i & 63, co = i >> 6;
+    const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
+    if (gy < H && gx < W) {
+      const float v = (red[(0 * 64 + p) * COUT + co] + red[(1 * 64 + p) * COUT + co]) +
+                      (red[(2 * 64 + p) * COUT + co] + red[(3 * 64 + p) * COUT + co]) + bias[co];
+      out[(((size_t)n * COUT + co) * H + gy) * W + gx] = v;
     }
   }
 }
 
-void conv3x3_small_cout(const float* x, int N, int H, int W, int Cin, const float* w, const float* bias, int Cout, float* out,
-                        cudaStream_t st) {
-  DDNM_CHECK(W % 8 == 0 && Cin % 4 == 0, "head convolution: W % 8, Cin % 4");
-  const long long strips = (long long)N * H * (W / 8);
-  const int grid = (int)cdivll(strips, 8);
-  const size_t smem = (size_t)9 * Cout * Cin * sizeof(float);
+void head_conv_gn_silu(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
+                       const float* w, const float* bias, int Cout, float* out_nchw, cudaStream_t st) {
+  DDNM_CHECK(x.C % 16 == 0 && x.ld % 4 == 0 && x.C % groups == 0, "head convolution: Cin % 16");
+  const size_t smem = ((size_t)4 * 34 * (x.C + 4) + (size_t)9 * Cout * x.C + 2 * x.C + 4 * 64 * Cout) * sizeof(float);
+  DDNM_CHECK(smem <= 227 * 1024, "head convolution tile does not fit shared memory");
+  dim3 grid(cdiv(x.W, 32), cdiv(x.H, 2), x.N);
   static size_t smem_set[2] = {0, 0};
   if (Cout == 3) {
     if (smem > smem_set[0]) {
-      CUDA_CHECK(cudaFuncSetAttribute(conv_small_cout_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_CHECK(cudaFuncSetAttribute(head_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set[0] = smem;
     }
-    conv_small_cout_kernel<3><<<grid, 256, smem, st>>>(x, w, bias, out, N, H, W, Cin);
+    head_conv_kernel<3><<<grid, 256, smem, st>>>(x.p, x.ld, x.N, x.H, x.W, x.C, groups, stats, gamma, beta, eps, w, bias, out_nchw);
   } else if (Cout == 6) {
     if (smem > smem_set[1]) {
-      CUDA_CHECK(cudaFuncSetAttribute(conv_small_cout_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_CHECK(cudaFuncSetAttribute(head_conv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set[1] = smem;
     }
-    conv_small_cout_kernel<6><<<grid, 256, smem, st>>>(x, w, bias, out, N, H, W, Cin);
+    head_conv_kernel<6><<<grid, 256, smem, st>>>(x.p, x.ld, x.N, x.H, x.W, x.C, groups, stats, gamma, beta, eps, w, bias, out_nchw);
   } else {
     throw Error("head convolution supports Cout 3 or 6");
   }
