@@ -17,6 +17,13 @@ class SimpleCfg(C.Structure):
                 ("in_channels", C.c_int), ("resolution", C.c_int), ("groups", C.c_int), ("eps", C.c_float)]
 
 
+class OpenAICfg(C.Structure):
+    _fields_ = [("image_size", C.c_int), ("model_channels", C.c_int), ("num_res_blocks", C.c_int), ("n_levels", C.c_int),
+                ("channel_mult", C.c_int * 8), ("n_attn_ds", C.c_int), ("attn_ds", C.c_int * 4),
+                ("num_head_channels", C.c_int), ("out_channels", C.c_int), ("in_channels", C.c_int), ("groups", C.c_int),
+                ("eps", C.c_float)]
+
+
 class OperatorDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("channels", C.c_int), ("img_dim", C.c_int), ("ratio", C.c_int),
                 ("v_small", C.c_void_p), ("u_small", C.c_void_p), ("singulars", C.c_void_p),
@@ -34,6 +41,7 @@ _P, _I, _LL, _F, _D = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 _SIGS = {
     "ddnm_version": (C.c_int, []),
     "ddnm_unet_simple_create": (C.c_int, [C.POINTER(SimpleCfg), _I, C.POINTER(_P)]),
+    "ddnm_unet_openai_create": (C.c_int, [C.POINTER(OpenAICfg), _I, C.POINTER(_P)]),
     "ddnm_unet_set_param": (C.c_int, [_P, C.c_char_p, _P, _LL]),
     "ddnm_unet_finalize": (C.c_int, [_P]),
     "ddnm_unet_forward": (C.c_int, [_P, _P, _P, _P, _P]),

@@ -32,38 +32,54 @@ int ddnm_unet_simple_create(const ddnm_simple_cfg* c, int batch, void** handle) 
   cfg.n_attn_res = c->n_attn_res;
   for (int i = 0; i < 4; ++i) cfg.attn_res[i] = c->attn_res[i];
   cfg.in_channels = c->in_channels; cfg.resolution = c->resolution; cfg.groups = c->groups; cfg.eps = c->eps;
-  *handle = new UNetSimple(cfg, batch);
+  *handle = static_cast<UNetEngine*>(new UNetSimple(cfg, batch));
+  DDNM_API_END
+}
+
+int ddnm_unet_openai_create(const ddnm_openai_cfg* c, int batch, void** handle) {
+  DDNM_API_BEGIN
+  DDNM_CHECK(c && handle, "null argument");
+  DDNM_CHECK(c->n_levels >= 1 && c->n_levels <= 8 && c->n_attn_ds >= 0 && c->n_attn_ds <= 4, "bad config");
+  OpenAICfg cfg;
+  cfg.image_size = c->image_size; cfg.model_channels = c->model_channels; cfg.num_res_blocks = c->num_res_blocks;
+  cfg.n_levels = c->n_levels;
+  for (int i = 0; i < 8; ++i) cfg.channel_mult[i] = c->channel_mult[i];
+  cfg.n_attn_ds = c->n_attn_ds;
+  for (int i = 0; i < 4; ++i) cfg.attn_ds[i] = c->attn_ds[i];
+  cfg.num_head_channels = c->num_head_channels; cfg.out_channels = c->out_channels; cfg.in_channels = c->in_channels;
+  cfg.groups = c->groups; cfg.eps = c->eps;
+  *handle = static_cast<UNetEngine*>(new UNetOpenAI(cfg, batch));
   DDNM_API_END
 }
 
 int ddnm_unet_set_param(void* h, const char* name, const float* data, long long numel) {
   DDNM_API_BEGIN
-  static_cast<UNetSimple*>(h)->set_param(name, data, numel);
+  static_cast<UNetEngine*>(h)->set_param(name, data, numel);
   DDNM_API_END
 }
 int ddnm_unet_finalize(void* h) {
   DDNM_API_BEGIN
-  static_cast<UNetSimple*>(h)->finalize();
+  static_cast<UNetEngine*>(h)->finalize();
   DDNM_API_END
 }
 int ddnm_unet_forward(void* h, const float* x, const float* t, float* out, void* stream) {
   DDNM_API_BEGIN
-  static_cast<UNetSimple*>(h)->forward(x, t, out, (cudaStream_t)stream);
+  static_cast<UNetEngine*>(h)->forward(x, t, out, (cudaStream_t)stream);
   DDNM_API_END
 }
 int ddnm_unet_set_graph(void* h, int on) {
   DDNM_API_BEGIN
-  static_cast<UNetSimple*>(h)->set_use_graph(on != 0);
+  static_cast<UNetEngine*>(h)->set_use_graph(on != 0);
   DDNM_API_END
 }
 int ddnm_unet_read_tap(void* h, const char* name, float* dst, long long cap, void* stream) {
   DDNM_API_BEGIN
-  DDNM_CHECK(static_cast<UNetSimple*>(h)->read_tap(name, dst, cap, (cudaStream_t)stream), std::string("unknown tap ") + name);
+  DDNM_CHECK(static_cast<UNetEngine*>(h)->read_tap(name, dst, cap, (cudaStream_t)stream), std::string("unknown tap ") + name);
   DDNM_API_END
 }
 int ddnm_unet_info(void* h, long long* ws, int* launches, double* flops) {
   DDNM_API_BEGIN
-  UNetSimple* u = static_cast<UNetSimple*>(h);
+  UNetEngine* u = static_cast<UNetEngine*>(h);
   if (ws) *ws = (long long)u->workspace_bytes();
   if (launches) *launches = u->num_launches();
   if (flops) *flops = u->flops_per_forward();
@@ -71,14 +87,14 @@ int ddnm_unet_info(void* h, long long* ws, int* launches, double* flops) {
 }
 int ddnm_unet_profile(void* h, const float* x, const float* t, float* out, void* stream, char* json, long long cap) {
   DDNM_API_BEGIN
-  std::string s = static_cast<UNetSimple*>(h)->profile(x, t, out, (cudaStream_t)stream);
+  std::string s = static_cast<UNetEngine*>(h)->profile(x, t, out, (cudaStream_t)stream);
   DDNM_CHECK((long long)s.size() + 1 <= cap, "json buffer too small");
   std::memcpy(json, s.c_str(), s.size() + 1);
   DDNM_API_END
 }
 int ddnm_unet_destroy(void* h) {
   DDNM_API_BEGIN
-  delete static_cast<UNetSimple*>(h);
+  delete static_cast<UNetEngine*>(h);
   DDNM_API_END
 }
 

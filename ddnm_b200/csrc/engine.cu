@@ -1,8 +1,8 @@
-// UNetSimple: launch program for guided_diffusion/models.py::Model (the celeba_hq.yml denoiser).
+// UNetEngine: what the two denoiser programs share — parameters, arena, scratch, op emitters, CUDA-graph replay.
 //
 // Data layout in HBM: activations fp32 NHWC; every skip tensor is born inside the channel slice of the concat
-// buffer its up-path consumer will read (torch.cat at models.py:331 costs nothing); the tensor-core convolutions
-// read fp16 (hi, lo) planes produced by the fused GroupNorm+SiLU+split pass.
+// buffer its up-path consumer will read (torch.cat at models.py:331 / unet.py:661 costs nothing); the tensor-core
+// convolutions read fp16 (hi, lo) planes produced by the fused GroupNorm+SiLU+split pass.
 #include "engine.cuh"
 
 #include <algorithm>
@@ -26,9 +26,9 @@ void* Arena::alloc(size_t bytes) {
   return p;
 }
 
-UNetSimple::UNetSimple(const SimpleCfg& cfg, int batch) : cfg_(cfg), B_(batch) {
+UNetEngine::UNetEngine(int batch, int in_channels, int out_ch, int resolution, int groups, float eps)
+    : B_(batch), in_ch_(in_channels), out_ch_(out_ch), R_(resolution), groups_(groups), eps_(eps) {
   DDNM_CHECK(batch >= 1, "batch must be positive");
-  DDNM_CHECK(cfg.ch % 64 == 0, "base channel count must be a multiple of 64 (tensor-core K blocks)");
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
   cudaDeviceProp prop;
@@ -37,13 +37,13 @@ UNetSimple::UNetSimple(const SimpleCfg& cfg, int batch) : cfg_(cfg), B_(batch) {
   num_sms_ = prop.multiProcessorCount;
 }
 
-UNetSimple::~UNetSimple() {
+UNetEngine::~UNetEngine() {
   if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
   if (graph_) cudaGraphDestroy(graph_);
   for (auto& kv : params_) cudaFree(kv.second.p);
 }
 
-void UNetSimple::set_param(const std::string& name, const float* data, long long numel) {
+void UNetEngine::set_param(const std::string& name, const float* data, long long numel) {
   DDNM_CHECK(!finalized_, "set_param after finalize");
   DDNM_CHECK(numel > 0 && data != nullptr, "empty parameter " + name);
   float* d = nullptr;
@@ -54,7 +54,7 @@ void UNetSimple::set_param(const std::string& name, const float* data, long long
   params_[name] = Param{d, numel};
 }
 
-const float* UNetSimple::P(const std::string& name, long long expect) const {
+const float* UNetEngine::P(const std::string& name, long long expect) const {
   auto it = params_.find(name);
   DDNM_CHECK(it != params_.end(), "missing parameter '" + name + "'");
   if (expect >= 0)
@@ -63,43 +63,31 @@ const float* UNetSimple::P(const std::string& name, long long expect) const {
   return it->second.p;
 }
 
-View UNetSimple::new_view(int H, int W, int C) {
+View UNetEngine::new_view(int H, int W, int C) {
   View v;
   v.N = B_; v.H = H; v.W = W; v.C = C; v.ld = C;
   v.p = (float*)arena_.alloc((size_t)B_ * H * W * C * sizeof(float));
   return v;
 }
 
-double* UNetSimple::new_stats() {
+double* UNetEngine::new_stats() {
   DDNM_CHECK(stats_count_ < stats_cap_, "stats pool exhausted");
-  return stats_base_ + (stats_count_++) * (size_t)B_ * cfg_.groups * 2;
+  return stats_base_ + (stats_count_++) * (size_t)B_ * groups_ * 2;
 }
 
-UNetSimple::TcWeights UNetSimple::prep_weights(const std::string& main, int Cout, int Cin, int taps, const std::string& side,
+UNetEngine::TcWeights UNetEngine::prep_weights(const std::string& main, int Cout, int Cin, int taps, const std::string& side,
                                                int CinSide) {
   TcWeights w;
   w.ktot = taps * Cin + CinSide;
   const size_t n = (size_t)Cout * w.ktot;
   w.hi = (__half*)arena_.alloc(n * sizeof(__half));
   w.lo = (__half*)arena_.alloc(n * sizeof(__half));
-  split_conv_weight(P(main + ".weight", (long long)Cout * Cin * taps), Cout, Cin, taps, w.hi, w.lo, w.ktot, 0, 0);
-  if (CinSide) split_conv_weight(P(side + ".weight", (long long)Cout * CinSide), Cout, CinSide, 1, w.hi, w.lo, w.ktot, taps * Cin, 0);
+  split_conv_weight(P(main, (long long)Cout * Cin * taps), Cout, Cin, taps, w.hi, w.lo, w.ktot, 0, 0);
+  if (CinSide) split_conv_weight(P(side, (long long)Cout * CinSide), Cout, CinSide, 1, w.hi, w.lo, w.ktot, taps * Cin, 0);
   return w;
 }
 
-UNetSimple::TcWeights UNetSimple::prep_qkv(const std::string& p, int C) {
-  TcWeights w;
-  w.ktot = C;
-  const size_t n = (size_t)3 * C * C;
-  w.hi = (__half*)arena_.alloc(n * sizeof(__half));
-  w.lo = (__half*)arena_.alloc(n * sizeof(__half));
-  const char* nm[3] = {".q", ".k", ".v"};
-  for (int i = 0; i < 3; ++i)
-    split_conv_weight(P(p + nm[i] + ".weight", (long long)C * C), C, C, 1, w.hi + (size_t)i * C * C, w.lo + (size_t)i * C * C, C, 0, 0);
-  return w;
-}
-
-const float* UNetSimple::bias_sum(const std::string& a, const std::string& b, int C) {
+const float* UNetEngine::bias_sum(const std::string& a, const std::string& b, int C) {
   std::vector<float> ha(C), hb(C, 0.f);
   CUDA_CHECK(cudaMemcpy(ha.data(), P(a, C), C * sizeof(float), cudaMemcpyDeviceToHost));
   if (!b.empty()) CUDA_CHECK(cudaMemcpy(hb.data(), P(b, C), C * sizeof(float), cudaMemcpyDeviceToHost));
@@ -109,31 +97,38 @@ const float* UNetSimple::bias_sum(const std::string& a, const std::string& b, in
   return d;
 }
 
-void UNetSimple::add_op(const std::string& name, const std::string& kind, double flops, double bytes,
+float* UNetEngine::dev_copy(const std::vector<float>& v) {
+  float* d = (float*)arena_.alloc(v.size() * sizeof(float));
+  CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return d;
+}
+
+void UNetEngine::add_op(const std::string& name, const std::string& kind, double flops, double bytes,
                         std::function<void(cudaStream_t)> f) {
   ops_.push_back(OpRecord{name, kind, flops, bytes, std::move(f)});
 }
 
 // GroupNorm(+SiLU) + fp16 split of x into scratch planes dst (dims as the consuming convolution sees them)
-void UNetSimple::emit_gn_split(const std::string& name, const View& x, const std::string& norm, bool silu, int mode,
-                               SplitView& dst) {
-  const long long out_elems = x.pixels() * x.C * (mode == SPLIT_UP2 ? 4 : 1);
+void UNetEngine::emit_gn_split(const std::string& name, const View& x, const std::string& norm, bool silu, int mode,
+                               SplitView& dst, const float* ss, int ss_ld) {
+  const long long out_elems = mode == SPLIT_UP2 ? x.pixels() * x.C * 4 : (mode == SPLIT_AVG2 ? x.pixels() * x.C / 4 : x.pixels() * x.C);
   DDNM_CHECK((size_t)out_elems <= split_elems_, "split scratch too small");
   dst.C = x.C;
   if (mode == SPLIT_SAME) { dst.N = x.N; dst.H = x.H; dst.W = x.W; }
   else if (mode == SPLIT_UP2) { dst.N = x.N; dst.H = 2 * x.H; dst.W = 2 * x.W; }
+  else if (mode == SPLIT_AVG2) { dst.N = x.N; dst.H = x.H / 2; dst.W = x.W / 2; }
   else { dst.N = 4 * x.N; dst.H = x.H / 2; dst.W = x.W / 2; }
   const double in_bytes = (double)x.pixels() * x.C * 4;
   if (!norm.empty()) {
     double* st = new_stats();
     const float* g = P(norm + ".weight", x.C);
     const float* b = P(norm + ".bias", x.C);
-    const int groups = cfg_.groups;
-    const float eps = cfg_.eps;
+    const int groups = groups_;
+    const float eps = eps_;
     add_op(name + ".gn_stats", "gn_stats", 0, in_bytes, [=](cudaStream_t s) { gn_stats(x, groups, st, s); });
     __half *hi = dst.hi, *lo = dst.lo;
     add_op(name + ".gn_split", "gn_split", 0, in_bytes + out_elems * 4.0,
-           [=](cudaStream_t s) { gn_apply_split(x, groups, st, g, b, eps, silu, mode, hi, lo, s); });
+           [=](cudaStream_t s) { gn_apply_split(x, groups, st, g, b, eps, silu, mode, hi, lo, s, ss, ss_ld); });
   } else {
     __half *hi = dst.hi, *lo = dst.lo;
     add_op(name + ".split", "gn_split", 0, in_bytes + out_elems * 4.0,
@@ -141,343 +136,72 @@ void UNetSimple::emit_gn_split(const std::string& name, const View& x, const std
   }
 }
 
-void UNetSimple::emit_tc(const std::string& name, const SplitView& a, int mode, const SplitView* side, const TcWeights& w,
-                         int Cout, const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr) {
-  TcLaunch L = tc_make_launch(a, mode, side, w.hi, w.lo, 1, Cout, out, chanadd, ca_ld, residual, ldr, 1.0f, num_sms_);
+void UNetEngine::emit_tc(const std::string& name, const SplitView& a, int mode, const SplitView* side, const TcWeights& w,
+                         int Cout, const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr, int res_mode) {
+  TcLaunch L = tc_make_launch(a, mode, side, w.hi, w.lo, 1, Cout, out, chanadd, ca_ld, residual, ldr, 1.0f, num_sms_, res_mode);
   const double bytes = (double)a.N * a.H * a.W * a.C * 4 + (side ? (double)side->N * side->H * side->W * side->C * 4 : 0) +
                        (double)Cout * w.ktot * 4 + (double)out.pixels() * Cout * 4 * (residual ? 2 : 1);
   add_op(name, "tc", L.flops, bytes, [L](cudaStream_t s) { tc_run(L, s); });
 }
 
-// ResnetBlock (models.py:115-134)
-void UNetSimple::emit_resblock(const std::string& p, const View& x, const View& out) {
-  const int Cin = x.C, Cout = out.C;
-  DDNM_CHECK((size_t)(x.pixels() * Cout) <= hbuf_elems_, "hbuf too small");
-  SplitView A{splitA_hi_, splitA_lo_}, Bs{splitB_hi_, splitB_lo_};
-  emit_gn_split(p + ".norm1", x, p + ".norm1", true, SPLIT_SAME, A);
-  TcWeights w1 = prep_weights(p + ".conv1", Cout, Cin, 9, "", 0);
-  View h;
-  h.p = hbuf_; h.N = B_; h.H = x.H; h.W = x.W; h.C = Cout; h.ld = Cout;
-  emit_tc(p + ".conv1", A, TAPS_3X3, nullptr, w1, Cout, h, ca_all_ + ca_off_.at(p), ca_total_, nullptr, 0);
-  emit_gn_split(p + ".norm2", h, p + ".norm2", true, SPLIT_SAME, A);
-  if (Cin != Cout) {
-    // nin_shortcut (1x1 on the raw block input) rides along as extra K blocks of conv2's GEMM
-    emit_gn_split(p + ".nin_in", x, "", false, SPLIT_SAME, Bs);
-    TcWeights w2 = prep_weights(p + ".conv2", Cout, Cout, 9, p + ".nin_shortcut", Cin);
-    emit_tc(p + ".conv2+nin", A, TAPS_3X3, &Bs, w2, Cout, out, bias_sum(p + ".conv2.bias", p + ".nin_shortcut.bias", Cout), 0,
-            nullptr, 0);
-  } else {
-    TcWeights w2 = prep_weights(p + ".conv2", Cout, Cout, 9, "", 0);
-    emit_tc(p + ".conv2", A, TAPS_3X3, nullptr, w2, Cout, out, P(p + ".conv2.bias", Cout), 0, x.p, x.ld);
-  }
+// scratch every program needs; split planes are shared by all convolutions of a forward (stream order serialises them)
+void UNetEngine::alloc_common(size_t split_elems, size_t hbuf_elems, int n_gn) {
+  split_elems_ = split_elems;
+  hbuf_elems_ = hbuf_elems;
+  splitA_hi_ = (__half*)arena_.alloc(split_elems * 2);
+  splitA_lo_ = (__half*)arena_.alloc(split_elems * 2);
+  splitB_hi_ = (__half*)arena_.alloc(split_elems * 2);
+  splitB_lo_ = (__half*)arena_.alloc(split_elems * 2);
+  hbuf_ = (float*)arena_.alloc(hbuf_elems * 4);
+  stats_cap_ = n_gn;
+  stats_base_ = (double*)arena_.alloc((size_t)n_gn * B_ * groups_ * 2 * sizeof(double));
+  x_in_ = (float*)arena_.alloc((size_t)B_ * in_ch_ * R_ * R_ * 4);
+  t_in_ = (float*)arena_.alloc((size_t)B_ * 4);
+  out_ = (float*)arena_.alloc((size_t)B_ * out_ch_ * R_ * R_ * 4);
+  double* sb = stats_base_;
+  const size_t sbytes = (size_t)n_gn * B_ * groups_ * 2 * sizeof(double);
+  add_op("stats.zero", "memset", 0, (double)sbytes, [=](cudaStream_t s) { CUDA_CHECK(cudaMemsetAsync(sb, 0, sbytes, s)); });
 }
 
-// AttnBlock (models.py:164-189): single head over T = H*W tokens, head dim = C
-void UNetSimple::emit_attn(const std::string& p, const View& x, const View& out) {
-  const int C = x.C, T = x.H * x.W;
-  SplitView A{splitA_hi_, splitA_lo_};
-  emit_gn_split(p + ".norm", x, p + ".norm", false, SPLIT_SAME, A);
-  TcWeights wqkv = prep_qkv(p, C);
-  std::vector<float> hb(3 * C);
-  const char* nm[3] = {".q.bias", ".k.bias", ".v.bias"};
-  for (int i = 0; i < 3; ++i) CUDA_CHECK(cudaMemcpy(hb.data() + i * C, P(p + nm[i], C), C * sizeof(float), cudaMemcpyDeviceToHost));
-  float* bqkv = (float*)arena_.alloc(3 * C * sizeof(float));
-  CUDA_CHECK(cudaMemcpy(bqkv, hb.data(), 3 * C * sizeof(float), cudaMemcpyHostToDevice));
-  View qkv;
-  qkv.p = qkv_; qkv.N = B_; qkv.H = x.H; qkv.W = x.W; qkv.C = 3 * C; qkv.ld = 3 * C;
-  emit_tc(p + ".qkv", A, TAPS_1X1, nullptr, wqkv, 3 * C, qkv, bqkv, 0, nullptr, 0);
-  float *q = qkv_, *S = attS_, *O = attO_;
-  const int Bn = B_;
-  const float scale = 1.0f / sqrtf((float)C);  // int(c) ** (-0.5)
-  add_op(p + ".qk", "sgemm", 2.0 * Bn * T * (double)T * C, (double)Bn * T * (2.0 * C + T) * 4, [=](cudaStream_t s) {
-    sgemm_batched(true, Bn, T, T, C, scale, q, 3 * C, (long long)T * 3 * C, q + C, 3 * C, (long long)T * 3 * C, S, T, (long long)T * T, s);
-  });
-  add_op(p + ".softmax", "softmax", 0, (double)Bn * T * T * 8, [=](cudaStream_t s) { softmax_rows(S, (long long)Bn * T, T, s); });
-  add_op(p + ".pv", "sgemm", 2.0 * Bn * T * (double)T * C, (double)Bn * T * (2.0 * C + T) * 4, [=](cudaStream_t s) {
-    sgemm_batched(false, Bn, T, C, T, 1.0f, S, T, (long long)T * T, q + 2 * C, 3 * C, (long long)T * 3 * C, O, C, (long long)T * C, s);
-  });
-  View ov;
-  ov.p = attO_; ov.N = B_; ov.H = x.H; ov.W = x.W; ov.C = C; ov.ld = C;
-  emit_gn_split(p + ".proj_in", ov, "", false, SPLIT_SAME, A);
-  TcWeights wp = prep_weights(p + ".proj_out", C, C, 1, "", 0);
-  emit_tc(p + ".proj_out", A, TAPS_1X1, nullptr, wp, C, out, P(p + ".proj_out.bias", C), 0, x.p, x.ld);
+// network stem: 3x3 conv on the caller's NCHW tensor -> NHWC view
+void UNetEngine::emit_stem(const std::string& wname, const View& out) {
+  const float* xin = x_in_;
+  const float *w = P(wname + ".weight", (long long)out.C * in_ch_ * 9), *b = P(wname + ".bias", out.C);
+  const int cin = in_ch_;
+  add_op("stem", "stem", 2.0 * B_ * R_ * R_ * (double)out.C * cin * 9, (double)B_ * R_ * R_ * (cin + out.C) * 4,
+         [=](cudaStream_t s) { conv3x3_small_cin(xin, cin, w, b, out, s); });
 }
 
-// Downsample (models.py:67-71): pad (0,1,0,1) + 3x3 stride 2
-void UNetSimple::emit_downsample(const std::string& p, const View& x, const View& out) {
-  SplitView A{splitA_hi_, splitA_lo_};
-  emit_gn_split(p + ".s2d", x, "", false, SPLIT_S2D, A);
-  TcWeights w = prep_weights(p + ".conv", x.C, x.C, 9, "", 0);
-  emit_tc(p + ".conv", A, TAPS_3X3_S2, nullptr, w, x.C, out, P(p + ".conv.bias", x.C), 0, nullptr, 0);
+// network head: GroupNorm + SiLU + 3x3 conv to out_ch, NCHW result
+void UNetEngine::emit_head(const std::string& norm, const std::string& conv, const View& fh) {
+  double* st = new_stats();
+  const float *g = P(norm + ".weight", fh.C), *b = P(norm + ".bias", fh.C);
+  const int groups = groups_;
+  const float eps = eps_;
+  const double ab = (double)fh.pixels() * fh.C * 4;
+  add_op("head.gn_stats", "gn_stats", 0, ab, [=](cudaStream_t s) { gn_stats(fh, groups, st, s); });
+  const float *w = P(conv + ".weight", (long long)out_ch_ * fh.C * 9), *bo = P(conv + ".bias", out_ch_);
+  float* o = out_;
+  const int oc = out_ch_;
+  add_op("head.norm+conv", "head", 2.0 * fh.pixels() * (double)oc * fh.C * 9, ab + (double)fh.pixels() * oc * 4,
+         [=](cudaStream_t s) { head_conv_gn_silu(fh, groups, st, g, b, eps, w, bo, oc, o, s); });
 }
 
-// Upsample (models.py:47-52): nearest x2 + 3x3
-void UNetSimple::emit_upsample(const std::string& p, const View& x, const View& out) {
-  SplitView A{splitA_hi_, splitA_lo_};
-  emit_gn_split(p + ".up2", x, "", false, SPLIT_UP2, A);
-  TcWeights w = prep_weights(p + ".conv", x.C, x.C, 9, "", 0);
-  emit_tc(p + ".conv", A, TAPS_3X3, nullptr, w, x.C, out, P(p + ".conv.bias", x.C), 0, nullptr, 0);
-}
-
-void UNetSimple::finalize() {
+void UNetEngine::finalize() {
   DDNM_CHECK(!finalized_, "finalize called twice");
   build_program();
   CUDA_CHECK(cudaDeviceSynchronize());
   finalized_ = true;
 }
 
-void UNetSimple::build_program() {
-  const SimpleCfg& c = cfg_;
-  const int L = c.n_levels, R = c.resolution, nrb = c.num_res_blocks;
-  auto has_attn = [&](int res) {
-    for (int i = 0; i < c.n_attn_res; ++i)
-      if (c.attn_res[i] == res) return true;
-    return false;
-  };
-  auto mult = [&](int lv) { return c.ch * c.ch_mult[lv]; };
-  auto in_mult = [&](int lv) { return lv == 0 ? c.ch : c.ch * c.ch_mult[lv - 1]; };
-
-  // ---- plan shapes: the hs stack (models.py:311-319) and the up-path concat buffers (:328-335) ----
-  struct HS { int res, C; };
-  std::vector<HS> hs_shape;
-  hs_shape.push_back({R, c.ch});
-  {
-    int res = R;
-    for (int lv = 0; lv < L; ++lv) {
-      for (int ib = 0; ib < nrb; ++ib) hs_shape.push_back({res, mult(lv)});
-      if (lv != L - 1) {
-        res /= 2;
-        hs_shape.push_back({res, mult(lv)});
-      }
-    }
-  }
-  const int n_up = L * (nrb + 1);
-  DDNM_CHECK((int)hs_shape.size() == n_up, "skip stack / up-block count mismatch");
-  struct UpB { int lv, ib, res, Ch, Cs, Cout; };
-  std::vector<UpB> upb;
-  {
-    int res = R >> (L - 1);
-    int block_in = mult(L - 1);
-    for (int lv = L - 1; lv >= 0; --lv) {
-      for (int ib = 0; ib <= nrb; ++ib) {
-        const int skip = (ib == nrb) ? in_mult(lv) : mult(lv);
-        upb.push_back({lv, ib, res, block_in, skip, mult(lv)});
-        block_in = mult(lv);
-      }
-      if (lv != 0) res *= 2;
-    }
-    for (int u = 0; u < n_up; ++u) {
-      const HS& h = hs_shape[n_up - 1 - u];
-      DDNM_CHECK(h.res == upb[u].res && h.C == upb[u].Cs, "skip shape does not match its up block");
-    }
-  }
-
-  // ---- scratch sizing ----
-  size_t split_max = 0, hbuf_max = 0, att_tok = 0, att_c = 0, att_T = 0;
-  int n_gn = 0;
-  std::vector<std::string> rb_names;
-  std::vector<int> rb_cout;
-  auto plan_conv_in = [&](int res, int Cin, bool up2) {
-    split_max = std::max(split_max, (size_t)B_ * res * res * Cin * (up2 ? 4 : 1));
-  };
-  auto plan_rb = [&](const std::string& p, int res, int Cin, int Cout) {
-    plan_conv_in(res, Cin, false);
-    plan_conv_in(res, Cout, false);
-    hbuf_max = std::max(hbuf_max, (size_t)B_ * res * res * Cout);
-    n_gn += 2;
-    rb_names.push_back(p);
-    rb_cout.push_back(Cout);
-  };
-  auto plan_attn = [&](int res, int C) {
-    plan_conv_in(res, C, false);
-    att_tok = std::max(att_tok, (size_t)res * res);
-    att_c = std::max(att_c, (size_t)C);
-    att_T = std::max(att_T, (size_t)res * res);
-    n_gn += 1;
-  };
-  {
-    int res = R;
-    for (int lv = 0; lv < L; ++lv) {
-      int cin = in_mult(lv);
-      for (int ib = 0; ib < nrb; ++ib) {
-        plan_rb("down." + std::to_string(lv) + ".block." + std::to_string(ib), res, cin, mult(lv));
-        cin = mult(lv);
-        if (has_attn(res)) plan_attn(res, cin);
-      }
-      if (lv != L - 1) {
-        plan_conv_in(res, cin, false);
-        res /= 2;
-      }
-    }
-    plan_rb("mid.block_1", res, mult(L - 1), mult(L - 1));
-    plan_attn(res, mult(L - 1));
-    plan_rb("mid.block_2", res, mult(L - 1), mult(L - 1));
-    for (const UpB& u : upb) {
-      plan_rb("up." + std::to_string(u.lv) + ".block." + std::to_string(u.ib), u.res, u.Ch + u.Cs, u.Cout);
-      if (has_attn(u.res)) plan_attn(u.res, u.Cout);
-      if (u.ib == nrb && u.lv != 0) plan_conv_in(u.res, u.Cout, true);
-    }
-    n_gn += 1;  // norm_out
-  }
-  split_elems_ = split_max;
-  hbuf_elems_ = hbuf_max;
-  splitA_hi_ = (__half*)arena_.alloc(split_max * 2);
-  splitA_lo_ = (__half*)arena_.alloc(split_max * 2);
-  splitB_hi_ = (__half*)arena_.alloc(split_max * 2);
-  splitB_lo_ = (__half*)arena_.alloc(split_max * 2);
-  hbuf_ = (float*)arena_.alloc(hbuf_max * 4);
-  qkv_ = (float*)arena_.alloc((size_t)B_ * att_tok * 3 * att_c * 4);
-  attS_ = (float*)arena_.alloc((size_t)B_ * att_T * att_T * 4);
-  attO_ = (float*)arena_.alloc((size_t)B_ * att_tok * att_c * 4);
-  stats_cap_ = n_gn;
-  stats_base_ = (double*)arena_.alloc((size_t)n_gn * B_ * c.groups * 2 * sizeof(double));
-  x_in_ = (float*)arena_.alloc((size_t)B_ * c.in_channels * R * R * 4);
-  t_in_ = (float*)arena_.alloc((size_t)B_ * 4);
-  out_ = (float*)arena_.alloc((size_t)B_ * c.out_ch * R * R * 4);
-
-  // ---- timestep embedding MLP + all per-block projections as one matrix (models.py:305-308, :121) ----
-  const int tch = c.ch * 4;
-  emb_ = (float*)arena_.alloc((size_t)B_ * c.ch * 4);
-  temb0_ = (float*)arena_.alloc((size_t)B_ * tch * 4);
-  temb_ = (float*)arena_.alloc((size_t)B_ * tch * 4);
-  freq_ = (float*)arena_.alloc((size_t)(c.ch / 2) * 4);
-  CUDA_CHECK(cudaMemcpy(freq_, P("__freq", c.ch / 2), (c.ch / 2) * 4, cudaMemcpyDeviceToDevice));
-  ca_total_ = 0;
-  for (size_t i = 0; i < rb_names.size(); ++i) {
-    ca_off_[rb_names[i]] = ca_total_;
-    ca_total_ += rb_cout[i];
-  }
-  tembW_all_ = (float*)arena_.alloc((size_t)ca_total_ * tch * 4);
-  tembB_all_ = (float*)arena_.alloc((size_t)ca_total_ * 4);
-  ca_all_ = (float*)arena_.alloc((size_t)B_ * ca_total_ * 4);
-  for (size_t i = 0; i < rb_names.size(); ++i) {
-    const std::string& p = rb_names[i];
-    const int off = ca_off_[p], co = rb_cout[i];
-    CUDA_CHECK(cudaMemcpy(tembW_all_ + (size_t)off * tch, P(p + ".temb_proj.weight", (long long)co * tch), (size_t)co * tch * 4,
-                          cudaMemcpyDeviceToDevice));
-    // conv1.bias joins the projection bias: both are added to every pixel of conv1's output (models.py:119,121)
-    const float* bs = bias_sum(p + ".temb_proj.bias", p + ".conv1.bias", co);
-    CUDA_CHECK(cudaMemcpy(tembB_all_ + off, bs, (size_t)co * 4, cudaMemcpyDeviceToDevice));
-  }
-
-  // ---- program ----
-  {
-    double* sb = stats_base_;
-    const size_t sbytes = (size_t)n_gn * B_ * c.groups * 2 * sizeof(double);
-    add_op("stats.zero", "memset", 0, (double)sbytes, [=](cudaStream_t s) { CUDA_CHECK(cudaMemsetAsync(sb, 0, sbytes, s)); });
-    float *t = t_in_, *emb = emb_, *t0 = temb0_, *t1 = temb_, *fr = freq_, *ca = ca_all_, *W = tembW_all_, *Bv = tembB_all_;
-    const float *w0 = P("temb.dense.0.weight", (long long)tch * c.ch), *b0 = P("temb.dense.0.bias", tch);
-    const float *w1 = P("temb.dense.1.weight", (long long)tch * tch), *b1 = P("temb.dense.1.bias", tch);
-    const int Bn = B_, chn = c.ch, cat = ca_total_;
-    add_op("temb", "temb", 0, 0, [=](cudaStream_t s) {
-      sinusoid(t, Bn, fr, chn, true, emb, s);
-      linear(emb, Bn, chn, w0, b0, tch, t0, tch, 0, 0, s);
-      linear(t0, Bn, tch, w1, b1, tch, t1, tch, 1, 0, s);
-      linear(t1, Bn, tch, W, Bv, cat, ca, cat, 1, 0, s);  // every block applies nonlinearity(temb) first
-    });
-  }
-  // concat buffers for the up path; hs[i] lives in cat[n_up-1-i].slice(Ch, Cs)
-  std::vector<View> cat(n_up);
-  for (int u = 0; u < n_up; ++u) cat[u] = new_view(upb[u].res, upb[u].res, upb[u].Ch + upb[u].Cs);
-  auto hs_slot = [&](int i) {
-    const int u = n_up - 1 - i;
-    return cat[u].slice(upb[u].Ch, upb[u].Cs);
-  };
-  std::vector<View> hs;
-  {
-    View v0 = hs_slot(0);
-    const float* xin = x_in_;
-    const float *w = P("conv_in.weight", (long long)c.ch * c.in_channels * 9), *b = P("conv_in.bias", c.ch);
-    const int cin = c.in_channels;
-    add_op("conv_in", "stem", 2.0 * B_ * R * R * (double)c.ch * cin * 9, (double)B_ * R * R * (cin + c.ch) * 4,
-           [=](cudaStream_t s) { conv3x3_small_cin(xin, cin, w, b, v0, s); });
-    hs.push_back(v0);
-    taps_["conv_in"] = v0;
-  }
-  int res = R;
-  for (int lv = 0; lv < L; ++lv) {
-    for (int ib = 0; ib < nrb; ++ib) {
-      const std::string p = "down." + std::to_string(lv) + ".block." + std::to_string(ib);
-      View slot = hs_slot((int)hs.size());
-      if (has_attn(res)) {
-        View tmp = new_view(res, res, mult(lv));
-        emit_resblock(p, hs.back(), tmp);
-        emit_attn("down." + std::to_string(lv) + ".attn." + std::to_string(ib), tmp, slot);
-      } else {
-        emit_resblock(p, hs.back(), slot);
-      }
-      hs.push_back(slot);
-      taps_["down." + std::to_string(lv) + "." + std::to_string(ib)] = slot;
-    }
-    if (lv != L - 1) {
-      View slot = hs_slot((int)hs.size());
-      emit_downsample("down." + std::to_string(lv) + ".downsample", hs.back(), slot);
-      hs.push_back(slot);
-      taps_["down." + std::to_string(lv) + ".ds"] = slot;
-      res /= 2;
-    }
-  }
-  {
-    const int C = mult(L - 1);
-    View m1 = new_view(res, res, C), m2 = new_view(res, res, C);
-    emit_resblock("mid.block_1", hs.back(), m1);
-    taps_["mid.block_1"] = m1;
-    emit_attn("mid.attn_1", m1, m2);
-    taps_["mid.attn_1"] = m2;
-    View dst = cat[0].slice(0, upb[0].Ch);
-    emit_resblock("mid.block_2", m2, dst);
-    taps_["mid.block_2"] = dst;
-  }
-  View final_h;
-  for (int u = 0; u < n_up; ++u) {
-    const UpB& ub = upb[u];
-    const std::string p = "up." + std::to_string(ub.lv) + ".block." + std::to_string(ub.ib);
-    const bool attn = has_attn(ub.res);
-    const bool last_in_level = ub.ib == nrb;
-    const bool upsample_next = last_in_level && ub.lv != 0;
-    View dest;
-    if (u == n_up - 1) dest = new_view(ub.res, ub.res, ub.Cout);
-    else if (upsample_next) dest = new_view(ub.res, ub.res, ub.Cout);
-    else dest = cat[u + 1].slice(0, upb[u + 1].Ch);
-    if (attn) {
-      View tmp = new_view(ub.res, ub.res, ub.Cout);
-      emit_resblock(p, cat[u], tmp);
-      emit_attn("up." + std::to_string(ub.lv) + ".attn." + std::to_string(ub.ib), tmp, dest);
-    } else {
-      emit_resblock(p, cat[u], dest);
-    }
-    taps_["up." + std::to_string(ub.lv) + "." + std::to_string(ub.ib)] = dest;
-    if (upsample_next) {
-      View d2 = cat[u + 1].slice(0, upb[u + 1].Ch);
-      emit_upsample("up." + std::to_string(ub.lv) + ".upsample", dest, d2);
-      taps_["up." + std::to_string(ub.lv) + ".us"] = d2;
-    }
-    if (u == n_up - 1) final_h = dest;
-  }
-  {
-    double* st = new_stats();
-    const float *g = P("norm_out.weight", final_h.C), *b = P("norm_out.bias", final_h.C);
-    const int groups = c.groups;
-    const float eps = c.eps;
-    const View fh = final_h;
-    const double ab = (double)fh.pixels() * fh.C * 4;
-    add_op("norm_out.gn_stats", "gn_stats", 0, ab, [=](cudaStream_t s) { gn_stats(fh, groups, st, s); });
-    const float *w = P("conv_out.weight", (long long)c.out_ch * fh.C * 9), *bo = P("conv_out.bias", c.out_ch);
-    float* o = out_;
-    const int Bn = B_, oc = c.out_ch, Cin = fh.C, Rr = R;
-    add_op("norm_out+conv_out", "head", 2.0 * Bn * Rr * Rr * (double)oc * Cin * 9, ab + (double)Bn * Rr * Rr * oc * 4,
-           [=](cudaStream_t s) { head_conv_gn_silu(fh, groups, st, g, b, eps, w, bo, oc, o, s); });
-  }
-}
-
-void UNetSimple::run_ops(cudaStream_t s) {
+void UNetEngine::run_ops(cudaStream_t s) {
   for (auto& op : ops_) op.run(s);
 }
 
-void UNetSimple::forward(const float* x, const float* t, float* out, cudaStream_t stream) {
+void UNetEngine::forward(const float* x, const float* t, float* out, cudaStream_t stream) {
   DDNM_CHECK(finalized_, "forward before finalize");
-  const size_t xin = (size_t)B_ * cfg_.in_channels * cfg_.resolution * cfg_.resolution * 4;
-  const size_t xout = (size_t)B_ * cfg_.out_ch * cfg_.resolution * cfg_.resolution * 4;
+  const size_t xin = (size_t)B_ * in_ch_ * R_ * R_ * 4;
+  const size_t xout = (size_t)B_ * out_ch_ * R_ * R_ * 4;
   if (x != x_in_) CUDA_CHECK(cudaMemcpyAsync(x_in_, x, xin, cudaMemcpyDeviceToDevice, stream));
   if (t != t_in_) CUDA_CHECK(cudaMemcpyAsync(t_in_, t, (size_t)B_ * 4, cudaMemcpyDeviceToDevice, stream));
   if (use_graph_) {
@@ -510,7 +234,7 @@ void UNetSimple::forward(const float* x, const float* t, float* out, cudaStream_
   if (out != out_) CUDA_CHECK(cudaMemcpyAsync(out, out_, xout, cudaMemcpyDeviceToDevice, stream));
 }
 
-bool UNetSimple::read_tap(const std::string& name, float* dst, long long capacity, cudaStream_t stream) {
+bool UNetEngine::read_tap(const std::string& name, float* dst, long long capacity, cudaStream_t stream) {
   auto it = taps_.find(name);
   if (it == taps_.end()) return false;
   const View& v = it->second;
@@ -519,13 +243,13 @@ bool UNetSimple::read_tap(const std::string& name, float* dst, long long capacit
   return true;
 }
 
-double UNetSimple::flops_per_forward() const {
+double UNetEngine::flops_per_forward() const {
   double f = 0;
   for (auto& op : ops_) f += op.flops;
   return f;
 }
 
-std::string UNetSimple::profile(const float* x, const float* t, float* out, cudaStream_t stream) {
+std::string UNetEngine::profile(const float* x, const float* t, float* out, cudaStream_t stream) {
   const bool g = use_graph_;
   use_graph_ = false;
   forward(x, t, out, stream);  // warm

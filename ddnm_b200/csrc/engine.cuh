@@ -1,5 +1,7 @@
-// The denoiser engine: a static launch program for the "simple" DDPM UNet (guided_diffusion/models.py Model),
-// built once per (config, batch) and replayed as a CUDA graph.
+// The denoiser engines: static launch programs for the two UNets on the reference's hot path
+//   UNetSimple  <- guided_diffusion/models.py::Model      (celeba_hq.yml, model.type == "simple")
+//   UNetOpenAI  <- guided_diffusion/unet.py::UNetModel    (imagenet_256.yml, model.type == "openai")
+// built once per (config, batch) and replayed as a CUDA graph.  UNetEngine holds everything they share.
 #pragma once
 #include <functional>
 #include <map>
@@ -41,10 +43,20 @@ struct OpRecord {
   std::function<void(cudaStream_t)> run;
 };
 
-class UNetSimple {
+struct OpenAICfg {
+  int image_size = 256, model_channels = 256, num_res_blocks = 2, n_levels = 6;
+  int channel_mult[8] = {1, 1, 2, 2, 4, 4, 0, 0};
+  int n_attn_ds = 3;
+  int attn_ds[4] = {8, 16, 32, 0};   // downsample rates at which attention runs (image_size // resolution)
+  int num_head_channels = 64;
+  int out_channels = 6, in_channels = 3, groups = 32;
+  float eps = 1e-5f;
+};
+
+class UNetEngine {
  public:
-  UNetSimple(const SimpleCfg& cfg, int batch);
-  ~UNetSimple();
+  UNetEngine(int batch, int in_channels, int out_ch, int resolution, int groups, float eps);
+  virtual ~UNetEngine();
   void set_param(const std::string& name, const float* data, long long numel);
   void finalize();
   // x: [B,3,R,R] NCHW fp32, t: [B] fp32 (device), out: [B,out_ch,R,R] NCHW fp32 (device)
@@ -54,38 +66,45 @@ class UNetSimple {
   // per-op timing of one eager (non-graph) forward; returns JSON
   std::string profile(const float* x, const float* t, float* out, cudaStream_t stream);
   int batch() const { return B_; }
+  int out_ch() const { return out_ch_; }
+  int in_channels() const { return in_ch_; }
+  int resolution() const { return R_; }
   float* x_in() const { return x_in_; }
   float* t_in() const { return t_in_; }
   float* out_buf() const { return out_; }
-  const SimpleCfg& cfg() const { return cfg_; }
   void set_use_graph(bool on) { use_graph_ = on; }
   size_t workspace_bytes() const { return arena_.used(); }
   int num_launches() const { return (int)ops_.size(); }
   double flops_per_forward() const;
 
- private:
+ protected:
   struct Param { float* p; long long n; };
   const float* P(const std::string& name, long long expect = -1) const;
   View new_view(int H, int W, int C);
   double* new_stats();
   struct TcWeights { __half *hi, *lo; int ktot; };
+  // main / side: full parameter names of the OIHW weight tensors ("" = absent)
   TcWeights prep_weights(const std::string& main, int Cout, int Cin, int taps, const std::string& side, int CinSide);
-  TcWeights prep_qkv(const std::string& p, int C);
   const float* bias_sum(const std::string& a, const std::string& b, int C);
+  float* dev_copy(const std::vector<float>& v);
+  bool has_param(const std::string& name) const { return params_.count(name) != 0; }
 
   void add_op(const std::string& name, const std::string& kind, double flops, double bytes, std::function<void(cudaStream_t)> f);
-  void emit_gn_split(const std::string& name, const View& x, const std::string& norm, bool silu, int mode, SplitView& dst);
+  // norm: parameter prefix of the GroupNorm ("" = raw split); ss: optional per-(image, channel) scale/shift rows
+  // [scale(C) | shift(C)] with row pitch ss_ld (use_scale_shift_norm, unet.py:250-252)
+  void emit_gn_split(const std::string& name, const View& x, const std::string& norm, bool silu, int mode, SplitView& dst,
+                     const float* ss = nullptr, int ss_ld = 0);
   void emit_tc(const std::string& name, const SplitView& a, int mode, const SplitView* side, const TcWeights& w, int Cout,
-               const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr);
-  void emit_resblock(const std::string& p, const View& x, const View& out);
-  void emit_attn(const std::string& p, const View& x, const View& out);
-  void emit_downsample(const std::string& p, const View& x, const View& out);
-  void emit_upsample(const std::string& p, const View& x, const View& out);
-  void build_program();
+               const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr, int res_mode = 0);
+  void emit_stem(const std::string& wname, const View& out);
+  void emit_head(const std::string& norm, const std::string& conv, const View& h);
+  void alloc_common(size_t split_elems, size_t hbuf_elems, int n_gn);
+  virtual void build_program() = 0;
   void run_ops(cudaStream_t s);
 
-  SimpleCfg cfg_;
-  int B_, num_sms_ = 148;
+  int B_, in_ch_, out_ch_, R_, groups_;
+  float eps_;
+  int num_sms_ = 148;
   bool finalized_ = false, use_graph_ = true;
   Arena arena_;
   std::map<std::string, Param> params_;
@@ -98,7 +117,7 @@ class UNetSimple {
   size_t split_elems_ = 0;
   float* hbuf_ = nullptr;      // resblock intermediate
   size_t hbuf_elems_ = 0;
-  float *qkv_ = nullptr, *attS_ = nullptr, *attO_ = nullptr, *headact_ = nullptr;
+  float *qkv_ = nullptr, *attS_ = nullptr, *attO_ = nullptr;
   double* stats_base_ = nullptr;
   size_t stats_count_ = 0, stats_cap_ = 0;
   float *emb_ = nullptr, *temb0_ = nullptr, *temb_ = nullptr, *ca_all_ = nullptr, *freq_ = nullptr;
@@ -107,6 +126,35 @@ class UNetSimple {
   float *tembW_all_ = nullptr, *tembB_all_ = nullptr;
   cudaGraph_t graph_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
+};
+
+class UNetSimple : public UNetEngine {
+ public:
+  UNetSimple(const SimpleCfg& cfg, int batch);
+
+ private:
+  void build_program() override;
+  void emit_resblock(const std::string& p, const View& x, const View& out);
+  void emit_attn(const std::string& p, const View& x, const View& out);
+  void emit_downsample(const std::string& p, const View& x, const View& out);
+  void emit_upsample(const std::string& p, const View& x, const View& out);
+  SimpleCfg cfg_;
+};
+
+class UNetOpenAI : public UNetEngine {
+ public:
+  UNetOpenAI(const OpenAICfg& cfg, int batch);
+
+ private:
+  enum ResKind { RES_PLAIN = 0, RES_DOWN = 1, RES_UP = 2 };
+  void build_program() override;
+  void emit_resblock(const std::string& p, const View& x, const View& out, int kind);
+  void emit_attn(const std::string& p, const View& x, const View& out);
+  OpenAICfg cfg_;
+  float* ss_all_ = nullptr;     // [B][ss_total_] scale|shift rows of every ResBlock (emb_layers outputs)
+  int ss_total_ = 0;
+  std::map<std::string, int> ss_off_;
+  float *embW_all_ = nullptr, *embB_all_ = nullptr;
 };
 
 }  // namespace ddnm

@@ -95,7 +95,8 @@ template <bool F32OUT>
 __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C, int ld, int N, int groups,
                                 const double* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu, int mode, int pix_per_cta,
-                                __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ out32) {
+                                __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ out32,
+                                const float* __restrict__ ss, int ss_ld) {
   __shared__ float sc[MAX_C], sh[MAX_C];
   const int n = blockIdx.y;
   const int HW = H * W;
@@ -108,9 +109,15 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
       double var = stats[((long long)n * groups + g) * 2 + 1] / cnt - mean * mean;
       var = var < 0 ? 0 : var;
       const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-      const float a = rstd * gamma[c];
+      float a = rstd * gamma[c];
+      float b = beta[c] - (float)mean * a;
+      if (ss) {  // h = norm(h) * (1 + scale) + shift
+        const float one_plus = 1.0f + ss[(size_t)n * ss_ld + c];
+        a *= one_plus;
+        b = fmaf(b, one_plus, ss[(size_t)n * ss_ld + C + c]);
+      }
       sc[c] = a;
-      sh[c] = beta[c] - (float)mean * a;
+      sh[c] = b;
     }
   } else {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -128,6 +135,36 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a8[j] = sc[c + j]; b8[j] = sh[c + j]; }
   const int p0 = blockIdx.x * pix_per_cta;
+  if (mode == SPLIT_AVG2) {
+    // output pixel = mean of the 2x2 block of ACTIVATED inputs (avg_pool2d after norm + SiLU)
+    const int Wo = W >> 1, HWo = (H >> 1) * Wo;
+    const int q1 = min(HWo, p0 + pix_per_cta);
+    for (int q = p0 + prow; q < q1; q += rows) {
+      const int oy = q / Wo, ox = q - oy * Wo;
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const float* sp = x + ((size_t)n * HW + (size_t)(2 * oy + (d >> 1)) * W + 2 * ox + (d & 1)) * ld + c;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(sp));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(sp + 4));
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = fmaf(v[j], a8[j], b8[j]);
+          if (silu) v[j] = swishf(v[j]);
+          acc[j] += v[j];
+        }
+      }
+      __align__(16) __half h8[8];
+      __align__(16) __half l8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_f16(acc[j] * 0.25f, h8[j], l8[j]);
+      const size_t o = ((size_t)n * HWo + q) * C + c;
+      *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h8);
+      *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l8);
+    }
+    return;
+  }
   const int p1 = min(HW, p0 + pix_per_cta);
   const float* src = x + ((size_t)n * HW + p0 + prow) * ld + c;
   const size_t step = (size_t)rows * ld;
@@ -178,10 +215,11 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
 }
 
 static void gn_apply_launch(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
-                            bool silu, int mode, __half* hi, __half* lo, float* out32, cudaStream_t st) {
+                            bool silu, int mode, __half* hi, __half* lo, float* out32, cudaStream_t st, const float* ss, int ss_ld) {
   DDNM_CHECK(x.C % 8 == 0 && x.C <= MAX_C && x.ld % 4 == 0, "gn_apply: unsupported channel count");
-  if (mode == SPLIT_S2D) DDNM_CHECK(x.H % 2 == 0 && x.W % 2 == 0, "space-to-depth needs even dims");
-  const int HW = x.H * x.W;
+  if (mode == SPLIT_S2D || mode == SPLIT_AVG2) DDNM_CHECK(x.H % 2 == 0 && x.W % 2 == 0, "space-to-depth / avg-pool need even dims");
+  if (ss) DDNM_CHECK(stats != nullptr, "scale-shift needs a normalisation");
+  const int HW = mode == SPLIT_AVG2 ? x.H * x.W / 4 : x.H * x.W;   // pixels the grid iterates over
   const int C8 = x.C / 8;
   const int rows = std::max(1, 256 / C8);
   const int threads = C8 * rows;
@@ -190,20 +228,20 @@ static void gn_apply_launch(const View& x, int groups, const double* stats, cons
   dim3 grid(cdiv(HW, ppc), x.N);
   if (out32)
     gn_apply_kernel<true><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, gamma, beta, eps, silu, mode,
-                                                 ppc, nullptr, nullptr, out32);
+                                                 ppc, nullptr, nullptr, out32, ss, ss_ld);
   else
     gn_apply_kernel<false><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, gamma, beta, eps, silu, mode,
-                                                  ppc, hi, lo, nullptr);
+                                                  ppc, hi, lo, nullptr, ss, ss_ld);
   CUDA_CHECK(cudaGetLastError());
 }
 
 void gn_apply_split(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
-                    bool silu, int mode, __half* hi, __half* lo, cudaStream_t s) {
-  gn_apply_launch(x, groups, stats, gamma, beta, eps, silu, mode, hi, lo, nullptr, s);
+                    bool silu, int mode, __half* hi, __half* lo, cudaStream_t s, const float* ss, int ss_ld) {
+  gn_apply_launch(x, groups, stats, gamma, beta, eps, silu, mode, hi, lo, nullptr, s, ss, ss_ld);
 }
 void gn_apply_f32(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
                   bool silu, float* out, cudaStream_t s) {
-  gn_apply_launch(x, groups, stats, gamma, beta, eps, silu, SPLIT_SAME, nullptr, nullptr, out, s);
+  gn_apply_launch(x, groups, stats, gamma, beta, eps, silu, SPLIT_SAME, nullptr, nullptr, out, s, nullptr, 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -438,11 +476,12 @@ void sinusoid(const float* t, int N, const float* freq, int dim, bool sin_first,
 // ---------------------------------------------------------------------------------------------------------------
 template <bool BT>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
-                                                    long long sa, const float* __restrict__ B, int ldb, long long sb,
-                                                    float* __restrict__ C, int ldc, long long sc) {
+                                                    long long sa, long long sa2, const float* __restrict__ B, int ldb,
+                                                    long long sb, long long sb2, float* __restrict__ C, int ldc, long long sc,
+                                                    long long sc2, int inner_n) {
   __shared__ float As[16][64 + 4], Bs[16][64 + 4];
-  const int b = blockIdx.z;
-  A += b * sa; B += b * sb; C += b * sc;
+  const int bo = blockIdx.z / inner_n, bi = blockIdx.z % inner_n;
+  A += bo * sa + bi * sa2; B += bo * sb + bi * sb2; C += bo * sc + bi * sc2;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   float acc[4][4] = {};
@@ -485,13 +524,15 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float a
       if (m < M && n < N) C[(long long)m * ldc + n] = alpha * acc[i][j];
     }
 }
-void sgemm_batched(bool bt, int batches, int M, int N, int K, float alpha, const float* A, int lda, long long sa,
-                   const float* B, int ldb, long long sb, float* C, int ldc, long long sc, cudaStream_t st) {
-  dim3 grid(cdiv(N, 64), cdiv(M, 64), batches);
+void sgemm_batched(bool bt, int outer_n, int inner_n, int M, int N, int K, float alpha, const float* A, int lda, long long sa,
+                   long long sa2, const float* B, int ldb, long long sb, long long sb2, float* C, int ldc, long long sc,
+                   long long sc2, cudaStream_t st) {
+  dim3 grid(cdiv(N, 64), cdiv(M, 64), outer_n * inner_n);
+  DDNM_CHECK(grid.z <= 65535, "too many GEMM batches for one launch");
   if (bt)
-    sgemm_kernel<true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sa, B, ldb, sb, C, ldc, sc);
+    sgemm_kernel<true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sa, sa2, B, ldb, sb, sb2, C, ldc, sc, sc2, inner_n);
   else
-    sgemm_kernel<false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sa, B, ldb, sb, C, ldc, sc);
+    sgemm_kernel<false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sa, sa2, B, ldb, sb, sb2, C, ldc, sc, sc2, inner_n);
   CUDA_CHECK(cudaGetLastError());
 }
 

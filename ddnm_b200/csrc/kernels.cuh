@@ -6,16 +6,18 @@
 
 namespace ddnm {
 
-enum SplitMode : int { SPLIT_SAME = 0, SPLIT_UP2 = 1, SPLIT_S2D = 2 };
+enum SplitMode : int { SPLIT_SAME = 0, SPLIT_UP2 = 1, SPLIT_S2D = 2, SPLIT_AVG2 = 3 };
 
 // GroupNorm statistics: stats[(n*G + g)*2 + {0,1}] += {sum, sum of squares} (double).  Caller zeroes stats.
 void gn_stats(const View& x, int groups, double* stats, cudaStream_t s);
 
 // y = [GN affine](x) -> [SiLU] -> fp16 (hi, lo) planes.  stats == nullptr: no normalisation (raw split).
 // mode SPLIT_UP2 writes a nearest-neighbour 2x upsampled plane, SPLIT_S2D writes 4 parity phases
-// (plane index = phase*N + n, phase = (y&1)*2 + (x&1)) for the stride-2 convolution.
+// (plane index = phase*N + n, phase = (y&1)*2 + (x&1)) for the stride-2 convolution, SPLIT_AVG2 writes the 2x2 average
+// pool of the activated tensor (ResBlock(down=True), unet.py:237-241).  ss != nullptr: use_scale_shift_norm —
+// y = GN(x) * (1 + ss[n*ss_ld + c]) + ss[n*ss_ld + C + c]   (unet.py:250-252).
 void gn_apply_split(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
-                    bool silu, int mode, __half* hi, __half* lo, cudaStream_t s);
+                    bool silu, int mode, __half* hi, __half* lo, cudaStream_t s, const float* ss = nullptr, int ss_ld = 0);
 // same normalisation, fp32 contiguous NHWC output (feeds the small-Cout output convolution)
 void gn_apply_f32(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
                   bool silu, float* out, cudaStream_t s);
@@ -35,8 +37,10 @@ void sinusoid(const float* t, int N, const float* freq, int dim, bool sin_first,
 
 // batched fp32 GEMM on CUDA cores (attention at small token counts).
 //   NT: C[b][m][n] = alpha * sum_k A[b][m][k] * B[b][n][k];   NN: ... * B[b][k][n]
-void sgemm_batched(bool b_transposed, int batches, int M, int N, int K, float alpha, const float* A, int lda, long long sa,
-                   const float* B, int ldb, long long sb, float* C, int ldc, long long sc, cudaStream_t s);
+// Two-level batch (image, head): batch index b = outer*inner_n + inner; operand offset = outer*s? + inner*s?2.
+void sgemm_batched(bool b_transposed, int outer_n, int inner_n, int M, int N, int K, float alpha, const float* A, int lda,
+                   long long sa, long long sa2, const float* B, int ldb, long long sb, long long sb2, float* C, int ldc,
+                   long long sc, long long sc2, cudaStream_t s);
 void softmax_rows(float* x, long long rows, int cols, cudaStream_t s);
 
 // OIHW fp32 conv weight -> K-major fp16 (hi, lo) rows: dst[co*ktot + koff + tap*Cin + ci]

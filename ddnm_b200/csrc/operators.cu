@@ -621,8 +621,8 @@ void Operator::fwht(float* buf, int B, cudaStream_t s) {
 void Operator::sandwich(const float* L, int lr, int lc, const float* X, int B, const float* R, int rr, int rc, float* T,
                         float* out, cudaStream_t s) {
   const int nb = B * C_;
-  sgemm_batched(false, nb, lr, rr, lc, 1.0f, L, lc, 0, X, rr, (long long)lc * rr, T, rr, (long long)lr * rr, s);
-  sgemm_batched(false, nb, lr, rc, rr, 1.0f, T, rr, (long long)lr * rr, R, rc, 0, out, rc, (long long)lr * rc, s);
+  sgemm_batched(false, nb, 1, lr, rr, lc, 1.0f, L, lc, 0, 0, X, rr, (long long)lc * rr, 0, T, rr, (long long)lr * rr, 0, s);
+  sgemm_batched(false, nb, 1, lr, rc, rr, 1.0f, T, rr, (long long)lr * rr, 0, R, rc, 0, 0, out, rc, (long long)lr * rc, 0, s);
 }
 
 void Operator::deblur_A(const float* x, int B, float* y, cudaStream_t s) {
@@ -666,8 +666,8 @@ void Operator::deblur_Apinv(const float* y, int B, float* x, cudaStream_t s) {
     mul_table_kernel<<<blocks(ns), 256, 0, s>>>(S, tabDinv_, 0, C_, sm * sm, ns);
     // x = Vk (D x sm) * S (sm x sm) * Vk^T (sm x D): first product is D x sm per image
     const int nb = B * C_;
-    sgemm_batched(false, nb, D_, sm, sm, 1.0f, V_, sm, 0, S, sm, (long long)sm * sm, T, sm, (long long)D_ * sm, s);
-    sgemm_batched(false, nb, D_, D_, sm, 1.0f, T, sm, (long long)D_ * sm, Vt_, D_, 0, x, D_, (long long)D_ * D_, s);
+    sgemm_batched(false, nb, 1, D_, sm, sm, 1.0f, V_, sm, 0, 0, S, sm, (long long)sm * sm, 0, T, sm, (long long)D_ * sm, 0, s);
+    sgemm_batched(false, nb, 1, D_, D_, sm, 1.0f, T, sm, (long long)D_ * sm, 0, Vt_, D_, 0, 0, x, D_, (long long)D_ * D_, 0, s);
   }
   CUDA_CHECK(cudaGetLastError());
 }

@@ -22,16 +22,16 @@ __global__ void travel_back_kernel(const float* __restrict__ x0, const float* __
   if (i < n) xn[i] = __fadd_rn(__fmul_rn(sa, x0[i]), __fmul_rn(z[i], s1));
 }
 
-static void sample(UNetSimple* unet, Operator* op, const ddnm_schedule* sc, const float* x_T, const float* y, const float* noise,
+static void sample(UNetEngine* unet, Operator* op, const ddnm_schedule* sc, const float* x_T, const float* y, const float* noise,
                    int B, float* out_x0, float* out_x0_pred, cudaStream_t st) {
   DDNM_CHECK(unet && op && sc && x_T && y && noise && out_x0, "null argument");
   DDNM_CHECK(unet->batch() == B, "engine was built for a different batch size");
-  const SimpleCfg& cfg = unet->cfg();
-  DDNM_CHECK(op->x_dim() == (long long)cfg.in_channels * cfg.resolution * cfg.resolution, "operator / denoiser image size mismatch");
-  DDNM_CHECK(cfg.out_ch == 3 || cfg.out_ch == 6, "denoiser must predict 3 (eps) or 6 (eps, sigma) channels");
+  const int R = unet->resolution();
+  DDNM_CHECK(op->x_dim() == (long long)unet->in_channels() * R * R, "operator / denoiser image size mismatch");
+  DDNM_CHECK(unet->out_ch() == 3 || unet->out_ch() == 6, "denoiser must predict 3 (eps) or 6 (eps, sigma) channels");
   const long long img = op->x_dim();
   const long long n = (long long)B * img;
-  const long long et_stride = (long long)cfg.out_ch * cfg.resolution * cfg.resolution;  // 6-channel nets: keep channels 0..2 (:54-55)
+  const long long et_stride = (long long)unet->out_ch() * R * R;  // 6-channel nets: keep channels 0..2 (:54-55)
   float* xt = unet->x_in();      // the denoiser reads its input here
   float* et = unet->out_buf();   // and leaves eps here
   float *x0t = nullptr, *xn = nullptr;
@@ -80,7 +80,7 @@ using namespace ddnm;
 extern "C" int ddnm_sample(void* unet, void* op, const ddnm_schedule* sched, const float* x_T, const float* y, const float* noise,
                            int B, float* out_x0, float* out_x0_pred, void* stream) {
   DDNM_API_BEGIN
-  sample(static_cast<UNetSimple*>(unet), static_cast<Operator*>(op), sched, x_T, y, noise, B, out_x0, out_x0_pred,
+  sample(static_cast<UNetEngine*>(unet), static_cast<Operator*>(op), sched, x_T, y, noise, B, out_x0, out_x0_pred,
          (cudaStream_t)stream);
   DDNM_API_END
 }

@@ -184,7 +184,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
       const bool valid = n < p.N;
       const long long pix = ((long long)n * p.H + (y0 + yi)) * p.W + (x0 + xi);
       float* orow = p.out + pix * p.ldc + n_idx * BN;
-      const float* rrow = p.residual ? p.residual + pix * p.ldr + n_idx * BN : nullptr;
+      // residual source row(s): same pixel, nearest-upsampled (x_upd of ResBlock(up=True), unet.py:240) or the 2x2
+      // average of a twice-as-large map (ResBlock(down=True))
+      const float* rrow = nullptr;
+      long long r_dx = 0, r_dy = 0;
+      if (p.residual) {
+        if (p.res_mode == 0) {
+          rrow = p.residual + pix * p.ldr + n_idx * BN;
+        } else if (p.res_mode == 1) {
+          const long long rp = ((long long)n * (p.H >> 1) + ((y0 + yi) >> 1)) * (p.W >> 1) + ((x0 + xi) >> 1);
+          rrow = p.residual + rp * p.ldr + n_idx * BN;
+        } else {
+          const long long rp = ((long long)n * (2 * p.H) + 2 * (y0 + yi)) * (2 * p.W) + 2 * (x0 + xi);
+          rrow = p.residual + rp * p.ldr + n_idx * BN;
+          r_dx = p.ldr;
+          r_dy = (long long)2 * p.W * p.ldr;
+        }
+      }
       const float* crow = p.chanadd ? p.chanadd + (long long)n * p.ca_ld + n_idx * BN : nullptr;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -207,7 +223,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
               o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
             }
             if (rrow) {
-              const float4 q = *reinterpret_cast<const float4*>(rrow + c0 + j);
+              float4 q = *reinterpret_cast<const float4*>(rrow + c0 + j);
+              if (p.res_mode == 2) {
+                const float4 q1 = *reinterpret_cast<const float4*>(rrow + r_dx + c0 + j);
+                const float4 q2 = *reinterpret_cast<const float4*>(rrow + r_dy + c0 + j);
+                const float4 q3 = *reinterpret_cast<const float4*>(rrow + r_dy + r_dx + c0 + j);
+                q.x = ((q.x + q1.x) + (q2.x + q3.x)) * 0.25f;
+                q.y = ((q.y + q1.y) + (q2.y + q3.y)) * 0.25f;
+                q.z = ((q.z + q1.z) + (q2.z + q3.z)) * 0.25f;
+                q.w = ((q.w + q1.w) + (q2.w + q3.w)) * 0.25f;
+              }
               o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
             }
             *reinterpret_cast<float4*>(orow + c0 + j) = o;
@@ -275,7 +300,7 @@ void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor) {
 
 TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1, const __half* w_hi, const __half* w_lo,
                         int w_batches, int Cout, const View& out, const float* chanadd, int ca_ld, const float* residual,
-                        int ldr, float alpha, int num_sms) {
+                        int ldr, float alpha, int num_sms, int res_mode) {
   TcLaunch L;
   TcParams& p = L.p;
   const int taps = (mode0 == TAPS_1X1) ? 1 : 9;
@@ -309,7 +334,7 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   }
   p.Cout = Cout; p.ldc = out.ld; p.out = out.p;
   DDNM_CHECK(out.C == Cout && out.ld % 4 == 0 && ((uintptr_t)out.p & 15) == 0, "output view misaligned");
-  p.chanadd = chanadd; p.ca_ld = ca_ld; p.residual = residual; p.ldr = ldr; p.alpha = alpha;
+  p.chanadd = chanadd; p.ca_ld = ca_ld; p.residual = residual; p.ldr = ldr; p.alpha = alpha; p.res_mode = res_mode;
   if (residual) DDNM_CHECK(ldr % 4 == 0 && ((uintptr_t)residual & 15) == 0, "residual misaligned");
   // UMMA shared-memory descriptor, high word: SBO = 1024 B (8 rows x 128 B) >> 4 at bits [32,46), version = 1 at
   // [46,48), layout SWIZZLE_128B (= 2) at [61,64).  (cute/arch/mma_sm100_desc.hpp SmemDescriptor)

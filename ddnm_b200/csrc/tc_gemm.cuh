@@ -27,6 +27,7 @@ struct TcParams {
   int ca_ld;                   // 0 = one row broadcast over images
   const float* residual;       // residual[pixel*ldr + co]; may be null
   int ldr;
+  int res_mode;                // 0: same pixel; 1: nearest-upsampled source (H/2 x W/2); 2: 2x2 average of a (2H x 2W) source
   float alpha;                 // out = alpha*acc + chanadd + residual
   uint32_t desc_hi;            // UMMA smem descriptor high word (SW128 K-major), see tc_gemm.cu
   uint32_t idesc;              // UMMA instruction descriptor
@@ -44,7 +45,7 @@ struct TcLaunch {
 // Ktot = taps*C0 + C1 (k index = tap*C0 + ci, then source-1 channels).
 TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1, const __half* w_hi, const __half* w_lo,
                         int w_batches, int Cout, const View& out, const float* chanadd, int ca_ld, const float* residual,
-                        int ldr, float alpha, int num_sms);
+                        int ldr, float alpha, int num_sms, int res_mode = 0);
 void tc_run(const TcLaunch& L, cudaStream_t stream);
 
 // debug knobs (tests only): override descriptor words for the NEXT launches built

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .model import Model
+from .model import _EngineModel
 from .operators import _Operator
 from .schedule import alpha_bar_table, time_pairs
 
@@ -26,10 +26,10 @@ def sample_device(x, model, b, eta, A_funcs, y, sigma_y, plus, config, noise=Non
 def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, noise=None, to_host=True):
     if cls_fn is not None:
         raise NotImplementedError("classifier guidance (imagenet_256_cc.yml) is outside the ddnm_b200 hot path")
-    if not isinstance(model, Model):
+    if not isinstance(model, _EngineModel):
         model = getattr(model, "module", model)          # tolerate nn.DataParallel-style wrappers
-    if not isinstance(model, Model) or not isinstance(A_funcs, _Operator):
-        raise TypeError("ddnm_b200.sampler needs a ddnm_b200.model.Model and a ddnm_b200.operators operator")
+    if not isinstance(model, _EngineModel) or not isinstance(A_funcs, _Operator):
+        raise TypeError("ddnm_b200.sampler needs a ddnm_b200.model denoiser and a ddnm_b200.operators operator")
     with torch.no_grad():
         if not x.is_cuda:
             x = x.to("cuda", non_blocking=True)            # the reference moves xs[-1] to 'cuda' itself (svd_ddnm.py:45)

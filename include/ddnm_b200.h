@@ -36,6 +36,21 @@ typedef struct {
 } ddnm_simple_cfg;   /* mirrors config.model.* / config.data.image_size read at models.py:195-204 */
 
 int ddnm_unet_simple_create(const ddnm_simple_cfg* cfg, int batch, void** handle);
+
+/* Denoiser: guided_diffusion/unet.py::UNetModel as built by script_util.create_model (:130-185) for imagenet_256.yml:
+ * use_scale_shift_norm, resblock_updown, legacy attention order, class_cond = false.  Replaces `et = model(xt, t)` for
+ * model.type == "openai" (UNetModel.forward, unet.py:635-664).  Parameter names = UNetModel.state_dict() keys
+ * (Conv1d qkv / proj_out weights keep their (O, I, 1) layout); "__freq" = exp(-log(1e4) * arange(mc/2) / (mc/2))
+ * (nn.py:113-115).  All handle functions below (set_param ... destroy) accept either denoiser kind. */
+typedef struct {
+  int image_size, model_channels, num_res_blocks, n_levels;
+  int channel_mult[8];
+  int n_attn_ds;
+  int attn_ds[4];             /* image_size // attention resolution, as create_model computes (:163-165) */
+  int num_head_channels, out_channels, in_channels, groups;
+  float eps;
+} ddnm_openai_cfg;
+int ddnm_unet_openai_create(const ddnm_openai_cfg* cfg, int batch, void** handle);
 /* name = key of Model.state_dict() (models.py:216-299), data = fp32 host or device, reference layout (OIHW);
  * plus the pseudo-parameter "__freq" = exp(arange(ch/2) * -log(1e4)/(ch/2-1)) (models.py:16-18). */
 int ddnm_unet_set_param(void* handle, const char* name, const float* data, long long numel);

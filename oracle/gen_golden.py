@@ -24,6 +24,7 @@ from oracle import operators as O          # noqa: E402
 from oracle import sampler as S            # noqa: E402
 from oracle import schedule as SCH         # noqa: E402
 from oracle import unet_simple as U        # noqa: E402
+from oracle import unet_openai as UO       # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -103,6 +104,51 @@ def unet_fixtures():
             out["celeba_out_sum"] = np.array([r.double().sum().item(), r.double().abs().sum().item()])
         print(f"unet {name}: ok, out std {r.std().item():.4f}")
     np.savez_compressed(os.path.join(GOLD, "unet_simple.npz"), **out)
+
+
+def ref_openai(cfg, seed):
+    from guided_diffusion.script_util import create_model
+    torch.manual_seed(seed)
+    m = create_model(image_size=cfg.image_size, num_channels=cfg.model_channels, num_res_blocks=cfg.num_res_blocks,
+                     channel_mult=",".join(str(c) for c in cfg.channel_mult), learn_sigma=(cfg.out_channels == 6), class_cond=False,
+                     attention_resolutions=",".join(str(r) for r in cfg.attention_resolutions), num_heads=4,
+                     num_head_channels=cfg.num_head_channels, num_heads_upsample=-1, use_scale_shift_norm=True, dropout=0.0,
+                     resblock_updown=True, use_fp16=False, use_new_attention_order=False)
+    return m.eval()
+
+
+def openai_fixtures():
+    """imagenet_256.yml UNetModel in fp32 mode, zero-initialised tensors re-drawn (see oracle.unet_openai.init_state_dict)."""
+    out = {}
+    for name, cfg, B in (("tiny", UO.OpenAIUNetConfig.tiny(), 2), ("imagenet", UO.OpenAIUNetConfig.imagenet_256(), 1)):
+        m = ref_openai(cfg, 1234)
+        rsd = m.state_dict()
+        sd = UO.init_state_dict(cfg, 1234)
+        assert set(sd) == set(rsd)
+        redrawn = 0
+        for k in sd:
+            if not torch.equal(sd[k], rsd[k]):
+                assert rsd[k].abs().sum() == 0, f"{k}: differs from the reference but is not a zero-initialised tensor"
+                redrawn += 1
+        m.load_state_dict(sd)
+        g = torch.Generator().manual_seed(99)
+        x = torch.randn(B, 3, cfg.image_size, cfg.image_size, generator=g)
+        t = torch.tensor([417.0, 3.0][:B])
+        with torch.no_grad():
+            r = m(x, t)
+            taps = {}
+            o = UO.forward(sd, x, t, cfg, taps=taps)
+        close(o, r, 0.0, f"openai unet {name}")
+        out[f"{name}_t"] = t.numpy()
+        if name == "tiny":
+            out["tiny_x"], out["tiny_out"] = x.numpy(), r.numpy()
+            for k in ("in.0", "in.1", "in.2", "in.3", "mid", "out.0", "out.2", "out.5"):
+                out["tiny_tap_" + k] = taps[k].numpy()
+        else:
+            out["imagenet_out_s8"] = r[:, :, ::8, ::8].contiguous().numpy()
+            out["imagenet_out_sum"] = np.array([r.double().sum().item(), r.double().abs().sum().item()])
+        print(f"openai unet {name}: ok ({redrawn} zero-init tensors re-drawn), out std {r.std().item():.4f}")
+    np.savez_compressed(os.path.join(GOLD, "unet_openai.npz"), **out)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -252,9 +298,11 @@ def sampler_fixtures():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["unet", "ops", "sampler"]
+    which = sys.argv[1:] or ["unet", "openai", "ops", "sampler"]
     if "unet" in which:
         unet_fixtures()
+    if "openai" in which:
+        openai_fixtures()
     if "ops" in which:
         operator_fixtures()
     if "sampler" in which:

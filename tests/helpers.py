@@ -88,3 +88,12 @@ def assert_close(got, ref, rtol=1e-3, atol=1e-4, what=""):
     tol = atol + rtol * ref.abs()
     bad = (err > tol)
     assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} elements outside rtol={rtol} atol={atol}; max err {err.max().item():.3e} (ref absmax {ref.abs().max().item():.3e})"
+
+
+def openai_model_kwargs(cfg):
+    """keyword arguments of script_util.create_model for an oracle OpenAIUNetConfig (imagenet_256.yml style)."""
+    return dict(image_size=cfg.image_size, num_channels=cfg.model_channels, num_res_blocks=cfg.num_res_blocks,
+                channel_mult=",".join(str(c) for c in cfg.channel_mult), learn_sigma=(cfg.out_channels == 6), class_cond=False,
+                attention_resolutions=",".join(str(r) for r in cfg.attention_resolutions), num_heads=4,
+                num_head_channels=cfg.num_head_channels, num_heads_upsample=-1, use_scale_shift_norm=True, dropout=0.0,
+                resblock_updown=True, use_fp16=True, use_new_attention_order=False)

@@ -10,9 +10,10 @@ import torch.nn.functional as F
 
 from oracle import sampler as S
 from oracle import schedule as SCH
+from oracle import unet_openai as UO
 from oracle import unet_simple as U
 
-from helpers import LAMBDA_CASES, assert_close, engine_op, model_config, oracle_ops, sampler_config
+from helpers import LAMBDA_CASES, assert_close, engine_op, model_config, openai_model_kwargs, oracle_ops, sampler_config
 from test_oracle_golden import SAMPLER_CASES, sampler_inputs
 
 pytestmark = pytest.mark.gpu
@@ -147,6 +148,67 @@ def test_unet_batch_rows_independent():
     full = m(x, t)
     for i in range(4):
         assert_close(m(x[i:i + 1], t[i:i + 1]), full[i:i + 1], 1e-5, 1e-5, f"row {i}")
+
+
+def _engine_openai(cfg, graph=True):
+    from ddnm_b200.model import create_model
+    m = create_model(**openai_model_kwargs(cfg))
+    m.convert_to_fp16()                       # what the reference runner does (diffusion.py:145-146); a no-op here
+    m.use_cuda_graph = graph
+    m.load_state_dict(UO.init_state_dict(cfg, 1234))
+    return m
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_openai_unet_tiny_vs_reference_golden(gold, graph):
+    g = gold["unet_openai"]
+    cfg = UO.OpenAIUNetConfig.tiny()
+    m = _engine_openai(cfg, graph)
+    x, t = torch.from_numpy(g["tiny_x"]).to(dev), torch.from_numpy(g["tiny_t"]).to(dev)
+    out = m(x, t)
+    assert out.shape == (2, 6, 32, 32)
+    assert_close(out, g["tiny_out"], what="openai unet tiny vs reference")
+    assert_close(m(x, t), g["tiny_out"], what="openai unet tiny replay vs reference")
+    for k in ("in.0", "in.1", "in.2", "in.3", "mid", "out.0", "out.2", "out.5"):
+        r = g["tiny_tap_" + k]
+        assert_close(m.read_tap(2, k, r.shape), r, what="openai tap " + k)
+
+
+def test_openai_unet_imagenet_vs_reference_golden(gold):
+    g = gold["unet_openai"]
+    cfg = UO.OpenAIUNetConfig.imagenet_256()
+    m = _engine_openai(cfg)
+    gen = torch.Generator().manual_seed(99)
+    x = torch.randn(1, 3, 256, 256, generator=gen)
+    out = m(x.to(dev), torch.from_numpy(g["imagenet_t"]).to(dev))
+    assert_close(out[:, :, ::8, ::8], g["imagenet_out_s8"], what="imagenet UNetModel vs reference (strided sample)")
+    assert abs(out.double().sum().item() - g["imagenet_out_sum"][0]) <= 1e-3 * g["imagenet_out_sum"][1]
+
+
+def test_sampler_with_openai_unet_six_channels(gold):
+    """DDNM+ colorization with the 6-channel (learn_sigma) net: the sampler keeps eps = channels 0..2 (svd_ddnm.py:54-55)."""
+    from ddnm_b200.sampler import ddnm_plus_diffusion
+    cfg = UO.OpenAIUNetConfig.tiny()
+    sd = UO.init_state_dict(cfg, 1234)
+    m = _engine_openai(cfg)
+    oop = oracle_ops(gold["operators"], 32)["color"]
+    eop = engine_op("color", oop, 32)
+    gsm = gold["sampler_tiny"]
+    g = torch.Generator().manual_seed(31)
+    x_orig = torch.rand(2, 3, 32, 32, generator=g) * 2 - 1
+    x_T = torch.randn(2, 3, 32, 32, generator=g)
+    y = oop.A(x_orig.reshape(2, -1))
+    T, tl, tr, sy = 6, 2, 2, 0.1
+    npairs = len(SCH.time_pairs(1000, T, tl, tr))
+    tape = [torch.randn(2, 3, 32, 32, generator=g) for _ in range(npairs)]
+    betas = torch.from_numpy(gsm["betas"])
+    xs, x0s = ddnm_plus_diffusion(x_T.to(dev), m, betas.to(dev), 0.85, eop, y.to(dev), sy, config=sampler_config(T, tl, tr),
+                                  noise=torch.stack(tape).to(dev))
+    with torch.no_grad():
+        ox, ox0 = S.ddnm_sample(x_T, lambda a, b: UO.forward(sd, a, b, cfg), betas, 0.85, oop, y, tape, t_sampling=T, travel_length=tl,
+                                travel_repeat=tr, sigma_y=sy)
+    assert_close(xs[0], ox, 1e-3, 3e-3, "openai-net sampler vs oracle")
+    assert_close(x0s[0], ox0, 1e-3, 3e-3, "openai-net sampler x0_pred vs oracle")
 
 
 # ------------------------------------------------------------------------------------------------ operators

@@ -6,6 +6,7 @@ import torch
 
 from oracle import sampler as S
 from oracle import schedule as SCH
+from oracle import unet_openai as UO
 from oracle import unet_simple as U
 
 from helpers import LAMBDA_CASES, oracle_ops
@@ -33,6 +34,31 @@ def test_unet_celeba_matches_reference(gold):
         out = U.forward(sd, x, torch.from_numpy(g["celeba_t"]), cfg)
     assert np.abs(out[:, :, ::8, ::8].numpy() - g["celeba_out_s8"]).max() <= 2e-5
     assert abs(out.double().sum().item() - g["celeba_out_sum"][0]) <= 1e-2
+
+
+def test_openai_unet_tiny_matches_reference(gold):
+    g = gold["unet_openai"]
+    cfg = UO.OpenAIUNetConfig.tiny()
+    sd = UO.init_state_dict(cfg, 1234)
+    taps = {}
+    with torch.no_grad():
+        out = UO.forward(sd, torch.from_numpy(g["tiny_x"]), torch.from_numpy(g["tiny_t"]), cfg, taps=taps)
+    assert out.shape[1] == 6
+    assert np.abs(out.numpy() - g["tiny_out"]).max() <= 1e-6
+    for k in ("in.0", "in.1", "in.2", "in.3", "mid", "out.0", "out.2", "out.5"):
+        assert np.abs(taps[k].numpy() - g["tiny_tap_" + k]).max() <= 1e-6, k
+
+
+def test_openai_unet_imagenet_matches_reference(gold):
+    g = gold["unet_openai"]
+    cfg = UO.OpenAIUNetConfig.imagenet_256()
+    sd = UO.init_state_dict(cfg, 1234)
+    gen = torch.Generator().manual_seed(99)
+    x = torch.randn(1, 3, 256, 256, generator=gen)
+    with torch.no_grad():
+        out = UO.forward(sd, x, torch.from_numpy(g["imagenet_t"]), cfg)
+    assert np.abs(out[:, :, ::8, ::8].numpy() - g["imagenet_out_s8"]).max() <= 5e-5
+    assert abs(out.double().sum().item() - g["imagenet_out_sum"][0]) <= 1e-4 * g["imagenet_out_sum"][1]
 
 
 @pytest.mark.parametrize("dim", [32, 256])

@@ -178,6 +178,88 @@ def group_unet(which="tiny", B=2, graph=1):
     return m, x, t
 
 
+def group_openai(which="tiny", B=2, graph=1):
+    from oracle import unet_openai as UO
+    from ddnm_b200.model import create_model
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from helpers import openai_model_kwargs
+    cfg = UO.OpenAIUNetConfig.tiny() if which == "tiny" else UO.OpenAIUNetConfig.imagenet_256()
+    sd = UO.init_state_dict(cfg, 1234)
+    m = create_model(**openai_model_kwargs(cfg))
+    m.use_cuda_graph = bool(int(graph))
+    m.load_state_dict(sd)
+    B = int(B)
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(B, 3, cfg.image_size, cfg.image_size, generator=g)
+    t = torch.tensor([417.0, 3.0, 999.0, 0.0][:B])
+    taps = {}
+    with torch.no_grad():
+        ref = UO.forward(sd, x, t, cfg, taps=taps)
+    t0 = time.time()
+    out = m(x.to(dev), t.to(dev))
+    torch.cuda.synchronize()
+    print(f"engine build+first forward {time.time() - t0:.2f}s; info {m.info(B)}")
+    for name in sorted(taps, key=lambda k: (k.split('.')[0] != 'in', k.split('.')[0] == 'out', int(k.split('.')[1]) if '.' in k else 0)):
+        r = taps[name]
+        got = m.read_tap(B, name, tuple(r.shape)).cpu()
+        print(f"   tap {name:8s} shape {tuple(r.shape)} max_err {(got - r).abs().max().item():.3e} ref_absmax {r.abs().max().item():.3e}")
+    err = (out.cpu() - ref).abs()
+    viol = (err > 1e-4 + 1e-3 * ref.abs()).float().mean().item()
+    print(f"[openai {which} B{B}] max_abs_err {err.max().item():.3e} ref_absmax {ref.abs().max().item():.3e} "
+          f"violations(rtol1e-3,atol1e-4) {viol * 100:.4f}%  ->", "PASS" if viol == 0 else "FAIL", flush=True)
+
+
+def group_openai_bench(B=8, iters=3):
+    from ddnm_b200.model import create_model
+    from ddnm_b200.weights import random_state_dict_openai
+    B, iters = int(B), int(iters)
+    m = create_model(image_size=256, num_channels=256, num_res_blocks=2, learn_sigma=True, attention_resolutions="32,16,8",
+                     num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True, use_fp16=True)
+    m.load_state_dict(random_state_dict_openai(m, 1234))
+    x = torch.randn(B, 3, 256, 256, device=dev)
+    t = torch.full((B,), 500.0, device=dev)
+    for _ in range(2):
+        m(x, t)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        m(x, t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    info = m.info(B)
+    print(f"[openai bench imagenet_256 B{B}] {ms:.2f} ms/forward  {B / ms * 1e3:.1f} img-fwd/s  "
+          f"{info['flops_per_forward'] / ms / 1e9:.1f} TFLOP/s algorithmic; workspace {info['workspace_bytes'] / 2**30:.2f} GiB; launches {info['launches']}")
+    prof = m.profile(x, t)
+    agg = {}
+    for p in prof:
+        a = agg.setdefault(p["kind"], [0.0, 0.0, 0.0, 0])
+        a[0] += p["ms"]; a[1] += p["flops"]; a[2] += p["bytes"]; a[3] += 1
+    tot = sum(a[0] for a in agg.values())
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        print(f"   {k:10s} n={a[3]:4d} {a[0]:8.3f} ms ({a[0] / tot * 100:5.1f}%)  {a[1] / max(a[0], 1e-9) / 1e9:8.1f} TFLOP/s  {a[2] / max(a[0], 1e-9) / 1e6:8.1f} GB/s")
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(prof, open(f"gpurun_out/unet_profile_openai_B{B}.json", "w"))
+
+
+def group_cpu_threads():
+    """how the CPU reference scales with torch threads on this host (choose the reference arm's thread count)"""
+    from oracle import unet_simple as U
+    cfg = U.SimpleUNetConfig.celeba_hq()
+    sd = U.init_state_dict(cfg, 1234)
+    x = torch.randn(1, 3, 256, 256)
+    t = torch.tensor([500.0])
+    print("cpu_count", os.cpu_count())
+    for nt in (8, 16, 32, 64, os.cpu_count()):
+        torch.set_num_threads(nt)
+        with torch.no_grad():
+            U.forward(sd, x, t, cfg)
+            t0 = time.time()
+            U.forward(sd, x, t, cfg)
+            print(f"   threads {nt}: {time.time() - t0:.2f} s / image-forward", flush=True)
+
+
 def group_unet_bench(which="celeba", B=16, iters=5):
     from oracle import unet_simple as U
     from ddnm_b200.model import Model
