@@ -91,7 +91,11 @@ def cpu_reference_rate(steps, warmup, sample_batch=2, sample_pairs=3):
     (every step costs the same: one UNet forward + one projection)."""
     import torch
     from oracle import operators as O, sampler as S, schedule as SCH, unet_simple as U
-    torch.set_num_threads(os.cpu_count())
+    # torch's CPU conv path collapses when oversubscribed: measured on the B200 host (128 hw threads) one image-forward takes
+    # 1.07 s at 8 threads, 1.20 s at 16, 1.25 s at 32, 1.92 s at 64 and 51.5 s at 128 (profiles/r01_cpu_threads.txt),
+    # so the reference arm runs at the thread count where it is fastest
+    nthreads = min(os.cpu_count() or 1, 16)
+    torch.set_num_threads(nthreads)
     cfg = U.SimpleUNetConfig.celeba_hq()
     sd = U.init_state_dict(cfg, 1234)
     op = O.SuperResolution.make(3, RES, 4)
@@ -120,8 +124,8 @@ def cpu_reference_rate(steps, warmup, sample_batch=2, sample_pairs=3):
     dt = (time.perf_counter() - t0) / steps
     per_pair = dt / sample_pairs
     rate = sample_batch / (per_pair * T_SAMPLING)
-    return rate, dt, dict(cores=os.cpu_count(), kind="port",
-                          sample=f"{sample_batch} images x {sample_pairs} of 100 DDIM steps per bench step (oracle port of the reference sampler, torch CPU fp32, {os.cpu_count()} threads), extrapolated x{T_SAMPLING / sample_pairs:.1f}")
+    return rate, dt, dict(cores=nthreads, kind="port",
+                          sample=f"{sample_batch} images x {sample_pairs} of 100 DDIM steps per bench step (oracle port of the reference sampler, torch CPU fp32, {nthreads} of {os.cpu_count()} host threads: more threads are slower), extrapolated x{T_SAMPLING / sample_pairs:.1f}")
 
 
 def run_reference(args):

@@ -110,7 +110,7 @@ void UNetEngine::add_op(const std::string& name, const std::string& kind, double
 
 // GroupNorm(+SiLU) + fp16 split of x into scratch planes dst (dims as the consuming convolution sees them)
 void UNetEngine::emit_gn_split(const std::string& name, const View& x, const std::string& norm, bool silu, int mode,
-                               SplitView& dst, const float* ss, int ss_ld) {
+                               SplitView& dst, const float* ss, int ss_ld, SplitView* raw) {
   const long long out_elems = mode == SPLIT_UP2 ? x.pixels() * x.C * 4 : (mode == SPLIT_AVG2 ? x.pixels() * x.C / 4 : x.pixels() * x.C);
   DDNM_CHECK((size_t)out_elems <= split_elems_, "split scratch too small");
   dst.C = x.C;
@@ -126,9 +126,14 @@ void UNetEngine::emit_gn_split(const std::string& name, const View& x, const std
     const int groups = groups_;
     const float eps = eps_;
     add_op(name + ".gn_stats", "gn_stats", 0, in_bytes, [=](cudaStream_t s) { gn_stats(x, groups, st, s); });
-    __half *hi = dst.hi, *lo = dst.lo;
-    add_op(name + ".gn_split", "gn_split", 0, in_bytes + out_elems * 4.0,
-           [=](cudaStream_t s) { gn_apply_split(x, groups, st, g, b, eps, silu, mode, hi, lo, s, ss, ss_ld); });
+    __half *hi = dst.hi, *lo = dst.lo, *rhi = nullptr, *rlo = nullptr;
+    if (raw) {
+      DDNM_CHECK(mode == SPLIT_SAME, "raw side output only with the plain split");
+      raw->N = x.N; raw->H = x.H; raw->W = x.W; raw->C = x.C;
+      rhi = raw->hi; rlo = raw->lo;
+    }
+    add_op(name + ".gn_split", "gn_split", 0, in_bytes + out_elems * 4.0 * (raw ? 2 : 1),
+           [=](cudaStream_t s) { gn_apply_split(x, groups, st, g, b, eps, silu, mode, hi, lo, s, ss, ss_ld, rhi, rlo); });
   } else {
     __half *hi = dst.hi, *lo = dst.lo;
     add_op(name + ".split", "gn_split", 0, in_bytes + out_elems * 4.0,

@@ -92,8 +92,9 @@ class UNetEngine {
   void add_op(const std::string& name, const std::string& kind, double flops, double bytes, std::function<void(cudaStream_t)> f);
   // norm: parameter prefix of the GroupNorm ("" = raw split); ss: optional per-(image, channel) scale/shift rows
   // [scale(C) | shift(C)] with row pitch ss_ld (use_scale_shift_norm, unet.py:250-252)
+  // raw: optional second destination receiving the un-normalised split of x in the same pass (1x1 shortcut input)
   void emit_gn_split(const std::string& name, const View& x, const std::string& norm, bool silu, int mode, SplitView& dst,
-                     const float* ss = nullptr, int ss_ld = 0);
+                     const float* ss = nullptr, int ss_ld = 0, SplitView* raw = nullptr);
   void emit_tc(const std::string& name, const SplitView& a, int mode, const SplitView* side, const TcWeights& w, int Cout,
                const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr, int res_mode = 0);
   void emit_stem(const std::string& wname, const View& out);

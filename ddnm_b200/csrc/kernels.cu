@@ -96,7 +96,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
                                 const double* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu, int mode, int pix_per_cta,
                                 __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ out32,
-                                const float* __restrict__ ss, int ss_ld) {
+                                const float* __restrict__ ss, int ss_ld, __half* __restrict__ raw_hi,
+                                __half* __restrict__ raw_lo) {
   __shared__ float sc[MAX_C], sh[MAX_C];
   const int n = blockIdx.y;
   const int HW = H * W;
@@ -172,6 +173,15 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
     const float4 a = __ldg(reinterpret_cast<const float4*>(src));
     const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
     float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (!F32OUT && raw_hi) {  // second output: the un-normalised tensor (input of the 1x1 shortcut convolution)
+      __align__(16) __half rh[8];
+      __align__(16) __half rl[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_f16(v[j], rh[j], rl[j]);
+      const size_t o = ((size_t)n * HW + p) * C + c;
+      *reinterpret_cast<uint4*>(raw_hi + o) = *reinterpret_cast<const uint4*>(rh);
+      *reinterpret_cast<uint4*>(raw_lo + o) = *reinterpret_cast<const uint4*>(rl);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       v[j] = fmaf(v[j], a8[j], b8[j]);
@@ -215,7 +225,9 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
 }
 
 static void gn_apply_launch(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
-                            bool silu, int mode, __half* hi, __half* lo, float* out32, cudaStream_t st, const float* ss, int ss_ld) {
+                            bool silu, int mode, __half* hi, __half* lo, float* out32, cudaStream_t st, const float* ss, int ss_ld,
+                            __half* raw_hi = nullptr, __half* raw_lo = nullptr) {
+  if (raw_hi) DDNM_CHECK(mode == SPLIT_SAME && raw_lo && !out32, "raw side output only with the plain split");
   DDNM_CHECK(x.C % 8 == 0 && x.C <= MAX_C && x.ld % 4 == 0, "gn_apply: unsupported channel count");
   if (mode == SPLIT_S2D || mode == SPLIT_AVG2) DDNM_CHECK(x.H % 2 == 0 && x.W % 2 == 0, "space-to-depth / avg-pool need even dims");
   if (ss) DDNM_CHECK(stats != nullptr, "scale-shift needs a normalisation");
@@ -228,16 +240,17 @@ static void gn_apply_launch(const View& x, int groups, const double* stats, cons
   dim3 grid(cdiv(HW, ppc), x.N);
   if (out32)
     gn_apply_kernel<true><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, gamma, beta, eps, silu, mode,
-                                                 ppc, nullptr, nullptr, out32, ss, ss_ld);
+                                                 ppc, nullptr, nullptr, out32, ss, ss_ld, nullptr, nullptr);
   else
     gn_apply_kernel<false><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, gamma, beta, eps, silu, mode,
-                                                  ppc, hi, lo, nullptr, ss, ss_ld);
+                                                  ppc, hi, lo, nullptr, ss, ss_ld, raw_hi, raw_lo);
   CUDA_CHECK(cudaGetLastError());
 }
 
 void gn_apply_split(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
-                    bool silu, int mode, __half* hi, __half* lo, cudaStream_t s, const float* ss, int ss_ld) {
-  gn_apply_launch(x, groups, stats, gamma, beta, eps, silu, mode, hi, lo, nullptr, s, ss, ss_ld);
+                    bool silu, int mode, __half* hi, __half* lo, cudaStream_t s, const float* ss, int ss_ld, __half* raw_hi,
+                    __half* raw_lo) {
+  gn_apply_launch(x, groups, stats, gamma, beta, eps, silu, mode, hi, lo, nullptr, s, ss, ss_ld, raw_hi, raw_lo);
 }
 void gn_apply_f32(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
                   bool silu, float* out, cudaStream_t s) {
@@ -323,77 +336,89 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
   constexpr int TW = 32, TH = 2;
   extern __shared__ float smem[];
   const int PS = Cin + 4;                                  // padded pixel stride (floats): conflict-free LDS.128
-  float* tile = smem;                                      // [(TH+2)*(TW+2)][PS]
-  float* ws = tile + (TH + 2) * (TW + 2) * PS;             // [9][COUT][Cin]
+  float* tile_s = smem;                                    // [(TH+2)*(TW+2)][PS]
+  float* ws = tile_s + (TH + 2) * (TW + 2) * PS;           // [9][COUT][Cin]
   float* sc = ws + 9 * COUT * Cin;                         // [Cin]
   float* sh = sc + Cin;                                    // [Cin]
   float* red = sh + Cin;                                   // [4][64][COUT]
-  const int n = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
   const int HW = H * W;
-  for (int i = threadIdx.x; i < 9 * COUT * Cin; i += blockDim.x) {
-    const int ci = i % Cin, co = (i / Cin) % COUT, tap = i / (Cin * COUT);
-    ws[i] = __ldg(&w[((size_t)co * Cin + ci) * 9 + tap]);
-  }
-  {
-    const int cpg = Cin / groups;
-    const double cnt = (double)HW * cpg;
-    for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
-      const int g = c / cpg;
-      const double mean = stats[((size_t)n * groups + g) * 2] / cnt;
-      double var = stats[((size_t)n * groups + g) * 2 + 1] / cnt - mean * mean;
-      var = var < 0 ? 0 : var;
-      const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
-      sc[c] = a;
-      sh[c] = beta[c] - (float)mean * a;
+  // weights -> smem once per (persistent) CTA, transposed to [tap][co][ci]
+  for (int co = 0; co < COUT; ++co)
+    for (int i = threadIdx.x; i < Cin * 9; i += blockDim.x) {
+      const int ci = i / 9, tap = i - ci * 9;
+      ws[(tap * COUT + co) * Cin + ci] = __ldg(&w[(size_t)co * Cin * 9 + i]);
     }
-  }
-  __syncthreads();
+  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const int total = tiles_per_img * N;
   const int C4 = Cin >> 2;
-  for (int i = threadIdx.x; i < (TH + 2) * (TW + 2) * C4; i += blockDim.x) {
-    const int c4 = i % C4, pp = i / C4;
-    const int tx = pp % (TW + 2), ty = pp / (TW + 2);
-    const int gy = y0 + ty - 1, gx = x0 + tx - 1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);            // zero padding applies AFTER the activation (conv pads its input)
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + gy) * W + gx) * ld + c4 * 4));
-      const int c = c4 * 4;
-      v.x = swishf(fmaf(v.x, sc[c + 0], sh[c + 0]));
-      v.y = swishf(fmaf(v.y, sc[c + 1], sh[c + 1]));
-      v.z = swishf(fmaf(v.z, sc[c + 2], sh[c + 2]));
-      v.w = swishf(fmaf(v.w, sc[c + 3], sh[c + 3]));
-    }
-    *reinterpret_cast<float4*>(tile + (size_t)pp * PS + c4 * 4) = v;
-  }
-  __syncthreads();
   const int pix = threadIdx.x & 63, quarter = threadIdx.x >> 6;
   const int py = pix >> 5, px = pix & 31;
   const int cq = Cin >> 2;                                 // channels per quarter
-  float acc[COUT];
+  int cur_n = -1;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int n = tile / tiles_per_img;
+    const int tr = tile - n * tiles_per_img;
+    const int y0 = (tr / tiles_x) * TH, x0 = (tr % tiles_x) * TW;
+    __syncthreads();                                       // previous tile fully consumed (tile / red / sc / sh reusable)
+    if (n != cur_n) {
+      cur_n = n;
+      const int cpg = Cin / groups;
+      const double cnt = (double)HW * cpg;
+      for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+        const int g = c / cpg;
+        const double mean = stats[((size_t)n * groups + g) * 2] / cnt;
+        double var = stats[((size_t)n * groups + g) * 2 + 1] / cnt - mean * mean;
+        var = var < 0 ? 0 : var;
+        const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
+        sc[c] = a;
+        sh[c] = beta[c] - (float)mean * a;
+      }
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < (TH + 2) * (TW + 2) * C4; i += blockDim.x) {
+      const int pp = i / C4, c4 = i - pp * C4;
+      const int ty = pp / (TW + 2), tx = pp - ty * (TW + 2);
+      const int gy = y0 + ty - 1, gx = x0 + tx - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);          // zero padding applies AFTER the activation (conv pads its input)
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + gy) * W + gx) * ld + c4 * 4));
+        const int c = c4 * 4;
+        v.x = swishf(fmaf(v.x, sc[c + 0], sh[c + 0]));
+        v.y = swishf(fmaf(v.y, sc[c + 1], sh[c + 1]));
+        v.z = swishf(fmaf(v.z, sc[c + 2], sh[c + 2]));
+        v.w = swishf(fmaf(v.w, sc[c + 3], sh[c + 3]));
+      }
+      *reinterpret_cast<float4*>(tile_s + (size_t)pp * PS + c4 * 4) = v;
+    }
+    __syncthreads();
+    float acc[COUT];
 #pragma unroll
-  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const float* tp = tile + (size_t)((py + tap / 3) * (TW + 2) + px + tap % 3) * PS + quarter * cq;
-    const float* wp = ws + (size_t)tap * COUT * Cin + quarter * cq;
-    for (int c = 0; c < cq; c += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(tp + c);
+    for (int tap = 0; tap < 9; ++tap) {
+      const float* tp = tile_s + (size_t)((py + tap / 3) * (TW + 2) + px + tap % 3) * PS + quarter * cq;
+      const float* wp = ws + (size_t)tap * COUT * Cin + quarter * cq;
+      for (int c = 0; c < cq; c += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(tp + c);
 #pragma unroll
-      for (int co = 0; co < COUT; ++co) {
-        const float4 ww = *reinterpret_cast<const float4*>(wp + (size_t)co * Cin + c);
-        acc[co] = fmaf(v.x, ww.x, fmaf(v.y, ww.y, fmaf(v.z, ww.z, fmaf(v.w, ww.w, acc[co]))));
+        for (int co = 0; co < COUT; ++co) {
+          const float4 ww = *reinterpret_cast<const float4*>(wp + (size_t)co * Cin + c);
+          acc[co] = fmaf(v.x, ww.x, fmaf(v.y, ww.y, fmaf(v.z, ww.z, fmaf(v.w, ww.w, acc[co]))));
+        }
       }
     }
-  }
 #pragma unroll
-  for (int co = 0; co < COUT; ++co) red[(quarter * 64 + pix) * COUT + co] = acc[co];
-  __syncthreads();
-  for (int i = threadIdx.x; i < 64 * COUT; i += blockDim.x) {
-    const int p = i & 63, co = i >> 6;
-    const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
-    if (gy < H && gx < W) {
-      const float v = (red[(0 * 64 + p) * COUT + co] + red[(1 * 64 + p) * COUT + co]) +
-                      (red[(2 * 64 + p) * COUT + co] + red[(3 * 64 + p) * COUT + co]) + bias[co];
-      out[(((size_t)n * COUT + co) * H + gy) * W + gx] = v;
+    for (int co = 0; co < COUT; ++co) red[(quarter * 64 + pix) * COUT + co] = acc[co];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * COUT; i += blockDim.x) {
+      const int p = i & 63, co = i >> 6;
+      const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
+      if (gy < H && gx < W) {
+        const float v = (red[(0 * 64 + p) * COUT + co] + red[(1 * 64 + p) * COUT + co]) +
+                        (red[(2 * 64 + p) * COUT + co] + red[(3 * 64 + p) * COUT + co]) + bias[co];
+        out[(((size_t)n * COUT + co) * H + gy) * W + gx] = v;
+      }
     }
   }
 }
@@ -403,7 +428,12 @@ void head_conv_gn_silu(const View& x, int groups, const double* stats, const flo
   DDNM_CHECK(x.C % 16 == 0 && x.ld % 4 == 0 && x.C % groups == 0, "head convolution: Cin % 16");
   const size_t smem = ((size_t)4 * 34 * (x.C + 4) + (size_t)9 * Cout * x.C + 2 * x.C + 4 * 64 * Cout) * sizeof(float);
   DDNM_CHECK(smem <= 227 * 1024, "head convolution tile does not fit shared memory");
-  dim3 grid(cdiv(x.W, 32), cdiv(x.H, 2), x.N);
+  const int total_tiles = cdiv(x.W, 32) * cdiv(x.H, 2) * x.N;
+  int dev = 0, sms = 148;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+  const int grid = std::min(total_tiles, sms * per_sm);    // persistent CTAs: weights / scale tables staged once
   static size_t smem_set[2] = {0, 0};
   if (Cout == 3) {
     if (smem > smem_set[0]) {

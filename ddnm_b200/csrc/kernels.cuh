@@ -17,7 +17,8 @@ void gn_stats(const View& x, int groups, double* stats, cudaStream_t s);
 // pool of the activated tensor (ResBlock(down=True), unet.py:237-241).  ss != nullptr: use_scale_shift_norm —
 // y = GN(x) * (1 + ss[n*ss_ld + c]) + ss[n*ss_ld + C + c]   (unet.py:250-252).
 void gn_apply_split(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
-                    bool silu, int mode, __half* hi, __half* lo, cudaStream_t s, const float* ss = nullptr, int ss_ld = 0);
+                    bool silu, int mode, __half* hi, __half* lo, cudaStream_t s, const float* ss = nullptr, int ss_ld = 0,
+                    __half* raw_hi = nullptr, __half* raw_lo = nullptr);  // raw_*: also emit the un-normalised split (SPLIT_SAME)
 // same normalisation, fp32 contiguous NHWC output (feeds the small-Cout output convolution)
 void gn_apply_f32(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
                   bool silu, float* out, cudaStream_t s);

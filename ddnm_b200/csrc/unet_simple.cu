@@ -15,7 +15,8 @@ void UNetSimple::emit_resblock(const std::string& p, const View& x, const View& 
   const int Cin = x.C, Cout = out.C;
   DDNM_CHECK((size_t)(x.pixels() * Cout) <= hbuf_elems_, "hbuf too small");
   SplitView A{splitA_hi_, splitA_lo_}, Bs{splitB_hi_, splitB_lo_};
-  emit_gn_split(p + ".norm1", x, p + ".norm1", true, SPLIT_SAME, A);
+  // blocks with a 1x1 shortcut also need the raw split of x: produced by the same pass that normalises it
+  emit_gn_split(p + ".norm1", x, p + ".norm1", true, SPLIT_SAME, A, nullptr, 0, Cin != Cout ? &Bs : nullptr);
   TcWeights w1 = prep_weights(p + ".conv1.weight", Cout, Cin, 9, "", 0);
   View h;
   h.p = hbuf_; h.N = B_; h.H = x.H; h.W = x.W; h.C = Cout; h.ld = Cout;
@@ -23,7 +24,6 @@ void UNetSimple::emit_resblock(const std::string& p, const View& x, const View& 
   emit_gn_split(p + ".norm2", h, p + ".norm2", true, SPLIT_SAME, A);
   if (Cin != Cout) {
     // nin_shortcut (1x1 on the raw block input) rides along as extra K blocks of conv2's GEMM
-    emit_gn_split(p + ".nin_in", x, "", false, SPLIT_SAME, Bs);
     TcWeights w2 = prep_weights(p + ".conv2.weight", Cout, Cout, 9, p + ".nin_shortcut.weight", Cin);
     emit_tc(p + ".conv2+nin", A, TAPS_3X3, &Bs, w2, Cout, out, bias_sum(p + ".conv2.bias", p + ".nin_shortcut.bias", Cout), 0,
             nullptr, 0);

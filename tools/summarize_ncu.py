@@ -1,0 +1,63 @@
+"""Turn ncu outputs brought back in gpurun_out/ into the committed summaries under profiles/.
+  python tools/summarize_ncu.py launches gpurun_out/launches_r01.csv profiles/r01_launch_summary.md
+  python tools/summarize_ncu.py full gpurun_out/prof_tc.ncu-rep profiles/r01_conv_tc_full.md
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+
+def launches(src, dst):
+    rows = list(csv.reader(open(src)))
+    hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[hi]
+    k, v, u = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg, n = collections.OrderedDict(), 0
+    for r in rows[hi + 1:]:
+        if len(r) <= v:
+            continue
+        name = re.sub(r"\(.*", "", r[k]).replace("void ", "").replace("ddnm::", "")
+        t = float(r[v].replace(",", ""))
+        t = t / 1e3 if r[u] == "ns" else (t * 1e3 if r[u] == "ms" else t)
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += t
+        n += 1
+    tot = sum(a[1] for a in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu launch list summary ({src})\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` — per-launch device time, "
+                f"cold-cache and serialised: compare SHARES, not absolutes.\n\n{n} launches, {tot / 1e3:.2f} ms total.\n\n"
+                "| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
+        for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{name}` | {c} | {t:.1f} | {t / tot * 100:.1f}% |\n")
+    print(open(dst).read())
+
+
+WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg.per_second", "lts__t_bytes.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg"]
+
+
+def full(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full summary ({src})\n\n")
+        for r in rows[2:]:
+            f.write(f"## {r[idx['Kernel Name']][:90]}  grid {r[idx['Grid Size']]} block {r[idx['Block Size']]}\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for w in WANT:
+                if w in idx:
+                    f.write(f"| {w} | {r[idx[w]]} | {units[idx[w]]} |\n")
+            f.write("\n")
+    print(open(dst).read())
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
