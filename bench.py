@@ -260,9 +260,16 @@ def main():
         all_ms = sum(p["ms"] for p in prof)
         ach = tc_fl / tc_ms / 1e9 if tc_ms > 0 else 0.0
         fwd_launches = sum(4 if p["kind"] == "temb" else (0 if p["kind"] == "memset" else 1) for p in prof)
+        traffic = None
+        try:   # one `ncu --set full` capture of the top launch (profiles/, per launch like `achieved`)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_tc_traffic.json")))["top_launch"]
+            traffic = dict(bytes=tj["traffic_bytes"], algorithmic_bytes=tj["algorithmic_bytes"], launch=tj["name"],
+                           tensor_pipe_active_pct=tj["tensor_pipe_active_pct"], source="profiles/r01_conv_tc_traffic.json")
+        except Exception:
+            pass
         roof = dict(bound="tensor", kernel="conv_tc_kernel<BN> (tcgen05 implicit GEMM, 3x fp16 split)", achieved=ach, peak=pk["tf_sust"],
                     unit="TFLOP/s", frac=ach / pk["tf_sust"], hw_mma_factor=3, frac_hw=3 * ach / pk["tf_sust"],
-                    peak_source=pk["src"] + ", sustained bf16 cuBLAS", traffic=None,
+                    peak_source=pk["src"] + ", sustained bf16 cuBLAS", traffic=traffic,
                     launches_per_forward=len(tc), avg_launch_ms=tc_ms / max(1, len(tc)), share_of_forward=tc_ms / all_ms,
                     note="achieved = algorithmic conv/GEMM FLOPs (2*M*N*K once) / summed per-launch CUDA-event time; each algorithmic MAC costs 3 fp16 MMAs (hi*hi+hi*lo+lo*hi) for fp32-grade products, so frac_hw = 3*frac is the tensor-pipe utilisation")
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,

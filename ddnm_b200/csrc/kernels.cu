@@ -456,32 +456,45 @@ void head_conv_gn_silu(const View& x, int groups, const double* stats, const flo
 // ---------------------------------------------------------------------------------------------------------------
 // Timestep MLP pieces (models.py:6-24, 305-308, 121).  One warp per output element.
 // ---------------------------------------------------------------------------------------------------------------
+// one warp per output feature o; the weight row is read once and reused for every image of the batch
 __global__ void linear_kernel(const float* __restrict__ in, int N, int K, const float* __restrict__ W,
                               const float* __restrict__ bias, int O, float* __restrict__ out, int ldo, int act_in, int act_out) {
-  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int o = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (gw >= (long long)N * O) return;
-  const int n = (int)(gw / O), o = (int)(gw % O);
-  const float* a = in + (long long)n * K;
+  if (o >= O) return;
   const float* w = W + (long long)o * K;
-  float acc = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    float v = a[k];
-    if (act_in) v = swishf(v);
-    acc = fmaf(v, w[k], acc);
-  }
+  constexpr int NB = 8;
+  for (int n0 = 0; n0 < N; n0 += NB) {
+    float acc[NB];
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-  if (lane == 0) {
-    float r = acc + (bias ? bias[o] : 0.f);
-    if (act_out) r = swishf(r);
-    out[(long long)n * ldo + o] = r;
+    for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(w + k);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (n0 + j < N) {
+          float v = in[(long long)(n0 + j) * K + k];
+          if (act_in) v = swishf(v);
+          acc[j] = fmaf(v, wv, acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      float a = acc[j];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+      if (lane == 0 && n0 + j < N) {
+        float r = a + (bias ? bias[o] : 0.f);
+        if (act_out) r = swishf(r);
+        out[(long long)(n0 + j) * ldo + o] = r;
+      }
+    }
   }
 }
 void linear(const float* in, int N, int K, const float* W, const float* bias, int O, float* out, int ldo, int act_in,
             int act_out, cudaStream_t st) {
-  const long long warps = (long long)N * O;
-  linear_kernel<<<(int)cdivll(warps * 32, 256), 256, 0, st>>>(in, N, K, W, bias, O, out, ldo, act_in, act_out);
+  linear_kernel<<<(int)cdivll((long long)O * 32, 256), 256, 0, st>>>(in, N, K, W, bias, O, out, ldo, act_in, act_out);
   CUDA_CHECK(cudaGetLastError());
 }
 

@@ -306,7 +306,6 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   const int taps = (mode0 == TAPS_1X1) ? 1 : 9;
   DDNM_CHECK(src0.C % BK == 0, "tensor-core conv needs Cin % 64 == 0");
   DDNM_CHECK(Cout % 64 == 0, "tensor-core conv needs Cout % 64 == 0");
-  L.BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
   p.H = out.H; p.W = out.W; p.N = out.N;
   // M tile: 128 consecutive pixels as [bn][bh][bw]
   p.bw = out.W >= 128 ? 128 : out.W;
@@ -317,6 +316,18 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   p.tiles_x = out.W / p.bw;
   p.tiles_y = out.H / p.bh;
   p.tiles_n = cdiv(out.N, p.bn);
+  // N tile: the widest that still gives every SM a tile.  Low-resolution layers (8x8, 16x16) have few M tiles but a long
+  // K loop (up to 144 k-blocks), so narrow N tiles spread them over more SMs at no extra HBM cost (A stays in L2).
+  {
+    const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+    L.BN = 64;
+    for (int bn : {256, 128}) {
+      if (Cout % bn == 0 && (long long)m_tiles * (Cout / bn) >= num_sms) {
+        L.BN = bn;
+        break;
+      }
+    }
+  }
   p.n_tiles = Cout / L.BN;
   p.mode0 = mode0;
   p.cb0 = src0.C / BK;
