@@ -128,7 +128,7 @@ def cpu_reference_rate(steps, warmup, sample_batch=2, sample_pairs=3):
                           sample=f"{sample_batch} images x {sample_pairs} of 100 DDIM steps per bench step (oracle port of the reference sampler, torch CPU fp32, {nthreads} of {os.cpu_count()} host threads: more threads are slower), extrapolated x{T_SAMPLING / sample_pairs:.1f}")
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -139,10 +139,19 @@ def run_reference(args):
                 ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32", data="synthetic",
                 config=dict(workload=WORKLOAD, note="CPU path of the reference algorithm; bounded sample, see cpu_baseline.sample"),
                 cpu_baseline=cb, e2e=dict(value=rate, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # exactly ONE line on stdout: libraries (NCCL prints its version banner) write to fd 1, so park the real stdout and
+    # point fd 1 at stderr until the JSON line is ready
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w")
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -152,7 +161,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
 
     import torch
@@ -288,7 +297,7 @@ def main():
             line["cpu_baseline"] = cb
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

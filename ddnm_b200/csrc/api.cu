@@ -147,12 +147,12 @@ int ddnm_conv_tc(const float* x, int N, int H, int W, int Cin, const float* w, c
   A.hi = tmp.get<__half>(pe); A.lo = tmp.get<__half>(pe); A.C = Cin;
   if (smode == SPLIT_S2D) { A.N = 4 * N; A.H = oH; A.W = oW; } else { A.N = N; A.H = oH; A.W = oW; }
   View xv = mkview(const_cast<float*>(x), N, H, W, Cin);
-  gn_apply_split(xv, 1, nullptr, nullptr, nullptr, 0.f, false, smode, A.hi, A.lo, s);
+  gn_apply_split(xv, 1, false, nullptr, nullptr, 0.f, false, smode, A.hi, A.lo, s);
   SplitView S;
   if (side_x) {
     const size_t se = (size_t)N * oH * oW * CinSide;
     S.hi = tmp.get<__half>(se); S.lo = tmp.get<__half>(se); S.N = N; S.H = oH; S.W = oW; S.C = CinSide;
-    gn_apply_split(mkview(const_cast<float*>(side_x), N, oH, oW, CinSide), 1, nullptr, nullptr, nullptr, 0.f, false, SPLIT_SAME,
+    gn_apply_split(mkview(const_cast<float*>(side_x), N, oH, oW, CinSide), 1, false, nullptr, nullptr, 0.f, false, SPLIT_SAME,
                    S.hi, S.lo, s);
   }
   const int ktot = taps * Cin + (side_x ? CinSide : 0);
@@ -187,7 +187,7 @@ int ddnm_conv_tc_bench(int N, int H, int W, int Cin, int Cout, int mode, int ite
   A.hi = tmp.get<__half>(pe); A.lo = tmp.get<__half>(pe); A.N = N; A.H = H; A.W = W; A.C = Cin;
   float* xf = tmp.get<float>(pe);
   CUDA_CHECK(cudaMemset(xf, 0, pe * 4));
-  gn_apply_split(mkview(xf, N, H, W, Cin), 1, nullptr, nullptr, nullptr, 0.f, false, SPLIT_SAME, A.hi, A.lo, 0);
+  gn_apply_split(mkview(xf, N, H, W, Cin), 1, false, nullptr, nullptr, 0.f, false, SPLIT_SAME, A.hi, A.lo, 0);
   const int ktot = taps * Cin;
   __half* wh = tmp.get<__half>((size_t)Cout * ktot);
   __half* wl = tmp.get<__half>((size_t)Cout * ktot);
@@ -217,11 +217,13 @@ int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const
   DDNM_API_BEGIN
   cudaStream_t s = (cudaStream_t)stream;
   Tmp tmp;
-  double* st = tmp.get<double>((size_t)N * groups * 2);
-  CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)N * groups * 2 * sizeof(double), s));
+  double* st = tmp.get<double>((size_t)N * C * 2);
+  CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)N * C * 2 * sizeof(double), s));
   View xv = mkview(const_cast<float*>(x), N, H, W, C);
-  gn_stats(xv, groups, st, s);
-  gn_apply_f32(xv, groups, st, gamma, beta, eps, silu != 0, out, s);
+  xv.st = st;
+  xv.st_ld = C;
+  gn_stats(xv, s);
+  gn_apply_f32(xv, groups, gamma, beta, eps, silu != 0, out, s);
   CUDA_CHECK(cudaStreamSynchronize(s));
   DDNM_API_END
 }

@@ -35,14 +35,20 @@ inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 
 // A strided NHWC fp32 activation view: element (n, y, x, c) at p[((n*H + y)*W + x)*ld + c].
 // ld >= C lets a tensor live inside a channel slice of a wider (concat) buffer.
+// st (optional): per-(image, channel) running sums for GroupNorm, st[(n*st_ld + c)*2 + {0,1}] = {sum, sum of squares}
+// over the image's pixels; filled by the kernel that PRODUCES the tensor (tensor-core epilogue / gn_stats), so the
+// normalisation never re-reads the tensor just to reduce it.
 struct View {
   float* p = nullptr;
   int N = 0, H = 0, W = 0, C = 0, ld = 0;
+  double* st = nullptr;
+  int st_ld = 0;
   long long pixels() const { return (long long)N * H * W; }
   View slice(int c0, int c) const {
     View v = *this;
     v.p = p + c0;
     v.C = c;
+    if (st) v.st = st + 2 * (size_t)c0;
     return v;
   }
 };

@@ -67,12 +67,25 @@ View UNetEngine::new_view(int H, int W, int C) {
   View v;
   v.N = B_; v.H = H; v.W = W; v.C = C; v.ld = C;
   v.p = (float*)arena_.alloc((size_t)B_ * H * W * C * sizeof(float));
+  v.st = new_stats(C);
+  v.st_ld = C;
   return v;
 }
 
-double* UNetEngine::new_stats() {
-  DDNM_CHECK(stats_count_ < stats_cap_, "stats pool exhausted");
-  return stats_base_ + (stats_count_++) * (size_t)B_ * groups_ * 2;
+// a [B][C][2] block of per-channel GroupNorm sums from the pool that one memset clears at the start of every forward
+double* UNetEngine::new_stats(int C) {
+  const size_t need = (size_t)B_ * C * 2;
+  if (stats_chunks_.empty() || stats_chunks_.back().used + need > stats_chunks_.back().cap) {
+    StatsChunk c;
+    c.cap = std::max<size_t>(need, (size_t)1 << 20);   // doubles
+    c.used = 0;
+    c.p = (double*)arena_.alloc(c.cap * sizeof(double));
+    stats_chunks_.push_back(c);
+  }
+  StatsChunk& c = stats_chunks_.back();
+  double* p = c.p + c.used;
+  c.used += need;
+  return p;
 }
 
 UNetEngine::TcWeights UNetEngine::prep_weights(const std::string& main, int Cout, int Cin, int taps, const std::string& side,
@@ -120,12 +133,11 @@ void UNetEngine::emit_gn_split(const std::string& name, const View& x, const std
   else { dst.N = 4 * x.N; dst.H = x.H / 2; dst.W = x.W / 2; }
   const double in_bytes = (double)x.pixels() * x.C * 4;
   if (!norm.empty()) {
-    double* st = new_stats();
+    DDNM_CHECK(x.st != nullptr, "GroupNorm input without producer-side statistics: " + name);
     const float* g = P(norm + ".weight", x.C);
     const float* b = P(norm + ".bias", x.C);
     const int groups = groups_;
     const float eps = eps_;
-    add_op(name + ".gn_stats", "gn_stats", 0, in_bytes, [=](cudaStream_t s) { gn_stats(x, groups, st, s); });
     __half *hi = dst.hi, *lo = dst.lo, *rhi = nullptr, *rlo = nullptr;
     if (raw) {
       DDNM_CHECK(mode == SPLIT_SAME, "raw side output only with the plain split");
@@ -133,11 +145,11 @@ void UNetEngine::emit_gn_split(const std::string& name, const View& x, const std
       rhi = raw->hi; rlo = raw->lo;
     }
     add_op(name + ".gn_split", "gn_split", 0, in_bytes + out_elems * 4.0 * (raw ? 2 : 1),
-           [=](cudaStream_t s) { gn_apply_split(x, groups, st, g, b, eps, silu, mode, hi, lo, s, ss, ss_ld, rhi, rlo); });
+           [=](cudaStream_t s) { gn_apply_split(x, groups, true, g, b, eps, silu, mode, hi, lo, s, ss, ss_ld, rhi, rlo); });
   } else {
     __half *hi = dst.hi, *lo = dst.lo;
     add_op(name + ".split", "gn_split", 0, in_bytes + out_elems * 4.0,
-           [=](cudaStream_t s) { gn_apply_split(x, 1, nullptr, nullptr, nullptr, 0.f, silu, mode, hi, lo, s); });
+           [=](cudaStream_t s) { gn_apply_split(x, 1, false, nullptr, nullptr, 0.f, silu, mode, hi, lo, s); });
   }
 }
 
@@ -150,7 +162,7 @@ void UNetEngine::emit_tc(const std::string& name, const SplitView& a, int mode, 
 }
 
 // scratch every program needs; split planes are shared by all convolutions of a forward (stream order serialises them)
-void UNetEngine::alloc_common(size_t split_elems, size_t hbuf_elems, int n_gn) {
+void UNetEngine::alloc_common(size_t split_elems, size_t hbuf_elems) {
   split_elems_ = split_elems;
   hbuf_elems_ = hbuf_elems;
   splitA_hi_ = (__half*)arena_.alloc(split_elems * 2);
@@ -158,14 +170,9 @@ void UNetEngine::alloc_common(size_t split_elems, size_t hbuf_elems, int n_gn) {
   splitB_hi_ = (__half*)arena_.alloc(split_elems * 2);
   splitB_lo_ = (__half*)arena_.alloc(split_elems * 2);
   hbuf_ = (float*)arena_.alloc(hbuf_elems * 4);
-  stats_cap_ = n_gn;
-  stats_base_ = (double*)arena_.alloc((size_t)n_gn * B_ * groups_ * 2 * sizeof(double));
   x_in_ = (float*)arena_.alloc((size_t)B_ * in_ch_ * R_ * R_ * 4);
   t_in_ = (float*)arena_.alloc((size_t)B_ * 4);
   out_ = (float*)arena_.alloc((size_t)B_ * out_ch_ * R_ * R_ * 4);
-  double* sb = stats_base_;
-  const size_t sbytes = (size_t)n_gn * B_ * groups_ * 2 * sizeof(double);
-  add_op("stats.zero", "memset", 0, (double)sbytes, [=](cudaStream_t s) { CUDA_CHECK(cudaMemsetAsync(sb, 0, sbytes, s)); });
 }
 
 // network stem: 3x3 conv on the caller's NCHW tensor -> NHWC view
@@ -175,26 +182,36 @@ void UNetEngine::emit_stem(const std::string& wname, const View& out) {
   const int cin = in_ch_;
   add_op("stem", "stem", 2.0 * B_ * R_ * R_ * (double)out.C * cin * 9, (double)B_ * R_ * R_ * (cin + out.C) * 4,
          [=](cudaStream_t s) { conv3x3_small_cin(xin, cin, w, b, out, s); });
+  // the only GroupNorm input not written by the tensor-core kernel: reduce it separately
+  add_op("stem.gn_stats", "gn_stats", 0, (double)out.pixels() * out.C * 4, [=](cudaStream_t s) { gn_stats(out, s); });
 }
 
 // network head: GroupNorm + SiLU + 3x3 conv to out_ch, NCHW result
 void UNetEngine::emit_head(const std::string& norm, const std::string& conv, const View& fh) {
-  double* st = new_stats();
+  DDNM_CHECK(fh.st != nullptr, "head input without statistics");
   const float *g = P(norm + ".weight", fh.C), *b = P(norm + ".bias", fh.C);
   const int groups = groups_;
   const float eps = eps_;
   const double ab = (double)fh.pixels() * fh.C * 4;
-  add_op("head.gn_stats", "gn_stats", 0, ab, [=](cudaStream_t s) { gn_stats(fh, groups, st, s); });
   const float *w = P(conv + ".weight", (long long)out_ch_ * fh.C * 9), *bo = P(conv + ".bias", out_ch_);
   float* o = out_;
   const int oc = out_ch_;
   add_op("head.norm+conv", "head", 2.0 * fh.pixels() * (double)oc * fh.C * 9, ab + (double)fh.pixels() * oc * 4,
-         [=](cudaStream_t s) { head_conv_gn_silu(fh, groups, st, g, b, eps, w, bo, oc, o, s); });
+         [=](cudaStream_t s) { head_conv_gn_silu(fh, groups, g, b, eps, w, bo, oc, o, s); });
 }
 
 void UNetEngine::finalize() {
   DDNM_CHECK(!finalized_, "finalize called twice");
   build_program();
+  // every GroupNorm sum is accumulated with atomics during the forward: clear the pool first
+  std::vector<OpRecord> zero;
+  for (const StatsChunk& c : stats_chunks_) {
+    double* sb = c.p;
+    const size_t sbytes = c.used * sizeof(double);
+    zero.push_back(OpRecord{"stats.zero", "memset", 0, (double)sbytes,
+                            [=](cudaStream_t s) { CUDA_CHECK(cudaMemsetAsync(sb, 0, sbytes, s)); }});
+  }
+  ops_.insert(ops_.begin(), zero.begin(), zero.end());
   CUDA_CHECK(cudaDeviceSynchronize());
   finalized_ = true;
 }

@@ -81,7 +81,7 @@ class UNetEngine {
   struct Param { float* p; long long n; };
   const float* P(const std::string& name, long long expect = -1) const;
   View new_view(int H, int W, int C);
-  double* new_stats();
+  double* new_stats(int C);
   struct TcWeights { __half *hi, *lo; int ktot; };
   // main / side: full parameter names of the OIHW weight tensors ("" = absent)
   TcWeights prep_weights(const std::string& main, int Cout, int Cin, int taps, const std::string& side, int CinSide);
@@ -99,7 +99,7 @@ class UNetEngine {
                const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr, int res_mode = 0);
   void emit_stem(const std::string& wname, const View& out);
   void emit_head(const std::string& norm, const std::string& conv, const View& h);
-  void alloc_common(size_t split_elems, size_t hbuf_elems, int n_gn);
+  void alloc_common(size_t split_elems, size_t hbuf_elems);
   virtual void build_program() = 0;
   void run_ops(cudaStream_t s);
 
@@ -119,8 +119,8 @@ class UNetEngine {
   float* hbuf_ = nullptr;      // resblock intermediate
   size_t hbuf_elems_ = 0;
   float *qkv_ = nullptr, *attS_ = nullptr, *attO_ = nullptr;
-  double* stats_base_ = nullptr;
-  size_t stats_count_ = 0, stats_cap_ = 0;
+  struct StatsChunk { double* p; size_t cap, used; };
+  std::vector<StatsChunk> stats_chunks_;
   float *emb_ = nullptr, *temb0_ = nullptr, *temb_ = nullptr, *ca_all_ = nullptr, *freq_ = nullptr;
   int ca_total_ = 0;
   std::map<std::string, int> ca_off_;

@@ -9,12 +9,13 @@ static constexpr int MAX_C = 2048;  // widest concat in either UNet
 __device__ __forceinline__ float swishf(float x) { return x / (1.0f + expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// GroupNorm statistics (torch.nn.GroupNorm(32, C): models.py:32-33 / nn.py:17-19).  One CTA = one image x one
-// pixel chunk; every thread owns 4 fixed channels (float4 loads along the contiguous NHWC channel axis), partial
-// sums meet in shared memory per channel, then per group, then one double atomicAdd pair per (CTA, group).
+// Per-channel sums for GroupNorm (torch.nn.GroupNorm(32, C): models.py:32-33 / nn.py:17-19) of a tensor that was NOT
+// produced by the tensor-core kernel (whose epilogue accumulates them itself).  One CTA = one image x one pixel chunk;
+// every thread owns 4 fixed channels (float4 loads along the contiguous NHWC channel axis), partial sums meet in
+// shared memory per channel, then one double atomicAdd pair per (CTA, channel).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int ld, int groups, int pix_per_cta,
-                                double* __restrict__ stats) {
+__global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int ld, int pix_per_cta,
+                                double* __restrict__ stats, int st_ld) {
   __shared__ float csum[MAX_C], csq[MAX_C];
   const int n = blockIdx.y;
   const int C4 = C >> 2;
@@ -59,20 +60,14 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int 
     }
   }
   __syncthreads();
-  const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    double a = 0, b = 0;
-    for (int j = 0; j < cpg; ++j) {
-      a += (double)csum[g * cpg + j];
-      b += (double)csq[g * cpg + j];
-    }
-    atomicAdd(&stats[((long long)n * groups + g) * 2 + 0], a);
-    atomicAdd(&stats[((long long)n * groups + g) * 2 + 1], b);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&stats[((size_t)n * st_ld + c) * 2 + 0], (double)csum[c]);
+    atomicAdd(&stats[((size_t)n * st_ld + c) * 2 + 1], (double)csq[c]);
   }
 }
 
-void gn_stats(const View& x, int groups, double* stats, cudaStream_t st) {
-  DDNM_CHECK(x.C % 4 == 0 && x.C <= MAX_C && x.C % groups == 0 && x.ld % 4 == 0, "gn_stats: unsupported channel count");
+void gn_stats(const View& x, cudaStream_t st) {
+  DDNM_CHECK(x.C % 4 == 0 && x.C <= MAX_C && x.ld % 4 == 0 && x.st != nullptr, "gn_stats: unsupported channel count / no stats slot");
   const int C4 = x.C / 4;
   const int rows = std::max(1, 256 / C4);
   const int threads = C4 * rows;
@@ -80,7 +75,7 @@ void gn_stats(const View& x, int groups, double* stats, cudaStream_t st) {
   long long want = cdivll((long long)HW * x.N, 592);
   int ppc = (int)std::max<long long>(rows * 4, cdivll(want, rows) * rows);
   dim3 grid(cdiv(HW, ppc), x.N);
-  gn_stats_kernel<<<grid, threads, 0, st>>>(x.p, HW, x.C, x.ld, groups, ppc, stats);
+  gn_stats_kernel<<<grid, threads, 0, st>>>(x.p, HW, x.C, x.ld, ppc, x.st, x.st_ld);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -93,7 +88,7 @@ void gn_stats(const View& x, int groups, double* stats, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------
 template <bool F32OUT>
 __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C, int ld, int N, int groups,
-                                const double* __restrict__ stats, const float* __restrict__ gamma,
+                                const double* __restrict__ stats, int st_ld, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu, int mode, int pix_per_cta,
                                 __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ out32,
                                 const float* __restrict__ ss, int ss_ld, __half* __restrict__ raw_hi,
@@ -106,8 +101,14 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
     const double cnt = (double)HW * cpg;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const int g = c / cpg;
-      const double mean = stats[((long long)n * groups + g) * 2] / cnt;
-      double var = stats[((long long)n * groups + g) * 2 + 1] / cnt - mean * mean;
+      const double* gs = stats + ((size_t)n * st_ld + (size_t)g * cpg) * 2;   // the group's channels are adjacent
+      double s1 = 0, s2 = 0;
+      for (int j = 0; j < cpg; ++j) {
+        s1 += gs[2 * j];
+        s2 += gs[2 * j + 1];
+      }
+      const double mean = s1 / cnt;
+      double var = s2 / cnt - mean * mean;
       var = var < 0 ? 0 : var;
       const float rstd = (float)(1.0 / sqrt(var + (double)eps));
       float a = rstd * gamma[c];
@@ -224,13 +225,15 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
   }
 }
 
-static void gn_apply_launch(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
+static void gn_apply_launch(const View& x, int groups, bool normalise, const float* gamma, const float* beta, float eps,
                             bool silu, int mode, __half* hi, __half* lo, float* out32, cudaStream_t st, const float* ss, int ss_ld,
                             __half* raw_hi = nullptr, __half* raw_lo = nullptr) {
   if (raw_hi) DDNM_CHECK(mode == SPLIT_SAME && raw_lo && !out32, "raw side output only with the plain split");
   DDNM_CHECK(x.C % 8 == 0 && x.C <= MAX_C && x.ld % 4 == 0, "gn_apply: unsupported channel count");
   if (mode == SPLIT_S2D || mode == SPLIT_AVG2) DDNM_CHECK(x.H % 2 == 0 && x.W % 2 == 0, "space-to-depth / avg-pool need even dims");
-  if (ss) DDNM_CHECK(stats != nullptr, "scale-shift needs a normalisation");
+  const double* stats = normalise ? x.st : nullptr;
+  if (normalise) DDNM_CHECK(x.st != nullptr && x.C % groups == 0, "normalisation needs the tensor's per-channel sums (View::st)");
+  if (ss) DDNM_CHECK(normalise, "scale-shift needs a normalisation");
   const int HW = mode == SPLIT_AVG2 ? x.H * x.W / 4 : x.H * x.W;   // pixels the grid iterates over
   const int C8 = x.C / 8;
   const int rows = std::max(1, 256 / C8);
@@ -239,22 +242,22 @@ static void gn_apply_launch(const View& x, int groups, const double* stats, cons
   int ppc = (int)std::max<long long>(rows, cdivll(want, rows) * rows);
   dim3 grid(cdiv(HW, ppc), x.N);
   if (out32)
-    gn_apply_kernel<true><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, gamma, beta, eps, silu, mode,
+    gn_apply_kernel<true><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, x.st_ld, gamma, beta, eps, silu, mode,
                                                  ppc, nullptr, nullptr, out32, ss, ss_ld, nullptr, nullptr);
   else
-    gn_apply_kernel<false><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, gamma, beta, eps, silu, mode,
+    gn_apply_kernel<false><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, x.st_ld, gamma, beta, eps, silu, mode,
                                                   ppc, hi, lo, nullptr, ss, ss_ld, raw_hi, raw_lo);
   CUDA_CHECK(cudaGetLastError());
 }
 
-void gn_apply_split(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
+void gn_apply_split(const View& x, int groups, bool normalise, const float* gamma, const float* beta, float eps,
                     bool silu, int mode, __half* hi, __half* lo, cudaStream_t s, const float* ss, int ss_ld, __half* raw_hi,
                     __half* raw_lo) {
-  gn_apply_launch(x, groups, stats, gamma, beta, eps, silu, mode, hi, lo, nullptr, s, ss, ss_ld, raw_hi, raw_lo);
+  gn_apply_launch(x, groups, normalise, gamma, beta, eps, silu, mode, hi, lo, nullptr, s, ss, ss_ld, raw_hi, raw_lo);
 }
-void gn_apply_f32(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
-                  bool silu, float* out, cudaStream_t s) {
-  gn_apply_launch(x, groups, stats, gamma, beta, eps, silu, SPLIT_SAME, nullptr, nullptr, out, s, nullptr, 0);
+void gn_apply_f32(const View& x, int groups, const float* gamma, const float* beta, float eps, bool silu, float* out,
+                  cudaStream_t s) {
+  gn_apply_launch(x, groups, true, gamma, beta, eps, silu, SPLIT_SAME, nullptr, nullptr, out, s, nullptr, 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -329,7 +332,7 @@ void conv3x3_small_cin(const float* x, int Cin, const float* w, const float* bia
 // ---------------------------------------------------------------------------------------------------------------
 template <int COUT>
 __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ x, int ld, int N, int H, int W, int Cin,
-                                                        int groups, const double* __restrict__ stats,
+                                                        int groups, const double* __restrict__ stats, int st_ld,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, const float* __restrict__ w, const float* __restrict__ bias,
                                                         float* __restrict__ out) {
@@ -367,8 +370,14 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
       const double cnt = (double)HW * cpg;
       for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
         const int g = c / cpg;
-        const double mean = stats[((size_t)n * groups + g) * 2] / cnt;
-        double var = stats[((size_t)n * groups + g) * 2 + 1] / cnt - mean * mean;
+        const double* gs = stats + ((size_t)n * st_ld + (size_t)g * cpg) * 2;
+        double s1 = 0, s2 = 0;
+        for (int j = 0; j < cpg; ++j) {
+          s1 += gs[2 * j];
+          s2 += gs[2 * j + 1];
+        }
+        const double mean = s1 / cnt;
+        double var = s2 / cnt - mean * mean;
         var = var < 0 ? 0 : var;
         const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
         sc[c] = a;
@@ -423,9 +432,10 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
   }
 }
 
-void head_conv_gn_silu(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
-                       const float* w, const float* bias, int Cout, float* out_nchw, cudaStream_t st) {
-  DDNM_CHECK(x.C % 16 == 0 && x.ld % 4 == 0 && x.C % groups == 0, "head convolution: Cin % 16");
+void head_conv_gn_silu(const View& x, int groups, const float* gamma, const float* beta, float eps, const float* w,
+                       const float* bias, int Cout, float* out_nchw, cudaStream_t st) {
+  DDNM_CHECK(x.C % 16 == 0 && x.ld % 4 == 0 && x.C % groups == 0 && x.st != nullptr, "head convolution: Cin % 16, stats slot");
+  const double* stats = x.st;
   const size_t smem = ((size_t)4 * 34 * (x.C + 4) + (size_t)9 * Cout * x.C + 2 * x.C + 4 * 64 * Cout) * sizeof(float);
   DDNM_CHECK(smem <= 227 * 1024, "head convolution tile does not fit shared memory");
   const int total_tiles = cdiv(x.W, 32) * cdiv(x.H, 2) * x.N;
@@ -440,13 +450,13 @@ void head_conv_gn_silu(const View& x, int groups, const double* stats, const flo
       CUDA_CHECK(cudaFuncSetAttribute(head_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set[0] = smem;
     }
-    head_conv_kernel<3><<<grid, 256, smem, st>>>(x.p, x.ld, x.N, x.H, x.W, x.C, groups, stats, gamma, beta, eps, w, bias, out_nchw);
+    head_conv_kernel<3><<<grid, 256, smem, st>>>(x.p, x.ld, x.N, x.H, x.W, x.C, groups, stats, x.st_ld, gamma, beta, eps, w, bias, out_nchw);
   } else if (Cout == 6) {
     if (smem > smem_set[1]) {
       CUDA_CHECK(cudaFuncSetAttribute(head_conv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       smem_set[1] = smem;
     }
-    head_conv_kernel<6><<<grid, 256, smem, st>>>(x.p, x.ld, x.N, x.H, x.W, x.C, groups, stats, gamma, beta, eps, w, bias, out_nchw);
+    head_conv_kernel<6><<<grid, 256, smem, st>>>(x.p, x.ld, x.N, x.H, x.W, x.C, groups, stats, x.st_ld, gamma, beta, eps, w, bias, out_nchw);
   } else {
     throw Error("head convolution supports Cout 3 or 6");
   }

@@ -8,27 +8,27 @@ namespace ddnm {
 
 enum SplitMode : int { SPLIT_SAME = 0, SPLIT_UP2 = 1, SPLIT_S2D = 2, SPLIT_AVG2 = 3 };
 
-// GroupNorm statistics: stats[(n*G + g)*2 + {0,1}] += {sum, sum of squares} (double).  Caller zeroes stats.
-void gn_stats(const View& x, int groups, double* stats, cudaStream_t s);
+// Per-channel GroupNorm sums of x into x.st (see View); only for tensors not produced by the tensor-core kernel.
+void gn_stats(const View& x, cudaStream_t s);
 
-// y = [GN affine](x) -> [SiLU] -> fp16 (hi, lo) planes.  stats == nullptr: no normalisation (raw split).
+// y = [GN affine](x) -> [SiLU] -> fp16 (hi, lo) planes.  normalise == false: raw split; true: uses x.st.
 // mode SPLIT_UP2 writes a nearest-neighbour 2x upsampled plane, SPLIT_S2D writes 4 parity phases
 // (plane index = phase*N + n, phase = (y&1)*2 + (x&1)) for the stride-2 convolution, SPLIT_AVG2 writes the 2x2 average
 // pool of the activated tensor (ResBlock(down=True), unet.py:237-241).  ss != nullptr: use_scale_shift_norm —
 // y = GN(x) * (1 + ss[n*ss_ld + c]) + ss[n*ss_ld + C + c]   (unet.py:250-252).
-void gn_apply_split(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
+void gn_apply_split(const View& x, int groups, bool normalise, const float* gamma, const float* beta, float eps,
                     bool silu, int mode, __half* hi, __half* lo, cudaStream_t s, const float* ss = nullptr, int ss_ld = 0,
                     __half* raw_hi = nullptr, __half* raw_lo = nullptr);  // raw_*: also emit the un-normalised split (SPLIT_SAME)
 // same normalisation, fp32 contiguous NHWC output (feeds the small-Cout output convolution)
-void gn_apply_f32(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
-                  bool silu, float* out, cudaStream_t s);
+void gn_apply_f32(const View& x, int groups, const float* gamma, const float* beta, float eps, bool silu, float* out,
+                  cudaStream_t s);
 
 // 3x3 pad-1 convolution with tiny Cin (the network stem): x NCHW [N,Cin,H,W] fp32, w OIHW, out NHWC view.
 void conv3x3_small_cin(const float* x_nchw, int Cin, const float* w_oihw, const float* bias, const View& out, cudaStream_t s);
 // Network head: GroupNorm affine + SiLU fused into a 3x3 pad-1 convolution with tiny Cout (3 or 6); x NHWC view,
 // stats from gn_stats, out NCHW [N,Cout,H,W].
-void head_conv_gn_silu(const View& x, int groups, const double* stats, const float* gamma, const float* beta, float eps,
-                       const float* w_oihw, const float* bias, int Cout, float* out_nchw, cudaStream_t s);
+void head_conv_gn_silu(const View& x, int groups, const float* gamma, const float* beta, float eps, const float* w_oihw,
+                       const float* bias, int Cout, float* out_nchw, cudaStream_t s);
 
 // out[n][o] = act_out( sum_k act_in(in[n][k]) * W[o][k] + bias[o] );  act: 0 none, 1 swish
 void linear(const float* in, int N, int K, const float* W, const float* bias, int O, float* out, int ldo, int act_in,

@@ -27,7 +27,8 @@ struct TcCfg {
   static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
   static constexpr int B_PLANE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int PART_BYTES = 2 * 4 * BN * 2 * 4;  // [acc stage][epilogue warp][column][sum, sumsq] fp32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + PART_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -47,6 +48,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* part = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));  // GroupNorm partial sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -210,14 +212,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
         uint32_t v[32];
         tmem_ld32(t0 + c0, v);
         tmem_ld_wait();
-        if (valid) {
+        float ov[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = p.alpha * __uint_as_float(v[j + 0]);
-            o.y = p.alpha * __uint_as_float(v[j + 1]);
-            o.z = p.alpha * __uint_as_float(v[j + 2]);
-            o.w = p.alpha * __uint_as_float(v[j + 3]);
+        for (int j = 0; j < 32; j += 4) {
+          float4 o;
+          o.x = p.alpha * __uint_as_float(v[j + 0]);
+          o.y = p.alpha * __uint_as_float(v[j + 1]);
+          o.z = p.alpha * __uint_as_float(v[j + 2]);
+          o.w = p.alpha * __uint_as_float(v[j + 3]);
+          if (valid) {
             if (crow) {
               const float4 c = __ldg(reinterpret_cast<const float4*>(crow + c0 + j));
               o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
@@ -236,6 +239,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
               o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
             }
             *reinterpret_cast<float4*>(orow + c0 + j) = o;
+          } else {
+            o = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          ov[j + 0] = o.x; ov[j + 1] = o.y; ov[j + 2] = o.z; ov[j + 3] = o.w;
+        }
+        if (p.stats) {
+          // GroupNorm statistics of the tile: transpose-reduce the 32 rows x 32 columns this warp holds so that lane L
+          // ends with the column-(c0+L) sum and sum of squares over the warp's 32 pixels (31 shuffles per statistic)
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sq[j] = ov[j] * ov[j];
+#pragma unroll
+          for (int k = 16; k >= 1; k >>= 1) {
+            const bool up = (lane & k) != 0;
+#pragma unroll
+            for (int i = 0; i < k; ++i) {
+              const float keep_s = up ? ov[i + k] : ov[i], send_s = up ? ov[i] : ov[i + k];
+              const float keep_q = up ? sq[i + k] : sq[i], send_q = up ? sq[i] : sq[i + k];
+              ov[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, k);
+              sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, k);
+            }
+          }
+          float* pw = part + (((size_t)acc * 4 + ew) * BN + c0 + lane) * 2;
+          pw[0] = ov[0];
+          pw[1] = sq[0];
+        }
+      }
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps: partial sums of this tile are in smem
+        const int rows_per_img = p.bw * p.bh;
+        for (int col = r; col < BN; col += 128) {
+          const float* pc = part + ((size_t)acc * 4 * BN + col) * 2;
+          if (rows_per_img >= 128) {  // whole tile belongs to image n0
+            const float s = (pc[0] + pc[2 * BN]) + (pc[4 * BN] + pc[6 * BN]);
+            const float q = (pc[1] + pc[2 * BN + 1]) + (pc[4 * BN + 1] + pc[6 * BN + 1]);
+            if (n0 < p.N) {
+              double* d = p.stats + ((size_t)n0 * p.st_ld + n_idx * BN + col) * 2;
+              atomicAdd(d, (double)s);
+              atomicAdd(d + 1, (double)q);
+            }
+          } else {  // 64 or 32 pixels per image: each warp's rows lie in one image
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const int nw = n0 + (w * 32) / rows_per_img;
+              if (nw < p.N) {
+                double* d = p.stats + ((size_t)nw * p.st_ld + n_idx * BN + col) * 2;
+                atomicAdd(d, (double)pc[2 * BN * w]);
+                atomicAdd(d + 1, (double)pc[2 * BN * w + 1]);
+              }
+            }
           }
         }
       }
@@ -346,6 +399,8 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   p.Cout = Cout; p.ldc = out.ld; p.out = out.p;
   DDNM_CHECK(out.C == Cout && out.ld % 4 == 0 && ((uintptr_t)out.p & 15) == 0, "output view misaligned");
   p.chanadd = chanadd; p.ca_ld = ca_ld; p.residual = residual; p.ldr = ldr; p.alpha = alpha; p.res_mode = res_mode;
+  p.stats = out.st; p.st_ld = out.st_ld;
+  if (out.st) DDNM_CHECK(p.bw * p.bh >= 32, "GroupNorm statistics need >= 32 pixels per image");
   if (residual) DDNM_CHECK(ldr % 4 == 0 && ((uintptr_t)residual & 15) == 0, "residual misaligned");
   // UMMA shared-memory descriptor, high word: SBO = 1024 B (8 rows x 128 B) >> 4 at bits [32,46), version = 1 at
   // [46,48), layout SWIZZLE_128B (= 2) at [61,64).  (cute/arch/mma_sm100_desc.hpp SmemDescriptor)

@@ -29,6 +29,8 @@ struct TcParams {
   int ldr;
   int res_mode;                // 0: same pixel; 1: nearest-upsampled source (H/2 x W/2); 2: 2x2 average of a (2H x 2W) source
   float alpha;                 // out = alpha*acc + chanadd + residual
+  double* stats;               // optional GroupNorm sums of the OUTPUT: stats[(image*st_ld + co)*2 + {0,1}] += {sum, sumsq}
+  int st_ld;
   uint32_t desc_hi;            // UMMA smem descriptor high word (SW128 K-major), see tc_gemm.cu
   uint32_t idesc;              // UMMA instruction descriptor
 };

@@ -26,6 +26,7 @@ void UNetOpenAI::emit_resblock(const std::string& p, const View& x, const View& 
   TcWeights w1 = prep_weights(p + ".in_layers.2.weight", Cout, Cin, 9, "", 0);
   View h;
   h.p = hbuf_; h.N = B_; h.H = out.H; h.W = out.W; h.C = Cout; h.ld = Cout;
+  h.st = new_stats(Cout); h.st_ld = Cout;   // conv1's epilogue accumulates the sums out_layers.0 needs
   emit_tc(p + ".conv1", A, TAPS_3X3, nullptr, w1, Cout, h, P(p + ".in_layers.2.bias", Cout), 0, nullptr, 0);
   // out_norm(h) * (1 + scale) + shift -> SiLU -> conv  (:250-253); scale|shift = emb_layers(emb) computed once per forward
   emit_gn_split(p + ".out", h, p + ".out_layers.0", true, SPLIT_SAME, A, ss_all_ + ss_off_.at(p), ss_total_);
@@ -167,7 +168,7 @@ void UNetOpenAI::build_program() {
   std::vector<Layer> mid = {{1, mid_ch, mid_ch}, {4, mid_ch, mid_ch}, {1, mid_ch, mid_ch}};
   plan_layers("middle_block", mid, mid_res);
   for (int i = 0; i < n_out; ++i) plan_layers("output_blocks." + std::to_string(i), outb[i].layers, outb[i].res_in);
-  alloc_common(split_max, hbuf_max, n_gn);
+  alloc_common(split_max, hbuf_max);
   qkv_ = (float*)arena_.alloc(att_qkv * 4);
   attS_ = (float*)arena_.alloc(att_S * 4);
   attO_ = (float*)arena_.alloc(att_O * 4);
@@ -200,9 +201,9 @@ void UNetOpenAI::build_program() {
     const int Bn = B_, mcn = mc, tot = ss_total_;
     add_op("time_embed", "temb", 0, 0, [=](cudaStream_t s) {
       sinusoid(t, Bn, fr, mcn, false, emb, s);               // [cos | sin]
-      linear(emb, Bn, mcn, w0, b0, tdim, t0, tdim, 0, 0, s);
-      linear(t0, Bn, tdim, w1, b1, tdim, t1, tdim, 1, 0, s);  // SiLU between the two Linears
-      linear(t1, Bn, tdim, W, Bv, tot, ss, tot, 1, 0, s);     // emb_layers = SiLU -> Linear, for all blocks at once
+      linear(emb, Bn, mcn, w0, b0, tdim, t0, tdim, 0, 1, s);  // SiLU between the two Linears, applied at the producer
+      linear(t0, Bn, tdim, w1, b1, tdim, t1, tdim, 0, 1, s);  // emb is only consumed through emb_layers' SiLU
+      linear(t1, Bn, tdim, W, Bv, tot, ss, tot, 0, 0, s);     // emb_layers Linear for all blocks at once
     });
   }
 

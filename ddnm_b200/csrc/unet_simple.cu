@@ -20,6 +20,7 @@ void UNetSimple::emit_resblock(const std::string& p, const View& x, const View& 
   TcWeights w1 = prep_weights(p + ".conv1.weight", Cout, Cin, 9, "", 0);
   View h;
   h.p = hbuf_; h.N = B_; h.H = x.H; h.W = x.W; h.C = Cout; h.ld = Cout;
+  h.st = new_stats(Cout); h.st_ld = Cout;   // conv1's epilogue accumulates the sums norm2 needs
   emit_tc(p + ".conv1", A, TAPS_3X3, nullptr, w1, Cout, h, ca_all_ + ca_off_.at(p), ca_total_, nullptr, 0);
   emit_gn_split(p + ".norm2", h, p + ".norm2", true, SPLIT_SAME, A);
   if (Cin != Cout) {
@@ -180,7 +181,7 @@ void UNetSimple::build_program() {
     }
     n_gn += 1;  // norm_out
   }
-  alloc_common(split_max, hbuf_max, n_gn);
+  alloc_common(split_max, hbuf_max);
   qkv_ = (float*)arena_.alloc((size_t)B_ * att_tok * 3 * att_c * 4);
   attS_ = (float*)arena_.alloc((size_t)B_ * att_T * att_T * 4);
   attO_ = (float*)arena_.alloc((size_t)B_ * att_tok * att_c * 4);
@@ -218,9 +219,11 @@ void UNetSimple::build_program() {
     const int Bn = B_, chn = c.ch, cat = ca_total_;
     add_op("temb", "temb", 0, 0, [=](cudaStream_t s) {
       sinusoid(t, Bn, fr, chn, true, emb, s);
-      linear(emb, Bn, chn, w0, b0, tch, t0, tch, 0, 0, s);
-      linear(t0, Bn, tch, w1, b1, tch, t1, tch, 1, 0, s);
-      linear(t1, Bn, tch, W, Bv, cat, ca, cat, 1, 0, s);  // every block applies nonlinearity(temb) first
+      // temb = dense1(swish(dense0(emb))); every block consumes swish(temb) (models.py:121), so the activations are
+      // applied once at the producers' outputs
+      linear(emb, Bn, chn, w0, b0, tch, t0, tch, 0, 1, s);
+      linear(t0, Bn, tch, w1, b1, tch, t1, tch, 0, 1, s);
+      linear(t1, Bn, tch, W, Bv, cat, ca, cat, 0, 0, s);
     });
   }
   // concat buffers for the up path; hs[i] lives in cat[n_up-1-i].slice(Ch, Cs)
