@@ -175,6 +175,57 @@ void UNetEngine::alloc_common(size_t split_elems, size_t hbuf_elems) {
   out_ = (float*)arena_.alloc((size_t)B_ * out_ch_ * R_ * R_ * 4);
 }
 
+void UNetEngine::alloc_attention(size_t qkv_elems, size_t s_elems, size_t o_elems) {
+  qkv_ = (float*)arena_.alloc(qkv_elems * 4);
+  attS_ = (float*)arena_.alloc(s_elems * 4);
+  attO_ = (float*)arena_.alloc(o_elems * 4);
+  qkvh_ = (__half*)arena_.alloc(qkv_elems * 2);
+  qkvl_ = (__half*)arena_.alloc(qkv_elems * 2);
+  ph_ = (__half*)arena_.alloc(s_elems * 2);
+  pl_ = (__half*)arena_.alloc(s_elems * 2);
+  vth_ = (__half*)arena_.alloc(o_elems * 2);
+  vtl_ = (__half*)arena_.alloc(o_elems * 2);
+}
+
+void UNetEngine::emit_attention_core(const std::string& name, int T, int heads, int ch, int qkv_ld, int head_stride, int q_off,
+                                     int k_off, int v_off, float alpha) {
+  float *q = qkv_, *S = attS_, *O = attO_;
+  const int Bn = B_, C = heads * ch;
+  const long long img = (long long)T * qkv_ld;
+  const double fl = 2.0 * Bn * heads * (double)T * T * ch;
+  const double sbytes = (double)Bn * heads * T * T * 4;
+  if (T % 128 == 0 && ch % 64 == 0) {
+    // tensor cores: raw fp16 split of q|k|v, S = alpha Q K^T, softmax -> fp16 P, V^T planes, O = P V
+    __half *qh = qkvh_, *ql = qkvl_, *ph = ph_, *pl = pl_, *vh = vth_, *vl = vtl_;
+    View qv;
+    qv.p = qkv_; qv.N = B_; qv.H = 1; qv.W = T; qv.C = qkv_ld; qv.ld = qkv_ld;
+    add_op(name + ".qkv_split", "gn_split", 0, (double)Bn * T * qkv_ld * 8,
+           [=](cudaStream_t s) { gn_apply_split(qv, 1, false, nullptr, nullptr, 0.f, false, SPLIT_SAME, qh, ql, s); });
+    const long long hs = head_stride ? head_stride : qkv_ld;   // extent-1 dims still need a legal (non-zero) TMA stride
+    GemmOperand A{qh + q_off, ql + q_off, qkv_ld, hs, img};
+    GemmOperand Bk{qh + k_off, ql + k_off, qkv_ld, hs, img};
+    TcLaunch L1 = tc_make_gemm_launch(A, Bk, T, T, ch, heads, Bn, S, (long long)heads * T * T, (long long)T * T, T, alpha, num_sms_);
+    add_op(name + ".qk", "tc", L1.flops, (double)Bn * T * qkv_ld * 4 + sbytes, [L1](cudaStream_t s) { tc_run(L1, s); });
+    add_op(name + ".softmax", "softmax", 0, sbytes * 2, [=](cudaStream_t s) { softmax_split(S, (long long)Bn * heads * T, T, ph, pl, s); });
+    add_op(name + ".v_transpose", "gn_split", 0, (double)Bn * T * C * 8,
+           [=](cudaStream_t s) { transpose_split(q, qkv_ld, head_stride, v_off, Bn, T, heads, ch, vh, vl, s); });
+    GemmOperand P{ph, pl, T, (long long)T * T, (long long)heads * T * T};
+    GemmOperand Vt{vh, vl, T, (long long)ch * T, (long long)heads * ch * T};
+    TcLaunch L2 = tc_make_gemm_launch(P, Vt, T, ch, T, heads, Bn, O, (long long)T * C, ch, C, 1.0f, num_sms_);
+    add_op(name + ".pv", "tc", L2.flops, sbytes + (double)Bn * T * C * 8, [L2](cudaStream_t s) { tc_run(L2, s); });
+  } else {
+    add_op(name + ".qk", "sgemm", fl, (double)Bn * heads * T * (2.0 * ch + T) * 4, [=](cudaStream_t s) {
+      sgemm_batched(true, Bn, heads, T, T, ch, alpha, q + q_off, qkv_ld, img, head_stride, q + k_off, qkv_ld, img, head_stride, S, T,
+                    (long long)heads * T * T, (long long)T * T, s);
+    });
+    add_op(name + ".softmax", "softmax", 0, sbytes * 2, [=](cudaStream_t s) { softmax_rows(S, (long long)Bn * heads * T, T, s); });
+    add_op(name + ".pv", "sgemm", fl, (double)Bn * heads * T * (2.0 * ch + T) * 4, [=](cudaStream_t s) {
+      sgemm_batched(false, Bn, heads, T, ch, T, 1.0f, S, T, (long long)heads * T * T, (long long)T * T, q + v_off, qkv_ld, img, head_stride, O,
+                    C, (long long)T * C, ch, s);
+    });
+  }
+}
+
 // network stem: 3x3 conv on the caller's NCHW tensor -> NHWC view
 void UNetEngine::emit_stem(const std::string& wname, const View& out) {
   const float* xin = x_in_;

@@ -97,6 +97,12 @@ class UNetEngine {
                      const float* ss = nullptr, int ss_ld = 0, SplitView* raw = nullptr);
   void emit_tc(const std::string& name, const SplitView& a, int mode, const SplitView* side, const TcWeights& w, int Cout,
                const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr, int res_mode = 0);
+  // softmax(alpha * Q K^T) V for `heads` heads of width ch over T tokens; q/k/v live in the fp32 qkv_ buffer
+  // ([token][qkv_ld], head h at column h*head_stride + {q_off, k_off, v_off}); result -> attO_ [token][heads*ch].
+  // T % 128 == 0 runs both contractions on the tensor cores, otherwise (8x8 maps) on CUDA cores.
+  void emit_attention_core(const std::string& name, int T, int heads, int ch, int qkv_ld, int head_stride, int q_off, int k_off,
+                           int v_off, float alpha);
+  void alloc_attention(size_t qkv_elems, size_t s_elems, size_t o_elems);
   void emit_stem(const std::string& wname, const View& out);
   void emit_head(const std::string& norm, const std::string& conv, const View& h);
   void alloc_common(size_t split_elems, size_t hbuf_elems);
@@ -119,6 +125,7 @@ class UNetEngine {
   float* hbuf_ = nullptr;      // resblock intermediate
   size_t hbuf_elems_ = 0;
   float *qkv_ = nullptr, *attS_ = nullptr, *attO_ = nullptr;
+  __half *qkvh_ = nullptr, *qkvl_ = nullptr, *ph_ = nullptr, *pl_ = nullptr, *vth_ = nullptr, *vtl_ = nullptr;
   struct StatsChunk { double* p; size_t cap, used; };
   std::vector<StatsChunk> stats_chunks_;
   float *emb_ = nullptr, *temb0_ = nullptr, *temb_ = nullptr, *ca_all_ = nullptr, *freq_ = nullptr;

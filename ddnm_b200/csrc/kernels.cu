@@ -610,6 +610,66 @@ __global__ void softmax_kernel(float* __restrict__ x, long long rows, int cols) 
   const float inv = 1.0f / sum;
   for (int i = lane; i < cols; i += 32) r[i] *= inv;
 }
+// softmax over the last dim with the probabilities emitted as fp16 (hi, lo) planes — the A operand of the P.V GEMM
+__global__ void softmax_split_kernel(const float* __restrict__ x, long long rows, int cols, __half* __restrict__ hi,
+                                     __half* __restrict__ lo) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* r = x + row * cols;
+  float m = -INFINITY;
+  for (int i = lane; i < cols; i += 32) m = fmaxf(m, r[i]);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  float sum = 0.f;
+  for (int i = lane; i < cols; i += 32) sum += expf(r[i] - m);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  const float inv = 1.0f / sum;
+  for (int i = lane * 2; i < cols; i += 64) {
+    __half h0, l0, h1, l1;
+    split_f16(expf(r[i] - m) * inv, h0, l0);
+    split_f16(expf(r[i + 1] - m) * inv, h1, l1);
+    *reinterpret_cast<__half2*>(hi + row * cols + i) = __halves2half2(h0, h1);
+    *reinterpret_cast<__half2*>(lo + row * cols + i) = __halves2half2(l0, l1);
+  }
+}
+void softmax_split(const float* x, long long rows, int cols, __half* hi, __half* lo, cudaStream_t st) {
+  DDNM_CHECK(cols % 2 == 0, "softmax_split: even row length");
+  softmax_split_kernel<<<(int)cdivll(rows * 32, 256), 256, 0, st>>>(x, rows, cols, hi, lo);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// V^T planes for the P.V GEMM: src[(img*T + t)*ld + head*head_stride + off + c] -> dst[((img*heads + head)*ch + c)*T + t]
+__global__ void transpose_split_kernel(const float* __restrict__ src, int ld, int head_stride, int off, int T, int heads, int ch,
+                                       __half* __restrict__ hi, __half* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z / heads, head = blockIdx.z % heads;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int t = t0 + j, c = c0 + tx;
+    tile[j][tx] = (t < T && c < ch) ? src[((size_t)img * T + t) * ld + (size_t)head * head_stride + off + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, t = t0 + tx;
+    if (c < ch && t < T) {
+      __half h, l;
+      split_f16(tile[tx][j], h, l);
+      const size_t o = (((size_t)img * heads + head) * ch + c) * T + t;
+      hi[o] = h;
+      lo[o] = l;
+    }
+  }
+}
+void transpose_split(const float* src, int ld, int head_stride, int off, int images, int T, int heads, int ch, __half* hi,
+                     __half* lo, cudaStream_t st) {
+  dim3 grid(cdiv(T, 32), cdiv(ch, 32), images * heads);
+  transpose_split_kernel<<<grid, 256, 0, st>>>(src, ld, head_stride, off, T, heads, ch, hi, lo);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 void softmax_rows(float* x, long long rows, int cols, cudaStream_t st) {
   softmax_kernel<<<(int)cdivll(rows * 32, 256), 256, 0, st>>>(x, rows, cols);
   CUDA_CHECK(cudaGetLastError());

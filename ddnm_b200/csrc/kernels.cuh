@@ -43,6 +43,11 @@ void sgemm_batched(bool b_transposed, int outer_n, int inner_n, int M, int N, in
                    long long sa, long long sa2, const float* B, int ldb, long long sb, long long sb2, float* C, int ldc,
                    long long sc, long long sc2, cudaStream_t s);
 void softmax_rows(float* x, long long rows, int cols, cudaStream_t s);
+// softmax whose result is written as fp16 (hi, lo) planes (A operand of the tensor-core P.V GEMM)
+void softmax_split(const float* x, long long rows, int cols, __half* hi, __half* lo, cudaStream_t s);
+// per-head transposed fp16 split: dst[((img*heads + head)*ch + c)*T + t] = src[(img*T + t)*ld + head*head_stride + off + c]
+void transpose_split(const float* src, int ld, int head_stride, int off, int images, int T, int heads, int ch, __half* hi,
+                     __half* lo, cudaStream_t s);
 
 // OIHW fp32 conv weight -> K-major fp16 (hi, lo) rows: dst[co*ktot + koff + tap*Cin + ci]
 void split_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, __half* hi, __half* lo, int ktot, int koff,

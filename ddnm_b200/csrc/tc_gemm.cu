@@ -100,7 +100,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int n_idx, x0, y0, n0;
         decode(tile, n_idx, x0, y0, n0);
-        const int bz = p.b_batched ? n0 : 0;
+        const int bz = p.b_batched == 1 ? n0 : 0;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -126,8 +126,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
             tma_load_4d(sa, &tm_a1h, fb, c, x0, y0, n0);
             tma_load_4d(sa + A_PLANE_BYTES, &tm_a1l, fb, c, x0, y0, n0);
           }
-          tma_load_3d(sa + 2 * A_PLANE_BYTES, &tm_bh, fb, kb * BK, n_idx * BN, bz);
-          tma_load_3d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tm_bl, fb, kb * BK, n_idx * BN, bz);
+          if (p.b_batched == 2) {
+            tma_load_4d(sa + 2 * A_PLANE_BYTES, &tm_bh, fb, kb * BK, n_idx * BN, y0, n0);
+            tma_load_4d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tm_bl, fb, kb * BK, n_idx * BN, y0, n0);
+          } else {
+            tma_load_3d(sa + 2 * A_PLANE_BYTES, &tm_bh, fb, kb * BK, n_idx * BN, bz);
+            tma_load_3d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tm_bl, fb, kb * BK, n_idx * BN, bz);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -185,7 +190,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
       const int n = n0 + ni;
       const bool valid = n < p.N;
       const long long pix = ((long long)n * p.H + (y0 + yi)) * p.W + (x0 + xi);
-      float* orow = p.out + pix * p.ldc + n_idx * BN;
+      float* orow = p.out + (long long)n * p.out_sn + (long long)(y0 + yi) * p.out_sy + (long long)(x0 + xi) * p.out_sx + n_idx * BN;
       // residual source row(s): same pixel, nearest-upsampled (x_upd of ResBlock(up=True), unet.py:240) or the 2x2
       // average of a twice-as-large map (ResBlock(down=True))
       const float* rrow = nullptr;
@@ -326,7 +331,9 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static CUtensorMap make_map_f16(const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+// strides_elems: element strides of dims 1..rank-1 (nullptr = densely packed)
+static CUtensorMap make_map_f16(const void* base, int rank, const uint64_t* dims, const uint32_t* box,
+                                const uint64_t* strides_elems = nullptr) {
   CUtensorMap m;
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t b[5], es[5];
@@ -336,7 +343,7 @@ static CUtensorMap make_map_f16(const void* base, int rank, const uint64_t* dims
     b[i] = box[i];
     es[i] = 1;
     stride *= dims[i];
-    if (i < rank - 1) gstr[i] = stride;
+    if (i < rank - 1) gstr[i] = strides_elems ? strides_elems[i] * 2 : stride;
   }
   CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, b, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -397,6 +404,7 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
     DDNM_CHECK(src0.H == out.H && src0.W == out.W && src0.N == out.N, "source/output shape mismatch");
   }
   p.Cout = Cout; p.ldc = out.ld; p.out = out.p;
+  p.out_sx = out.ld; p.out_sy = (long long)out.W * out.ld; p.out_sn = (long long)out.H * out.W * out.ld;
   DDNM_CHECK(out.C == Cout && out.ld % 4 == 0 && ((uintptr_t)out.p & 15) == 0, "output view misaligned");
   p.chanadd = chanadd; p.ca_ld = ca_ld; p.residual = residual; p.ldr = ldr; p.alpha = alpha; p.res_mode = res_mode;
   p.stats = out.st; p.st_ld = out.st_ld;
@@ -428,6 +436,51 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   const int total = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
   L.grid = std::min(total, num_sms);
   L.flops = 2.0 * (double)out.pixels() * Cout * Ktot;
+  return L;
+}
+
+TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int heads, int images, float* out,
+                             long long out_sn, long long out_sy, long long out_sx, float alpha, int num_sms) {
+  TcLaunch L;
+  TcParams& p = L.p;
+  DDNM_CHECK(M % 128 == 0 && N % 64 == 0 && K % BK == 0, "attention GEMM: M % 128, N % 64, K % 64");
+  p.H = heads; p.W = M; p.N = images;
+  p.bw = 128; p.bh = 1; p.bn = 1;
+  p.tiles_x = M / 128; p.tiles_y = heads; p.tiles_n = images;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  L.BN = 64;
+  for (int bn : {256, 128}) {
+    if (N % bn == 0 && (long long)m_tiles * (N / bn) >= num_sms) {
+      L.BN = bn;
+      break;
+    }
+  }
+  p.n_tiles = N / L.BN;
+  p.mode0 = TAPS_1X1;
+  p.cb0 = K / BK; p.kb0 = K / BK; p.kb1 = 0;
+  p.phase_stride = 0;
+  p.b_batched = 2;
+  p.Cout = N; p.ldc = (int)out_sx; p.out = out;
+  p.out_sn = out_sn; p.out_sy = out_sy; p.out_sx = out_sx;
+  DDNM_CHECK(out_sx % 4 == 0 && out_sy % 4 == 0 && out_sn % 4 == 0 && ((uintptr_t)out & 15) == 0, "attention GEMM output misaligned");
+  p.chanadd = nullptr; p.ca_ld = 0; p.residual = nullptr; p.ldr = 0; p.res_mode = 0; p.alpha = alpha;
+  p.stats = nullptr; p.st_ld = 0;
+  p.desc_hi = g_desc_hi_override ? g_desc_hi_override : (64u | (1u << 14) | (2u << 29));
+  p.idesc = ((1u << 4) | ((uint32_t)(L.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24)) ^ g_idesc_xor;
+  const uint64_t ad[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)heads, (uint64_t)images};
+  const uint64_t as[3] = {(uint64_t)A.s_row, (uint64_t)A.s_head, (uint64_t)A.s_img};
+  const uint32_t abox[4] = {(uint32_t)BK, 128u, 1u, 1u};
+  L.a0h = make_map_f16(A.hi, 4, ad, abox, as);
+  L.a0l = make_map_f16(A.lo, 4, ad, abox, as);
+  L.a1h = L.a0h;
+  L.a1l = L.a0l;
+  const uint64_t bd[4] = {(uint64_t)K, (uint64_t)N, (uint64_t)heads, (uint64_t)images};
+  const uint64_t bs[3] = {(uint64_t)B.s_row, (uint64_t)B.s_head, (uint64_t)B.s_img};
+  const uint32_t bbox[4] = {(uint32_t)BK, (uint32_t)L.BN, 1u, 1u};
+  L.bh = make_map_f16(B.hi, 4, bd, bbox, bs);
+  L.bl = make_map_f16(B.lo, 4, bd, bbox, bs);
+  L.grid = std::min(m_tiles * p.n_tiles, num_sms);
+  L.flops = 2.0 * (double)images * heads * M * (double)N * K;
   return L;
 }
 

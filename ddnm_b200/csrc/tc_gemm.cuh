@@ -20,7 +20,9 @@ struct TcParams {
   int cb0, kb0;                // source 0: 64-channel blocks per tap, total k-blocks (= taps * cb0)
   int kb1;                     // source 1 (always 1x1, e.g. the nin_shortcut input): k-blocks, 0 = absent
   int phase_stride;            // TAPS_3X3_S2: images per parity phase in the source's outer dim
-  int b_batched;               // 1: B operand has one matrix per image (attention), z coordinate = image
+  int b_batched;               // 1: B has one matrix per image (3D map, z = image); 2: B is a 4D map sharing the A tile's
+                               //    two outer coordinates (attention: y = head, n = image)
+  long long out_sn, out_sy, out_sx;  // output element strides per image / row / column of the M tile's pixel grid
   int Cout, ldc;
   float* out;                  // out[pixel*ldc + co]
   const float* chanadd;        // chanadd[image*ca_ld + co] added per (image, channel): bias (+ timestep projection); may be null
@@ -49,6 +51,18 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
                         int w_batches, int Cout, const View& out, const float* chanadd, int ca_ld, const float* residual,
                         int ldr, float alpha, int num_sms, int res_mode = 0);
 void tc_run(const TcLaunch& L, cudaStream_t stream);
+
+// Strided fp16 (hi, lo) operand for the batched-GEMM builder: element (k, row, head, image) at
+// base[k + row*s_row + head*s_head + image*s_img]; k extent = K (multiple of 64).
+struct GemmOperand {
+  const __half* hi;
+  const __half* lo;
+  long long s_row, s_head, s_img;
+};
+// out[img*out_sn + head*out_sy + m*out_sx + n] = alpha * sum_k A[k, m, head, img] * B[k, n, head, img]
+// (multi-head attention: QK^T and PV).  M % 128 == 0, N % 64 == 0, K % 64 == 0.
+TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int heads, int images, float* out,
+                             long long out_sn, long long out_sy, long long out_sx, float alpha, int num_sms);
 
 // debug knobs (tests only): override descriptor words for the NEXT launches built
 void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor);

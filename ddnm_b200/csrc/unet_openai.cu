@@ -54,19 +54,7 @@ void UNetOpenAI::emit_attn(const std::string& p, const View& x, const View& out)
   View qkv;
   qkv.p = qkv_; qkv.N = B_; qkv.H = x.H; qkv.W = x.W; qkv.C = 3 * C; qkv.ld = 3 * C;
   emit_tc(p + ".qkv", A, TAPS_1X1, nullptr, wqkv, 3 * C, qkv, P(p + ".qkv.bias", 3 * C), 0, nullptr, 0);
-  float *q = qkv_, *S = attS_, *O = attO_;
-  const int Bn = B_;
-  const float s2 = 1.0f / std::sqrt((float)ch);  // (ch^-1/4)^2
-  const long long img = (long long)T * 3 * C;
-  add_op(p + ".qk", "sgemm", 2.0 * Bn * heads * (double)T * T * ch, (double)Bn * heads * T * (2.0 * ch + T) * 4, [=](cudaStream_t s) {
-    sgemm_batched(true, Bn, heads, T, T, ch, s2, q, 3 * C, img, 3 * ch, q + ch, 3 * C, img, 3 * ch, S, T, (long long)heads * T * T,
-                  (long long)T * T, s);
-  });
-  add_op(p + ".softmax", "softmax", 0, (double)Bn * heads * T * T * 8, [=](cudaStream_t s) { softmax_rows(S, (long long)Bn * heads * T, T, s); });
-  add_op(p + ".pv", "sgemm", 2.0 * Bn * heads * (double)T * T * ch, (double)Bn * heads * T * (2.0 * ch + T) * 4, [=](cudaStream_t s) {
-    sgemm_batched(false, Bn, heads, T, ch, T, 1.0f, S, T, (long long)heads * T * T, (long long)T * T, q + 2 * ch, 3 * C, img, 3 * ch, O, C,
-                  (long long)T * C, ch, s);
-  });
+  emit_attention_core(p, T, heads, ch, 3 * C, 3 * ch, 0, ch, 2 * ch, 1.0f / std::sqrt((float)ch));  // (ch^-1/4)^2
   View ov;
   ov.p = attO_; ov.N = B_; ov.H = x.H; ov.W = x.W; ov.C = C; ov.ld = C;
   emit_gn_split(p + ".proj_in", ov, "", false, SPLIT_SAME, A);
@@ -169,9 +157,7 @@ void UNetOpenAI::build_program() {
   plan_layers("middle_block", mid, mid_res);
   for (int i = 0; i < n_out; ++i) plan_layers("output_blocks." + std::to_string(i), outb[i].layers, outb[i].res_in);
   alloc_common(split_max, hbuf_max);
-  qkv_ = (float*)arena_.alloc(att_qkv * 4);
-  attS_ = (float*)arena_.alloc(att_S * 4);
-  attO_ = (float*)arena_.alloc(att_O * 4);
+  alloc_attention(att_qkv, att_S, att_O);
 
   // ---- timestep embedding (nn.py:103-121, unet.py:472-476,649) and every emb_layers Linear as one matrix (unet.py:188-194) ----
   const int tdim = mc * 4;

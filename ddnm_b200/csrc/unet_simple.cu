@@ -54,16 +54,8 @@ void UNetSimple::emit_attn(const std::string& p, const View& x, const View& out)
   View qkv;
   qkv.p = qkv_; qkv.N = B_; qkv.H = x.H; qkv.W = x.W; qkv.C = 3 * C; qkv.ld = 3 * C;
   emit_tc(p + ".qkv", A, TAPS_1X1, nullptr, wqkv, 3 * C, qkv, bqkv, 0, nullptr, 0);
-  float *q = qkv_, *S = attS_, *O = attO_;
-  const int Bn = B_;
-  const float scale = 1.0f / sqrtf((float)C);  // int(c) ** (-0.5)
-  add_op(p + ".qk", "sgemm", 2.0 * Bn * T * (double)T * C, (double)Bn * T * (2.0 * C + T) * 4, [=](cudaStream_t s) {
-    sgemm_batched(true, Bn, 1, T, T, C, scale, q, 3 * C, (long long)T * 3 * C, 0, q + C, 3 * C, (long long)T * 3 * C, 0, S, T, (long long)T * T, 0, s);
-  });
-  add_op(p + ".softmax", "softmax", 0, (double)Bn * T * T * 8, [=](cudaStream_t s) { softmax_rows(S, (long long)Bn * T, T, s); });
-  add_op(p + ".pv", "sgemm", 2.0 * Bn * T * (double)T * C, (double)Bn * T * (2.0 * C + T) * 4, [=](cudaStream_t s) {
-    sgemm_batched(false, Bn, 1, T, C, T, 1.0f, S, T, (long long)T * T, 0, q + 2 * C, 3 * C, (long long)T * 3 * C, 0, O, C, (long long)T * C, 0, s);
-  });
+  // one head of width C; w_ = bmm(q, k) * int(c) ** (-0.5)
+  emit_attention_core(p, T, 1, C, 3 * C, 0, 0, C, 2 * C, 1.0f / sqrtf((float)C));
   View ov;
   ov.p = attO_; ov.N = B_; ov.H = x.H; ov.W = x.W; ov.C = C; ov.ld = C;
   emit_gn_split(p + ".proj_in", ov, "", false, SPLIT_SAME, A);
@@ -182,9 +174,7 @@ void UNetSimple::build_program() {
     n_gn += 1;  // norm_out
   }
   alloc_common(split_max, hbuf_max);
-  qkv_ = (float*)arena_.alloc((size_t)B_ * att_tok * 3 * att_c * 4);
-  attS_ = (float*)arena_.alloc((size_t)B_ * att_T * att_T * 4);
-  attO_ = (float*)arena_.alloc((size_t)B_ * att_tok * att_c * 4);
+  alloc_attention((size_t)B_ * att_tok * 3 * att_c, (size_t)B_ * att_T * att_T, (size_t)B_ * att_tok * att_c);
 
   // ---- timestep embedding MLP + all per-block projections as one matrix (models.py:305-308, :121) ----
   const int tch = c.ch * 4;
