@@ -30,6 +30,11 @@ class OperatorDesc(C.Structure):
                 ("singulars_orig", C.c_void_p), ("perm", C.c_void_p), ("mask", C.c_void_p)]
 
 
+class SimpleDeg(C.Structure):
+    _fields_ = [("use_mask", C.c_int), ("use_gray", C.c_int), ("scale", C.c_int), ("img_dim", C.c_int), ("channels", C.c_int),
+                ("mask", C.c_void_p)]
+
+
 class Schedule(C.Structure):
     _fields_ = [("n_pairs", C.c_int), ("t_i", C.c_void_p), ("t_j", C.c_void_p), ("abar", C.c_void_p),
                 ("num_timesteps", C.c_int), ("eta", C.c_float), ("sigma_y", C.c_float), ("plus", C.c_int)]
@@ -59,6 +64,9 @@ _SIGS = {
     "ddnm_operator_lambda_noise": (C.c_int, [_P, _P, _P, _I, _F, _F, _F, _F, _P, _P]),
     "ddnm_operator_destroy": (C.c_int, [_P]),
     "ddnm_sample": (C.c_int, [_P, _P, C.POINTER(Schedule), _P, _P, _P, _I, _P, _P, _P]),
+    "ddnm_simplified_A": (C.c_int, [C.POINTER(SimpleDeg), _P, _I, _P, _P]),
+    "ddnm_simplified_Ap": (C.c_int, [C.POINTER(SimpleDeg), _P, _I, _P, _P]),
+    "ddnm_sample_simplified": (C.c_int, [_P, C.POINTER(SimpleDeg), C.POINTER(Schedule), _P, _P, _P, _I, _P, _P, _P]),
     "ddnm_conv_tc": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P]),
     "ddnm_conv_direct": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
     "ddnm_conv_tc_bench": (C.c_int, [_I, _I, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_D)]),

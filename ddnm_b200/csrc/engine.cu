@@ -197,8 +197,10 @@ void UNetEngine::emit_attention_core(const std::string& name, int T, int heads, 
   if (T % 128 == 0 && ch % 64 == 0) {
     // tensor cores: raw fp16 split of q|k|v, S = alpha Q K^T, softmax -> fp16 P, V^T planes, O = P V
     __half *qh = qkvh_, *ql = qkvl_, *ph = ph_, *pl = pl_, *vh = vth_, *vl = vtl_;
+    // the raw split is elementwise, so the [token][qkv_ld] buffer is viewed as rows of C = heads*ch channels (<= MAX_C)
+    DDNM_CHECK(qkv_ld % C == 0, "qkv row is not a multiple of the attention width");
     View qv;
-    qv.p = qkv_; qv.N = B_; qv.H = 1; qv.W = T; qv.C = qkv_ld; qv.ld = qkv_ld;
+    qv.p = qkv_; qv.N = B_; qv.H = 1; qv.W = T * (qkv_ld / C); qv.C = C; qv.ld = C;
     add_op(name + ".qkv_split", "gn_split", 0, (double)Bn * T * qkv_ld * 8,
            [=](cudaStream_t s) { gn_apply_split(qv, 1, false, nullptr, nullptr, 0.f, false, SPLIT_SAME, qh, ql, s); });
     const long long hs = head_stride ? head_stride : qkv_ld;   // extent-1 dims still need a legal (non-zero) TMA stride

@@ -68,3 +68,75 @@ def ddnm_diffusion(x, model, b, eta, A_funcs, y, cls_fn=None, classes=None, conf
 
 def ddnm_plus_diffusion(x, model, b, eta, A_funcs, y, sigma_y, cls_fn=None, classes=None, config=None, noise=None):
     return _run(x, model, b, eta, A_funcs, y, sigma_y, True, cls_fn, classes, config, noise)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The runner's "simplified" DDNM+ (guided_diffusion/diffusion.py:211-415): the reference inlines this loop in
+# Diffusion.simplified_ddnm_plus; here it is a function with the same ingredients.
+# ------------------------------------------------------------------------------------------------------------------
+class SimplifiedDegradation:
+    """A / Ap of diffusion.py:244-290 for ``args.deg`` in {colorization, denoising, sr_averagepooling, inpainting,
+    mask_color_sr, diy}; ``mask`` is the (H, W) 0/1 array of exp/inp_masks/mask.npy."""
+
+    def __init__(self, deg, deg_scale=1, mask=None, image_size=256, device="cuda"):
+        table = {"colorization": (0, 1, 1), "denoising": (0, 0, 1), "sr_averagepooling": (0, 0, None), "inpainting": (1, 0, 1),
+                 "mask_color_sr": (1, 1, None), "diy": (1, 1, None)}
+        if deg not in table:
+            raise NotImplementedError("degradation type not supported")
+        use_mask, use_gray, sc = table[deg]
+        self.scale = int(round(deg_scale)) if sc is None else sc
+        self.image_size = image_size
+        self._mask = None
+        if use_mask:
+            assert mask is not None, "this degradation needs the inpainting mask"
+            self._mask = torch.as_tensor(mask).to(device=device, dtype=torch.float32).reshape(image_size, image_size).contiguous()
+        d = _lib.SimpleDeg()
+        d.use_mask, d.use_gray, d.scale, d.img_dim, d.channels = use_mask, use_gray, self.scale, image_size, 3
+        d.mask = None if self._mask is None else self._mask.data_ptr()
+        self._d = d
+
+    def A(self, z):
+        z = z.float().contiguous()
+        s = self.image_size // self.scale
+        y = torch.empty(z.shape[0], 3, s, s, device=z.device, dtype=torch.float32)
+        _lib.check(_lib.lib().ddnm_simplified_A(C.byref(self._d), _lib.ptr(z), z.shape[0], _lib.ptr(y), _lib.cur_stream()))
+        return y
+
+    def Ap(self, y):
+        y = y.float().contiguous()
+        x = torch.empty(y.shape[0], 3, self.image_size, self.image_size, device=y.device, dtype=torch.float32)
+        _lib.check(_lib.lib().ddnm_simplified_Ap(C.byref(self._d), _lib.ptr(y), y.shape[0], _lib.ptr(x), _lib.cur_stream()))
+        return x
+
+
+def simplified_ddnm_plus(x, model, b, eta, degradation, y, sigma_y, config=None, noise=None):
+    """x: x_T (B,3,H,W); y = degradation.A(x_orig); sigma_y already doubled (diffusion.py:292).  Returns
+    ``([x_0.cpu()], [x0_pred.cpu()])`` like the SVD samplers."""
+    if not isinstance(model, _EngineModel):
+        model = getattr(model, "module", model)
+    if not isinstance(model, _EngineModel) or not isinstance(degradation, SimplifiedDegradation):
+        raise TypeError("simplified_ddnm_plus needs a ddnm_b200.model denoiser and a SimplifiedDegradation")
+    with torch.no_grad():
+        if not x.is_cuda:
+            x = x.to("cuda", non_blocking=True)
+        n = x.size(0)
+        pairs = time_pairs(config.diffusion.num_diffusion_timesteps, config.time_travel.T_sampling,
+                           config.time_travel.travel_length, config.time_travel.travel_repeat)
+        abar = np.ascontiguousarray(alpha_bar_table(b).numpy())
+        ti = np.ascontiguousarray(np.array([p[0] for p in pairs], dtype=np.int32))
+        tj = np.ascontiguousarray(np.array([p[1] for p in pairs], dtype=np.int32))
+        x = x.float().contiguous()
+        if noise is None:
+            noise = torch.empty((len(pairs),) + tuple(x.shape), device=x.device, dtype=torch.float32)
+            for k in range(len(pairs)):
+                noise[k] = torch.randn_like(x)
+        else:
+            noise = noise.to(x.device).float().contiguous()
+        yv = y.to(x.device, non_blocking=True).float().contiguous()
+        s = _lib.Schedule()
+        s.n_pairs, s.t_i, s.t_j, s.abar = len(pairs), ti.ctypes.data, tj.ctypes.data, abar.ctypes.data
+        s.num_timesteps, s.eta, s.sigma_y, s.plus = int(config.diffusion.num_diffusion_timesteps), float(eta), float(sigma_y), 1
+        out, x0p = torch.empty_like(x), torch.empty_like(x)
+        _lib.check(_lib.lib().ddnm_sample_simplified(model.engine(n), C.byref(degradation._d), C.byref(s), _lib.ptr(x), _lib.ptr(yv),
+                                                    _lib.ptr(noise), n, _lib.ptr(out), _lib.ptr(x0p), _lib.cur_stream()))
+        return [out.to("cpu")], [x0p.to("cpu")]

@@ -116,6 +116,23 @@ int ddnm_sample(void* unet, void* op, const ddnm_schedule* sched, const float* x
                 float* out_x0, float* out_x0_pred, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * "Simplified" DDNM+ (guided_diffusion/diffusion.py:211-415, the README quick-start path): image-space operators composed
+ * of mask (A1 = z*mask, :256), colour->gray (color2gray/gray2color, :33-42) and average pooling (AdaptiveAvgPool2d /
+ * MeanUpsample, :27-31,:252-253), with the scalar lambda_t / gamma_t update of :355-381.  deg table (:244-290):
+ *   colorization = gray; denoising = none; sr_averagepooling = scale; inpainting = mask; mask_color_sr / diy = all three.
+ * y and A's output are (B, 3, D/scale, D/scale) fp32 (gray replicates its value over the 3 channels, as the reference).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int use_mask, use_gray, scale, img_dim, channels;
+  const float* mask;          /* DEVICE [img_dim*img_dim] 0/1 (exp/inp_masks/mask.npy), NULL when use_mask == 0 */
+} ddnm_simple_deg;
+int ddnm_simplified_A(const ddnm_simple_deg* deg, const float* x, int B, float* y, void* stream);
+int ddnm_simplified_Ap(const ddnm_simple_deg* deg, const float* y, int B, float* x, void* stream);
+/* schedule->sigma_y is the doubled level (diffusion.py:292); schedule->plus is ignored */
+int ddnm_sample_simplified(void* unet, const ddnm_simple_deg* deg, const ddnm_schedule* sched, const float* x_T, const float* y,
+                           const float* noise, int B, float* out_x0, float* out_x0_pred, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Op-level entry points (unit tests, micro-benchmarks).  NHWC fp32 tensors, OIHW weights.
  * mode: 0 = 3x3 pad 1, 1 = 1x1, 2 = 3x3 stride 2 pad (0,1,0,1); up2: nearest x2 before the conv.
  * ---------------------------------------------------------------------------------------------- */

@@ -296,9 +296,73 @@ def sampler_fixtures():
     np.savez_compressed(os.path.join(GOLD, "sampler_tiny.npz"), **out)
 
 
+# --------------------------------------------------------------------------------------------------
+SIMPLIFIED_CASES = [("sr_averagepooling", 4, 0.1, 3, 1, 1), ("colorization", 1, 0.0, 3, 1, 1), ("inpainting", 1, 0.05, 3, 1, 1),
+                    ("denoising", 1, 0.2, 3, 1, 1), ("mask_color_sr", 2, 0.05, 4, 2, 2)]   # deg, scale, sigma_y(arg), T, l, r
+
+
+def simplified_fixtures():
+    """Run the reference runner's own Diffusion.simplified_ddnm_plus (diffusion.py:211-415) on one synthetic image with the
+    dataset / PNG writer stubbed out, capture the image it would save, and pin oracle.simplified to it."""
+    import guided_diffusion.diffusion as D
+    from oracle import simplified as SP
+    cfg = U.SimpleUNetConfig.celeba_hq()
+    m = ref_model(cfg, 1234)
+    sd = U.init_state_dict(cfg, 1234)
+    betas = SCH.linear_betas()
+    g = torch.Generator().manual_seed(2024)
+    x01 = torch.rand(1, 3, 256, 256, generator=g)                      # the "dataset image" in [0, 1]
+    mask = torch.from_numpy(np.load(os.path.join(REF, "exp/inp_masks/mask.npy")))
+    out = {"x01": x01.numpy(), "mask_bits": np.packbits(mask.numpy().astype(np.uint8).reshape(-1))}
+    cwd = os.getcwd()
+    os.chdir(REF)                                                        # the runner loads exp/inp_masks/mask.npy relatively
+    try:
+        for deg, scale, sy, T, tl, tr in SIMPLIFIED_CASES:
+            npairs = len(SCH.time_pairs(1000, T, tl, tr))
+            nrng = torch.Generator().manual_seed(556)
+            tape = [torch.randn(1, 3, 256, 256, generator=nrng) for _ in range(npairs)]
+            saved = {}
+            fake = ns(args=ns(deg=deg, deg_scale=float(scale), sigma_y=sy, eta=0.85, subset_start=-1, subset_end=-1, seed=1234,
+                              image_folder="/tmp/ddnm_golden_unused"),
+                      config=ns(data=ns(num_workers=0, channels=3, image_size=256, uniform_dequantization=False,
+                                        gaussian_dequantization=False, rescaled=True, logit_transform=False),
+                                sampling=ns(batch_size=1), diffusion=ns(num_diffusion_timesteps=1000),
+                                time_travel=ns(T_sampling=T, travel_length=tl, travel_repeat=tr)),
+                      betas=betas, device=torch.device("cpu"))
+            ds = torch.utils.data.TensorDataset(x01, torch.zeros(1, dtype=torch.long))
+            orig = (D.get_dataset, D.tvu.save_image, D.os.makedirs)
+            D.get_dataset = lambda a, c: (ds, ds)
+            D.tvu.save_image = lambda t, path, **k: saved.__setitem__(os.path.basename(path), t.detach().clone())
+            D.os.makedirs = lambda *a, **k: None
+            try:
+                torch.manual_seed(4242)                                  # x_T = first torch.randn after this seed (:310-316)
+                with torch.no_grad(), cpu_shim(tape):
+                    D.Diffusion.simplified_ddnm_plus(fake, m, None)
+            finally:
+                D.get_dataset, D.tvu.save_image, D.os.makedirs = orig
+            ref_img = [v for k, v in saved.items() if k.endswith("_0.png")][-1].reshape(1, 3, 256, 256)
+            # oracle
+            torch.manual_seed(4242)
+            x_T = torch.randn(1, 3, 256, 256)
+            A, Ap = SP.degradation(deg, scale, mask.float(), 256)
+            x_orig = 2 * x01 - 1.0
+            y = A(x_orig)
+            with torch.no_grad():
+                ox, _ = SP.simplified_sample(x_T, lambda a, b: U.forward(sd, a, b, cfg), betas, 0.85, A, Ap, y, 2 * sy, tape,
+                                             t_sampling=T, travel_length=tl, travel_repeat=tr)
+            oimg = torch.clamp((ox + 1.0) / 2.0, 0.0, 1.0)
+            d = close(oimg, ref_img, 2e-4, f"simplified {deg}")
+            key = f"{deg}_s{scale}_sy{sy}_T{T}_l{tl}_r{tr}"
+            out[key + "_img_s4"] = ref_img[:, :, ::4, ::4].contiguous().numpy()
+            print(f"simplified {key}: ok (oracle-ref {d:.2e})")
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(GOLD, "simplified.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["unet", "openai", "ops", "sampler"]
+    which = sys.argv[1:] or ["unet", "openai", "ops", "sampler", "simplified"]
     if "unet" in which:
         unet_fixtures()
     if "openai" in which:
@@ -307,4 +371,6 @@ if __name__ == "__main__":
         operator_fixtures()
     if "sampler" in which:
         sampler_fixtures()
+    if "simplified" in which:
+        simplified_fixtures()
     print("golden fixtures written to", GOLD)

@@ -17,4 +17,4 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def gold():
     import numpy as np
-    return {name: np.load(os.path.join(GOLD, name + ".npz")) for name in ("unet_simple", "unet_openai", "operators", "sampler_tiny")}
+    return {name: np.load(os.path.join(GOLD, name + ".npz")) for name in ("unet_simple", "unet_openai", "operators", "sampler_tiny", "simplified")}

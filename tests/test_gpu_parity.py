@@ -14,7 +14,7 @@ from oracle import unet_openai as UO
 from oracle import unet_simple as U
 
 from helpers import LAMBDA_CASES, assert_close, engine_op, model_config, openai_model_kwargs, oracle_ops, sampler_config
-from test_oracle_golden import SAMPLER_CASES, sampler_inputs
+from test_oracle_golden import SAMPLER_CASES, SIMPLIFIED_CASES, sampler_inputs, simplified_inputs
 
 pytestmark = pytest.mark.gpu
 dev = "cuda"
@@ -360,3 +360,25 @@ def test_product_path_has_no_cpu_fallback():
     m.load_state_dict(U.init_state_dict(cfg, 1234))
     with pytest.raises(AssertionError):
         m(torch.zeros(1, 3, 32, 32), torch.zeros(1))     # CPU tensors are rejected, never silently computed on the host
+
+
+# ------------------------------------------------------------------------------------------------ simplified DDNM+
+@pytest.mark.parametrize("case", SIMPLIFIED_CASES, ids=lambda c: c[0])
+def test_simplified_ddnm_plus_vs_reference_runner(gold, case):
+    """README quick-start path (diffusion.py:211-415): engine vs the image the reference runner saved, and vs the oracle."""
+    from ddnm_b200.sampler import SimplifiedDegradation, simplified_ddnm_plus
+    from oracle import simplified as SP
+    deg, scale, sy, T, tl, tr = case
+    g = gold["simplified"]
+    cfg = U.SimpleUNetConfig.celeba_hq()
+    m = _engine_model(cfg)
+    x_T, x_orig, mask, tape = simplified_inputs(g, T, tl, tr)
+    D = SimplifiedDegradation(deg, scale, mask, 256)
+    A, Ap = SP.degradation(deg, scale, mask, 256)
+    y = D.A(x_orig.to(dev))
+    assert_close(y, A(x_orig), 1e-4, 1e-5, f"simplified {deg}: A")
+    assert_close(D.Ap(y), Ap(A(x_orig)), 1e-4, 1e-5, f"simplified {deg}: Ap")
+    xs, _ = simplified_ddnm_plus(x_T.to(dev), m, SCH.linear_betas().to(dev), 0.85, D, y, 2 * sy, config=sampler_config(T, tl, tr),
+                                 noise=torch.stack(tape).to(dev))
+    img = torch.clamp((xs[0] + 1.0) / 2.0, 0.0, 1.0)
+    assert_close(img[:, :, ::4, ::4], g[f"{deg}_s{scale}_sy{sy}_T{T}_l{tl}_r{tr}_img_s4"], 1e-3, 5e-4, f"simplified {deg} vs reference runner")

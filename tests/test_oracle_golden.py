@@ -116,3 +116,33 @@ def test_sampler_matches_reference(gold, case):
     # the random-init net amplifies 1e-7 rounding differences by ~1e3 over the trajectory (1/sqrt(alpha-bar) early on)
     assert np.abs(x0.numpy() - g[key + "_x0"]).max() <= 1e-3
     assert np.abs(x0p.numpy() - g[key + "_x0pred"]).max() <= 1e-3
+
+
+SIMPLIFIED_CASES = [("sr_averagepooling", 4, 0.1, 3, 1, 1), ("colorization", 1, 0.0, 3, 1, 1), ("inpainting", 1, 0.05, 3, 1, 1),
+                    ("denoising", 1, 0.2, 3, 1, 1), ("mask_color_sr", 2, 0.05, 4, 2, 2)]
+
+
+def simplified_inputs(g, T, tl, tr):
+    npairs = len(SCH.time_pairs(1000, T, tl, tr))
+    nrng = torch.Generator().manual_seed(556)
+    tape = [torch.randn(1, 3, 256, 256, generator=nrng) for _ in range(npairs)]
+    torch.manual_seed(4242)
+    x_T = torch.randn(1, 3, 256, 256)
+    mask = torch.from_numpy(np.unpackbits(g["mask_bits"])[: 256 * 256].reshape(256, 256).astype(np.float32))
+    return x_T, 2 * torch.from_numpy(g["x01"]) - 1.0, mask, tape
+
+
+@pytest.mark.parametrize("case", SIMPLIFIED_CASES[:2] + SIMPLIFIED_CASES[4:], ids=lambda c: c[0])
+def test_simplified_loop_matches_reference_runner(gold, case):
+    from oracle import simplified as SP
+    deg, scale, sy, T, tl, tr = case
+    g = gold["simplified"]
+    cfg = U.SimpleUNetConfig.celeba_hq()
+    sd = U.init_state_dict(cfg, 1234)
+    x_T, x_orig, mask, tape = simplified_inputs(g, T, tl, tr)
+    A, Ap = SP.degradation(deg, scale, mask, 256)
+    with torch.no_grad():
+        ox, _ = SP.simplified_sample(x_T, lambda a, b: U.forward(sd, a, b, cfg), SCH.linear_betas(), 0.85, A, Ap, A(x_orig), 2 * sy, tape,
+                                     t_sampling=T, travel_length=tl, travel_repeat=tr)
+    img = torch.clamp((ox + 1.0) / 2.0, 0.0, 1.0)
+    assert np.abs(img[:, :, ::4, ::4].numpy() - g[f"{deg}_s{scale}_sy{sy}_T{T}_l{tl}_r{tr}_img_s4"]).max() <= 5e-4
