@@ -27,7 +27,8 @@ class OpenAICfg(C.Structure):
 class OperatorDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("channels", C.c_int), ("img_dim", C.c_int), ("ratio", C.c_int),
                 ("v_small", C.c_void_p), ("u_small", C.c_void_p), ("singulars", C.c_void_p),
-                ("singulars_orig", C.c_void_p), ("perm", C.c_void_p), ("mask", C.c_void_p)]
+                ("singulars_orig", C.c_void_p), ("perm", C.c_void_p), ("mask", C.c_void_p), ("v_small2", C.c_void_p),
+                ("u_small2", C.c_void_p)]
 
 
 class SimpleDeg(C.Structure):

@@ -444,6 +444,40 @@ __global__ void deblur_coeff_kernel(const float* __restrict__ v, const float* __
   }
 }
 
+// Denoising (svd_operators.py:442-476): A = I; Lambda / Lambda_noise are SCALAR rules of their own (not the table rule)
+template <int FN>
+__global__ void denoise_kernel(const float* __restrict__ in0, const float* __restrict__ in1, long long in1_stride,
+                               const float* __restrict__ in2, const float* __restrict__ y, StepScalars sc, float* __restrict__ out0,
+                               float* __restrict__ out1, int B, long long img) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * img) return;
+  const int b = (int)(i / img);
+  const PlusScalars& ps = sc.plus;
+  const float asy = __fmul_rn(ps.a, ps.sigma_y);
+  // Lambda (:462-467): sigma_t < a*sigma_y ? v * (sigma_t * sqrt(1-eta^2) / a / sigma_y) : v
+  const float lam = (ps.sigma_t < asy) ? __fdiv_rn(__fdiv_rn(__fmul_rn(ps.sigma_t, ps.c), ps.a), ps.sigma_y) : 1.0f;
+  // Lambda_noise (:469-474): sigma_t >= a*sigma_y ? v * sqrt(sigma_t^2 - a^2 sigma_y^2) : v * sigma_t * eta   (epsilon unused)
+  const float t2 = __fsub_rn(__fmul_rn(ps.sigma_t, ps.sigma_t), __fmul_rn(__fmul_rn(ps.a, ps.a), ps.sy2));
+  if (FN == LF_LAMBDA) {
+    out0[i] = (ps.sigma_t < asy) ? __fmul_rn(in0[i], lam) : in0[i];
+  } else if (FN == LF_NOISE) {
+    out0[i] = (ps.sigma_t >= asy) ? __fmul_rn(in0[i], sqrtf(t2)) : __fmul_rn(__fmul_rn(in0[i], ps.sigma_t), ps.eta);
+  } else {  // LF_STEP
+    const float et = in1[(long long)b * in1_stride + (i - (long long)b * img)];
+    const float z = in2[i];
+    const float x0 = x0_from(in0[i], et, sc);
+    out0[i] = x0;
+    const float resid = __fsub_rn(x0, y[i]);
+    if (!sc.use_plus) {
+      out1[i] = renoise(__fsub_rn(x0, resid), z, et, sc);
+    } else {
+      const float L = (ps.sigma_t < asy) ? __fmul_rn(resid, lam) : resid;
+      const float nz = (ps.sigma_t >= asy) ? __fmul_rn(z, sqrtf(t2)) : __fmul_rn(__fmul_rn(z, ps.sigma_t), ps.eta);
+      out1[i] = __fadd_rn(__fmul_rn(sc.sqrt_atn, __fsub_rn(x0, L)), nz);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Operator
 // ------------------------------------------------------------------------------------------------------------------
@@ -463,7 +497,8 @@ static std::vector<float> transpose(const float* m, int r, int c) {
 }
 
 Operator::Operator(int kind, int channels, int img_dim, int ratio, const float* v_small, const float* u_small,
-                   const float* singulars, const float* singulars_orig, const long long* perm, const long long* mask)
+                   const float* singulars, const float* singulars_orig, const long long* perm, const long long* mask,
+                   const float* v_small2, const float* u_small2)
     : kind_(kind), C_(channels), D_(img_dim), ratio_(ratio) {
   const int n2 = D_ * D_;
   DDNM_CHECK(channels >= 1 && img_dim >= 2, "bad operator geometry");
@@ -511,13 +546,27 @@ Operator::Operator(int kind, int channels, int img_dim, int ratio, const float* 
       M_ = (long long)C_ * n2 / ratio;
       break;
     }
-    case OP_DEBLUR: {
-      DDNM_CHECK(v_small && u_small && singulars && singulars_orig && perm, "Deblurring needs U, V, singular tables and perm");
+    case OP_DENOISE:
+      M_ = (long long)C_ * n2;   // svd_operators.py:442-476: A = identity
+      break;
+    case OP_DEBLUR:
+    case OP_DEBLUR2D: {
+      if (kind == OP_DEBLUR) DDNM_CHECK(singulars_orig != nullptr, "Deblurring needs the un-thresholded singulars");
+      DDNM_CHECK(v_small && u_small && singulars && perm, "Deblurring needs U, V, singular tables and perm");
       V_ = upload(owned_, v_small, (size_t)n2);
       U_ = upload(owned_, u_small, (size_t)n2);
       auto vt = transpose(v_small, D_, D_), ut = transpose(u_small, D_, D_);
       Vt_ = upload(owned_, vt.data(), (size_t)n2);
       Ut_ = upload(owned_, ut.data(), (size_t)n2);
+      Vr_ = V_; Vrt_ = Vt_; Ur_ = U_; Urt_ = Ut_;
+      if (kind == OP_DEBLUR2D) {   // svd_operators.py:1094-1166: different 1-D factors on the two sides, no Lambda
+        DDNM_CHECK(v_small2 && u_small2, "Deblurring2D needs the second pair of factors");
+        auto vt2 = transpose(v_small2, D_, D_), ut2 = transpose(u_small2, D_, D_);
+        Vr_ = upload(owned_, v_small2, (size_t)n2);
+        Ur_ = upload(owned_, u_small2, (size_t)n2);
+        Vrt_ = upload(owned_, vt2.data(), (size_t)n2);
+        Urt_ = upload(owned_, ut2.data(), (size_t)n2);
+      }
       // singulars() = _singulars.repeat(1, 3) is TILED while spectral vectors are (pos, chan)-interleaved
       // (svd_operators.py:1001 vs :984): D[c][perm[p]] = S[(C*p + c) mod n2]
       std::vector<float> tD((size_t)C_ * n2), tDi((size_t)C_ * n2), tS(n2);
@@ -529,7 +578,7 @@ Operator::Operator(int kind, int channels, int img_dim, int ratio, const float* 
           tD[(size_t)c * n2 + q] = s;
           tDi[(size_t)c * n2 + q] = s == 0.f ? 0.f : 1.0f / s;
         }
-        tS[q] = singulars_orig[p];
+        tS[q] = singulars_orig ? singulars_orig[p] : 0.f;
       }
       tabD_ = upload(owned_, tD.data(), tD.size());
       tabDinv_ = upload(owned_, tDi.data(), tDi.size());
@@ -628,12 +677,12 @@ void Operator::sandwich(const float* L, int lr, int lc, const float* X, int B, c
 void Operator::deblur_A(const float* x, int B, float* y, cudaStream_t s) {
   const int n2 = D_ * D_;
   const long long n = (long long)B * C_ * n2;
-  if (kind_ == OP_DEBLUR) {
+  if (kind_ == OP_DEBLUR || kind_ == OP_DEBLUR2D) {
     float* T = scratch(0, n);
     float* S = scratch(1, n);
-    sandwich(Vt_, D_, D_, x, B, V_, D_, D_, T, S, s);
+    sandwich(Vt_, D_, D_, x, B, Vr_, D_, D_, T, S, s);
     mul_table_kernel<<<blocks(n), 256, 0, s>>>(S, tabD_, 1, C_, n2, n);
-    sandwich(U_, D_, D_, S, B, Ut_, D_, D_, T, y, s);
+    sandwich(U_, D_, D_, S, B, Urt_, D_, D_, T, y, s);
   } else {  // SRConv: Vk^T X Vk -> (sm x sm), scale, U . U^T
     const int sm = D_ / ratio_;
     float* T = scratch(0, (size_t)B * C_ * sm * D_);
@@ -650,12 +699,12 @@ void Operator::deblur_A(const float* x, int B, float* y, cudaStream_t s) {
 void Operator::deblur_Apinv(const float* y, int B, float* x, cudaStream_t s) {
   const int n2 = D_ * D_;
   const long long n = (long long)B * C_ * n2;
-  if (kind_ == OP_DEBLUR) {
+  if (kind_ == OP_DEBLUR || kind_ == OP_DEBLUR2D) {
     float* T = scratch(0, n);
     float* S = scratch(1, n);
-    sandwich(Ut_, D_, D_, y, B, U_, D_, D_, T, S, s);
+    sandwich(Ut_, D_, D_, y, B, Ur_, D_, D_, T, S, s);
     mul_table_kernel<<<blocks(n), 256, 0, s>>>(S, tabDinv_, 1, C_, n2, n);
-    sandwich(V_, D_, D_, S, B, Vt_, D_, D_, T, x, s);
+    sandwich(V_, D_, D_, S, B, Vrt_, D_, D_, T, x, s);
   } else {
     const int sm = D_ / ratio_;
     float* S = scratch(1, (size_t)B * C_ * sm * sm);
@@ -675,6 +724,10 @@ void Operator::deblur_Apinv(const float* y, int B, float* x, cudaStream_t s) {
 void Operator::A(const float* x, int B, float* y, cudaStream_t s) {
   StepScalars sc{};
   const int n2 = D_ * D_;
+  if (kind_ == OP_DENOISE) {
+    CUDA_CHECK(cudaMemcpyAsync(y, x, (size_t)B * C_ * n2 * 4, cudaMemcpyDeviceToDevice, s));
+    return;
+  }
   switch (kind_) {
     case OP_SR: case OP_COLOR:
       local_dispatch<LF_A>(kind_, ratio_, x, nullptr, 0, nullptr, nullptr, V_, u00_, s0_, sc, y, nullptr, B, C_, D_, s);
@@ -698,6 +751,10 @@ void Operator::A(const float* x, int B, float* y, cudaStream_t s) {
 void Operator::A_pinv(const float* y, int B, float* x, cudaStream_t s) {
   StepScalars sc{};
   const int n2 = D_ * D_;
+  if (kind_ == OP_DENOISE) {
+    CUDA_CHECK(cudaMemcpyAsync(x, y, (size_t)B * C_ * n2 * 4, cudaMemcpyDeviceToDevice, s));
+    return;
+  }
   switch (kind_) {
     case OP_SR: case OP_COLOR:
       local_dispatch<LF_PINV>(kind_, ratio_, nullptr, nullptr, 0, nullptr, y, V_, u00_, s0_, sc, x, nullptr, B, C_, D_, s);
@@ -718,6 +775,13 @@ void Operator::project(const float* x0, const float* y, int B, float* out, cudaS
   StepScalars sc{};
   const int n2 = D_ * D_;
   const long long n = (long long)B * C_ * n2;
+  if (kind_ == OP_DENOISE) {   // x0 - (x0 - y)
+    float* R = scratch(4, n);
+    sub_kernel<<<blocks(n), 256, 0, s>>>(x0, y, R, n);
+    sub_kernel<<<blocks(n), 256, 0, s>>>(x0, R, out, n);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   switch (kind_) {
     case OP_SR: case OP_COLOR:
       local_dispatch<LF_PROJECT>(kind_, ratio_, x0, nullptr, 0, nullptr, y, V_, u00_, s0_, sc, out, nullptr, B, C_, D_, s);
@@ -752,6 +816,12 @@ void Operator::lambda(const float* v, int B, const PlusScalars& ps, float* out, 
   sc.plus = ps;
   const int n2 = D_ * D_;
   const long long n = (long long)B * C_ * n2;
+  if (kind_ == OP_DENOISE) {
+    denoise_kernel<LF_LAMBDA><<<blocks(n), 256, 0, s>>>(v, nullptr, 0, nullptr, nullptr, sc, out, nullptr, B, (long long)C_ * n2);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
+  if (kind_ == OP_DEBLUR2D) throw Error("Deblurring2D defines no Lambda (svd_operators.py:1094-1166): sigma_y > 0 is unsupported, as in the reference");
   switch (kind_) {
     case OP_SR: case OP_COLOR:
       local_dispatch<LF_LAMBDA>(kind_, ratio_, v, nullptr, 0, nullptr, nullptr, V_, u00_, s0_, sc, out, nullptr, B, C_, D_, s);
@@ -787,6 +857,12 @@ void Operator::lambda_noise(const float* v, const float* eps, int B, const PlusS
   const int n2 = D_ * D_;
   const long long n = (long long)B * C_ * n2;
   const long long img = (long long)C_ * n2;
+  if (kind_ == OP_DENOISE) {
+    denoise_kernel<LF_NOISE><<<blocks(n), 256, 0, s>>>(v, nullptr, 0, nullptr, nullptr, sc, out, nullptr, B, img);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
+  if (kind_ == OP_DEBLUR2D) throw Error("Deblurring2D defines no Lambda_noise (svd_operators.py:1094-1166)");
   switch (kind_) {
     case OP_SR: case OP_COLOR:
       local_dispatch<LF_NOISE>(kind_, ratio_, v, eps, img, nullptr, nullptr, V_, u00_, s0_, sc, out, nullptr, B, C_, D_, s);
@@ -820,6 +896,8 @@ void Operator::step(const float* xt, const float* et, long long et_stride, const
     local_dispatch<LF_STEP>(kind_, ratio_, xt, et, et_stride, noise, y, V_, u00_, s0_, sc, x0_t, xt_next, B, C_, D_, s);
   } else if (kind_ == OP_INPAINT) {
     inpaint_kernel<LF_STEP><<<blocks(n), 256, 0, s>>>(xt, et, et_stride, noise, y, rank_, sc, x0_t, xt_next, B, C_, n2, M_);
+  } else if (kind_ == OP_DENOISE) {
+    denoise_kernel<LF_STEP><<<blocks(n), 256, 0, s>>>(xt, et, et_stride, noise, y, sc, x0_t, xt_next, B, img);
   } else {
     // generic path: x0_t, residual r = A^+(A x0_t - y), then the DDNM / DDNM+ update
     float* et3 = scratch(5, n);
@@ -861,7 +939,7 @@ int ddnm_operator_create(const ddnm_operator_desc* d, void** handle) {
   DDNM_API_BEGIN
   DDNM_CHECK(d && handle, "null argument");
   *handle = new Operator(d->kind, d->channels, d->img_dim, d->ratio, d->v_small, d->u_small, d->singulars, d->singulars_orig,
-                         d->perm, d->mask);
+                         d->perm, d->mask, d->v_small2, d->u_small2);
   DDNM_API_END
 }
 long long ddnm_operator_y_dim(void* h) { return h ? static_cast<Operator*>(h)->y_dim() : -1; }

@@ -7,7 +7,7 @@
 
 namespace ddnm {
 
-enum OpKind : int { OP_SR = 0, OP_COLOR = 1, OP_INPAINT = 2, OP_WH = 3, OP_DEBLUR = 4, OP_SRCONV = 5 };
+enum OpKind : int { OP_SR = 0, OP_COLOR = 1, OP_INPAINT = 2, OP_WH = 3, OP_DEBLUR = 4, OP_SRCONV = 5, OP_DENOISE = 6, OP_DEBLUR2D = 7 };
 
 // scalars of one DDNM+ step (svd_ddnm.py:119-131); all fp32 exactly as the reference's 0-dim tensors / casts
 struct PlusScalars {
@@ -28,7 +28,8 @@ struct StepScalars {
 class Operator {
  public:
   Operator(int kind, int channels, int img_dim, int ratio, const float* v_small, const float* u_small, const float* singulars,
-           const float* singulars_orig, const long long* perm, const long long* mask);
+           const float* singulars_orig, const long long* perm, const long long* mask, const float* v_small2 = nullptr,
+           const float* u_small2 = nullptr);
   ~Operator();
   long long y_dim() const { return M_; }
   long long x_dim() const { return (long long)C_ * D_ * D_; }
@@ -56,6 +57,7 @@ class Operator {
   long long M_ = 0;
   // device artefacts
   float *V_ = nullptr, *Vt_ = nullptr, *U_ = nullptr, *Ut_ = nullptr;
+  float *Vr_ = nullptr, *Vrt_ = nullptr, *Ur_ = nullptr, *Urt_ = nullptr;   // right-hand factors (== left ones unless Deblurring2D)
   float u00_ = 1.f, s0_ = 1.f;
   float *tabD_ = nullptr, *tabDinv_ = nullptr, *tabSorig_ = nullptr;  // deblur: per (c, pos) / per pos tables; srconv: S2, S2inv
   int *rank_ = nullptr;      // inpaint: kept-rank per pixel or -1

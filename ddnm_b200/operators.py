@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-KIND = dict(sr=0, color=1, inpaint=2, wh=3, deblur=4, srconv=5)
+KIND = dict(sr=0, color=1, inpaint=2, wh=3, deblur=4, srconv=5, denoise=6, deblur2d=7)
 
 
 def _host_f32(t):
@@ -28,13 +28,13 @@ class _Operator:
     never calls (V, Vt, U, Ut, singulars, add_zeros) raise NotImplementedError exactly like the reference's base class."""
 
     def _create(self, kind, channels, img_dim, ratio=0, v_small=None, u_small=None, singulars=None, singulars_orig=None,
-                perm=None, mask=None):
+                perm=None, mask=None, v_small2=None, u_small2=None):
         self.channels, self.img_dim = channels, img_dim
         keep = [_host_f32(v_small), _host_f32(u_small), _host_f32(singulars), _host_f32(singulars_orig), _host_i64(perm),
-                _host_i64(mask)]
+                _host_i64(mask), _host_f32(v_small2), _host_f32(u_small2)]
         d = _lib.OperatorDesc()
         d.kind, d.channels, d.img_dim, d.ratio = KIND[kind], channels, img_dim, ratio
-        for name, arr in zip(("v_small", "u_small", "singulars", "singulars_orig", "perm", "mask"), keep):
+        for name, arr in zip(("v_small", "u_small", "singulars", "singulars_orig", "perm", "mask", "v_small2", "u_small2"), keep):
             setattr(d, name, None if arr is None else arr.ctypes.data)
         self._h = C.c_void_p()
         _lib.check(_lib.lib().ddnm_operator_create(C.byref(d), C.byref(self._h)))
@@ -196,6 +196,47 @@ class SRConv(_Operator):
         self.U_small, self.singulars_small, self.V_small = artefacts
         self.ratio = stride
         self._create("srconv", channels, img_dim, stride, self.V_small, self.U_small, self.singulars_small)
+
+    def Lambda(self, *a, **k):
+        raise NotImplementedError()
+
+    def Lambda_noise(self, *a, **k):
+        raise NotImplementedError()
+
+
+class Denoising(_Operator):
+    """svd_operators.py:442-476 — ``Denoising(channels, img_dim, device)``."""
+
+    def __init__(self, channels, img_dim, device):
+        self._create("denoise", channels, img_dim)
+
+
+def _band(kernel, img_dim, device):
+    A_small = torch.zeros(img_dim, img_dim, device=device)
+    for i in range(img_dim):
+        for j in range(i - kernel.shape[0] // 2, i + kernel.shape[0] // 2):
+            if j < 0 or j >= img_dim:
+                continue
+            A_small[i, j] = kernel[j - i + kernel.shape[0] // 2]
+    return A_small
+
+
+class Deblurring2D(_Operator):
+    """svd_operators.py:1094-1166 — ``Deblurring2D(kernel1, kernel2, channels, img_dim, device)`` (deblur_aniso).
+    Defines no Lambda: DDNM+ raises, as in the reference."""
+
+    def __init__(self, kernel1, kernel2, channels, img_dim, device, artefacts=None):
+        if artefacts is None:
+            U1, S1, V1 = torch.svd(_band(kernel1, img_dim, device), some=False)
+            U2, S2, V2 = torch.svd(_band(kernel2, img_dim, device), some=False)
+            S1[S1 < 3e-2] = 0
+            S2[S2 < 3e-2] = 0
+            big = torch.matmul(S1.reshape(img_dim, 1), S2.reshape(1, img_dim)).reshape(img_dim ** 2)
+            big, perm = big.sort(descending=True)
+            artefacts = (U1, V1, U2, V2, big, perm)
+        self.U_small1, self.V_small1, self.U_small2, self.V_small2, self._singulars, self._perm = artefacts
+        self._create("deblur2d", channels, img_dim, 1, self.V_small1, self.U_small1, self._singulars, None, self._perm,
+                     v_small2=self.V_small2, u_small2=self.U_small2)
 
     def Lambda(self, *a, **k):
         raise NotImplementedError()

@@ -68,7 +68,8 @@ int ddnm_unet_destroy(void* handle);
  * Degradation operators: functions/svd_operators.py A_functions contract (:52-97):
  * A, A_pinv, Lambda, Lambda_noise, plus the fused projection x0 - A^+(A x0 - y) of svd_ddnm.py:59-61.
  * kind: 0 SuperResolution(:479) 1 Colorization(:627) 2 Inpainting(:324) 3 WalshHadamardCS(:211)
- *       4 Deblurring(:934) 5 SRConv(:851).  Artefacts (V_small, perm, mask, singular tables) are inputs.
+ *       4 Deblurring(:934) 5 SRConv(:851) 6 Denoising(:442) 7 Deblurring2D(:1094).
+ * Artefacts (V_small, perm, mask, singular tables) are inputs.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   int kind, channels, img_dim, ratio;
@@ -79,6 +80,8 @@ typedef struct {
   const long long* perm;      /* WalshHadamardCS: [dim*dim]; Deblurring: [dim*dim] */
   const long long* mask;      /* Inpainting: [dim*dim*channels] keep flags over the (pixel, channel)-interleaved vector the
                                  reference's missing_indices address (diffusion.py:466-470); 0 = missing */
+  const float* v_small2;      /* Deblurring2D: V_small2 [dim,dim] (right-hand factor); others NULL */
+  const float* u_small2;      /* Deblurring2D: U_small2 [dim,dim] */
 } ddnm_operator_desc;         /* all pointers: host memory, copied at creation */
 
 int ddnm_operator_create(const ddnm_operator_desc* desc, void** handle);

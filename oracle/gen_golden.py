@@ -205,7 +205,22 @@ def build_ops(dim, rng):
     r = R.SRConv(k, 3, dim, "cpu", stride=4)
     ops.append(("bicubic", r, O.SRConv(3, dim, 4, r.U_small, r.singulars_small, r.V_small),
                 dict(U_small=r.U_small, singulars_small=r.singulars_small, V_small=r.V_small)))
+    ops.append(("denoise", R.Denoising(3, dim, "cpu"), O.Denoising(3, dim), dict()))
+    k1, k2 = aniso_kernels()
+    r = R.Deblurring2D(k1, k2, 3, dim, "cpu")
+    ops.append(("deblur2d", r, O.Deblurring2D(3, dim, r.U_small1, r.V_small1, r.U_small2, r.V_small2, r._singulars, r._perm),
+                dict(U_small1=r.U_small1, V_small1=r.V_small1, U_small2=r.U_small2, V_small2=r.V_small2, singulars=r._singulars,
+                     perm=r._perm)))
     return ops
+
+
+def aniso_kernels():
+    # diffusion.py:510-521 (deblur_aniso)
+    def pdf(sigma):
+        return lambda z: torch.exp(torch.Tensor([-0.5 * (z / sigma) ** 2]))
+    k2 = torch.Tensor([pdf(20)(i) for i in range(-4, 5)])
+    k1 = torch.Tensor([pdf(1)(i) for i in range(-4, 5)])
+    return k1 / k1.sum(), k2 / k2.sum()
 
 
 LAMBDA_CASES = [(0.9, 0.1, 0.3), (0.99, 0.1, 0.02), (1.0, 0.1, 0.0), (0.5, 0.0, 0.4)]   # (a, sigma_y, sigma_t)
@@ -236,7 +251,7 @@ def operator_fixtures():
             out[f"{tag}_{name}_A"] = sub(y).numpy()
             out[f"{tag}_{name}_Apinv"] = sub(pin).numpy()
             out[f"{tag}_{name}_proj"] = sub(proj).numpy()
-            if name != "bicubic":
+            if name not in ("bicubic", "deblur2d"):
                 for ci, (a, sy, st) in enumerate(LAMBDA_CASES):
                     at, stt = torch.tensor(a), torch.tensor(st)
                     L = r.Lambda(v.clone(), at, sy, stt, 0.85)

@@ -379,3 +379,79 @@ class SRConv(OracleOperator):
 
     def Lambda_noise(self, *args):
         raise NotImplementedError()
+
+
+# ----------------------------------------------------------------------------------------------
+class Denoising(OracleOperator):
+    """svd_operators.py:442-476.  A = identity; Lambda / Lambda_noise are scalar rules (epsilon is ignored)."""
+
+    def __init__(self, channels, img_dim):
+        self.channels, self.img_dim = channels, img_dim
+
+    def A(self, v):
+        return v.clone().reshape(v.shape[0], -1)
+
+    def A_pinv(self, y):
+        return y.clone().reshape(y.shape[0], -1)
+
+    def Lambda(self, v, a, sigma_y, sigma_t, eta):
+        if sigma_t < a * sigma_y:
+            factor = (sigma_t * (1 - eta ** 2) ** 0.5 / a / sigma_y).item()
+            return v * factor
+        return v
+
+    def Lambda_noise(self, v, a, sigma_y, sigma_t, eta, eps):
+        if sigma_t >= a * sigma_y:
+            factor = torch.sqrt(sigma_t ** 2 - a ** 2 * sigma_y ** 2).item()
+            return v * factor
+        return v * sigma_t * eta
+
+
+class Deblurring2D(OracleOperator):
+    """svd_operators.py:1094-1166 (deblur_aniso): X -> U1 (D_c o (V1^T X V2)) U2^T with the same tiled-singular quirk as
+    Deblurring (``singulars()`` = repeat(1, 3), :1162); base-class A_pinv; no Lambda."""
+
+    def __init__(self, channels, img_dim, U1, V1, U2, V2, singulars_sorted, perm):
+        self.channels, self.img_dim = channels, img_dim
+        self.U1, self.V1, self.U2, self.V2 = U1, V1, U2, V2
+        self.S, self.perm = singulars_sorted, torch.as_tensor(perm).long()
+        n2 = img_dim ** 2
+        tiled = self.S.repeat(1, channels).reshape(-1)
+        D = torch.zeros(channels, n2)
+        D[:, self.perm] = tiled.reshape(n2, channels).t()
+        self.D = D.reshape(channels, img_dim, img_dim)
+        self.Dinv = torch.where(self.D == 0, torch.zeros_like(self.D), 1.0 / self.D)
+
+    @staticmethod
+    def band(kernel, img_dim):
+        k = kernel.shape[0]
+        A = torch.zeros(img_dim, img_dim)
+        for i in range(img_dim):
+            for j in range(i - k // 2, i + k // 2):
+                if 0 <= j < img_dim:
+                    A[i, j] = kernel[j - i + k // 2]
+        return A
+
+    @staticmethod
+    def make(kernel1, kernel2, channels, img_dim, ZERO=3e-2):
+        U1, S1, V1 = torch.svd(Deblurring2D.band(kernel1, img_dim), some=False)
+        U2, S2, V2 = torch.svd(Deblurring2D.band(kernel2, img_dim), some=False)
+        S1[S1 < ZERO] = 0
+        S2[S2 < ZERO] = 0
+        big = torch.matmul(S1.reshape(img_dim, 1), S2.reshape(1, img_dim)).reshape(-1)
+        big, perm = big.sort(descending=True)
+        return Deblurring2D(channels, img_dim, U1, V1, U2, V2, big, perm)
+
+    def A(self, v):
+        spec = torch.matmul(torch.matmul(self.V1.t(), self._img(v)), self.V2) * self.D
+        return torch.matmul(torch.matmul(self.U1, spec), self.U2.t()).reshape(v.shape[0], -1)
+
+    def A_pinv(self, y):
+        spec = torch.matmul(torch.matmul(self.U1.t(), self._img(y)), self.U2) * self.Dinv
+        return torch.matmul(torch.matmul(self.V1, spec), self.V2.t()).reshape(y.shape[0], -1)
+
+    def Lambda(self, *args):
+        raise NotImplementedError()
+
+    def Lambda_noise(self, *args):
+        raise NotImplementedError()

@@ -48,12 +48,16 @@ def oracle_ops(gold_ops, dim=32):
                                      art(gold_ops, tag, "deblur", "perm"))
         ops["bicubic"] = O.SRConv(3, dim, 4, art(gold_ops, tag, "bicubic", "U_small"), art(gold_ops, tag, "bicubic", "singulars_small"),
                                   art(gold_ops, tag, "bicubic", "V_small"))
+        ops["deblur2d"] = O.Deblurring2D(3, dim, art(gold_ops, tag, "deblur2d", "U_small1"), art(gold_ops, tag, "deblur2d", "V_small1"),
+                                         art(gold_ops, tag, "deblur2d", "U_small2"), art(gold_ops, tag, "deblur2d", "V_small2"),
+                                         art(gold_ops, tag, "deblur2d", "singulars"), art(gold_ops, tag, "deblur2d", "perm"))
     else:
         ops["sr4"] = O.SuperResolution.make(3, dim, 4)
         ops["color"] = O.Colorization.make(dim)
         ops["deblur"] = O.Deblurring.make(gauss_kernel(), 3, dim)
         ops["bicubic"] = O.SRConv.make(O.SRConv.bicubic_kernel(4), 3, dim, 4)
     ops["wh"] = O.WalshHadamardCS(3, dim, 4, art(gold_ops, tag, "wh", "perm"))
+    ops["denoise"] = O.Denoising(3, dim)
     return ops
 
 
@@ -74,6 +78,10 @@ def engine_op(name, oop, dim, device="cuda"):
         return E.Deblurring(None, 3, dim, device, artefacts=(oop.U_small, oop.V_small, oop.S, oop.S_orig, oop.perm))
     if name == "bicubic":
         return E.SRConv(None, 3, dim, device, stride=4, artefacts=(oop.U_small, oop.S_small, oop.V_small))
+    if name == "denoise":
+        return E.Denoising(3, dim, device)
+    if name == "deblur2d":
+        return E.Deblurring2D(None, None, 3, dim, device, artefacts=(oop.U1, oop.V1, oop.U2, oop.V2, oop.S, oop.perm))
     raise KeyError(name)
 
 
