@@ -49,6 +49,7 @@ _SIGS = {
     "ddnm_unet_simple_create": (C.c_int, [C.POINTER(SimpleCfg), _I, C.POINTER(_P)]),
     "ddnm_unet_openai_create": (C.c_int, [C.POINTER(OpenAICfg), _I, C.POINTER(_P)]),
     "ddnm_unet_set_param": (C.c_int, [_P, C.c_char_p, _P, _LL]),
+    "ddnm_unet_set_precision": (C.c_int, [_P, _I]),
     "ddnm_unet_finalize": (C.c_int, [_P]),
     "ddnm_unet_forward": (C.c_int, [_P, _P, _P, _P, _P]),
     "ddnm_unet_set_graph": (C.c_int, [_P, _I]),

@@ -67,6 +67,11 @@ int ddnm_unet_forward(void* h, const float* x, const float* t, float* out, void*
   static_cast<UNetEngine*>(h)->forward(x, t, out, (cudaStream_t)stream);
   DDNM_API_END
 }
+int ddnm_unet_set_precision(void* h, int fp16_terms) {
+  DDNM_API_BEGIN
+  static_cast<UNetEngine*>(h)->set_terms(fp16_terms);
+  DDNM_API_END
+}
 int ddnm_unet_set_graph(void* h, int on) {
   DDNM_API_BEGIN
   static_cast<UNetEngine*>(h)->set_use_graph(on != 0);

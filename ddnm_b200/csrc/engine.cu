@@ -253,9 +253,23 @@ void UNetEngine::emit_head(const std::string& norm, const std::string& conv, con
          [=](cudaStream_t s) { head_conv_gn_silu(fh, groups, g, b, eps, w, bo, oc, o, s); });
 }
 
+void UNetEngine::set_terms(int t) {
+  DDNM_CHECK(!finalized_, "precision must be chosen before finalize");
+  DDNM_CHECK(t == 1 || t == 3, "terms must be 1 (fast fp16) or 3 (fp32-grade)");
+  terms_ = t;
+}
+
 void UNetEngine::finalize() {
   DDNM_CHECK(!finalized_, "finalize called twice");
-  build_program();
+  const int prev = tc_get_terms();
+  tc_set_terms(terms_);
+  try {
+    build_program();
+  } catch (...) {
+    tc_set_terms(prev);
+    throw;
+  }
+  tc_set_terms(prev);
   // every GroupNorm sum is accumulated with atomics during the forward: clear the pool first
   std::vector<OpRecord> zero;
   for (const StatsChunk& c : stats_chunks_) {

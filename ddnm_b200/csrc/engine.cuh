@@ -73,6 +73,8 @@ class UNetEngine {
   float* t_in() const { return t_in_; }
   float* out_buf() const { return out_; }
   void set_use_graph(bool on) { use_graph_ = on; }
+  // 3 = fp32-grade products (parity mode, default); 1 = single fp16 product per MAC (fast, NOT parity-grade). Before finalize.
+  void set_terms(int t);
   size_t workspace_bytes() const { return arena_.used(); }
   int num_launches() const { return (int)ops_.size(); }
   double flops_per_forward() const;
@@ -113,6 +115,7 @@ class UNetEngine {
   float eps_;
   int num_sms_ = 148;
   bool finalized_ = false, use_graph_ = true;
+  int terms_ = 3;
   Arena arena_;
   std::map<std::string, Param> params_;
   std::vector<OpRecord> ops_;

@@ -105,7 +105,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t fb = full_bar(stage);
-          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+          mbar_expect_tx(fb, p.terms == 1 ? Cfg::STAGE_BYTES / 2 : Cfg::STAGE_BYTES);
+          const bool lo = p.terms != 1;
           if (kb < p.kb0) {
             const int tap = kb / p.cb0;
             const int c = (kb - tap * p.cb0) * BK;
@@ -120,18 +121,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
               cn += ((dy & 1) * 2 + (dx & 1)) * p.phase_stride;
             }
             tma_load_4d(sa, &tm_a0h, fb, c, cx, cy, cn);
-            tma_load_4d(sa + A_PLANE_BYTES, &tm_a0l, fb, c, cx, cy, cn);
+            if (lo) tma_load_4d(sa + A_PLANE_BYTES, &tm_a0l, fb, c, cx, cy, cn);
           } else {
             const int c = (kb - p.kb0) * BK;
             tma_load_4d(sa, &tm_a1h, fb, c, x0, y0, n0);
-            tma_load_4d(sa + A_PLANE_BYTES, &tm_a1l, fb, c, x0, y0, n0);
+            if (lo) tma_load_4d(sa + A_PLANE_BYTES, &tm_a1l, fb, c, x0, y0, n0);
           }
           if (p.b_batched == 2) {
             tma_load_4d(sa + 2 * A_PLANE_BYTES, &tm_bh, fb, kb * BK, n_idx * BN, y0, n0);
-            tma_load_4d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tm_bl, fb, kb * BK, n_idx * BN, y0, n0);
+            if (lo) tma_load_4d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tm_bl, fb, kb * BK, n_idx * BN, y0, n0);
           } else {
             tma_load_3d(sa + 2 * A_PLANE_BYTES, &tm_bh, fb, kb * BK, n_idx * BN, bz);
-            tma_load_3d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tm_bl, fb, kb * BK, n_idx * BN, bz);
+            if (lo) tma_load_3d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tm_bl, fb, kb * BK, n_idx * BN, bz);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -162,8 +163,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
           for (int k = 0; k < BK / 16; ++k) {
             const uint32_t adv = 2u * k;  // 16 fp16 = 32 bytes = 2 x 16-byte units inside the swizzle row
             umma_f16(d_tmem, hi | (ah + adv), hi | (bh + adv), p.idesc, (uint32_t)((kb | k) != 0));
-            umma_f16(d_tmem, hi | (ah + adv), hi | (bl + adv), p.idesc, 1u);
-            umma_f16(d_tmem, hi | (al + adv), hi | (bh + adv), p.idesc, 1u);
+            if (p.terms != 1) {
+              umma_f16(d_tmem, hi | (ah + adv), hi | (bl + adv), p.idesc, 1u);
+              umma_f16(d_tmem, hi | (al + adv), hi | (bh + adv), p.idesc, 1u);
+            }
           }
           umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
           if (++stage == STAGES) {
@@ -353,6 +356,12 @@ static CUtensorMap make_map_f16(const void* base, int rank, const uint64_t* dims
 }
 
 static uint32_t g_desc_hi_override = 0, g_idesc_xor = 0;
+static int g_terms = 3;
+void tc_set_terms(int terms) {
+  DDNM_CHECK(terms == 1 || terms == 3, "terms must be 1 or 3");
+  g_terms = terms;
+}
+int tc_get_terms() { return g_terms; }
 void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor) {
   g_desc_hi_override = desc_hi;
   g_idesc_xor = idesc_xor;
@@ -408,6 +417,7 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   DDNM_CHECK(out.C == Cout && out.ld % 4 == 0 && ((uintptr_t)out.p & 15) == 0, "output view misaligned");
   p.chanadd = chanadd; p.ca_ld = ca_ld; p.residual = residual; p.ldr = ldr; p.alpha = alpha; p.res_mode = res_mode;
   p.stats = out.st; p.st_ld = out.st_ld;
+  p.terms = g_terms;
   if (out.st) DDNM_CHECK(p.bw * p.bh >= 32, "GroupNorm statistics need >= 32 pixels per image");
   if (residual) DDNM_CHECK(ldr % 4 == 0 && ((uintptr_t)residual & 15) == 0, "residual misaligned");
   // UMMA shared-memory descriptor, high word: SBO = 1024 B (8 rows x 128 B) >> 4 at bits [32,46), version = 1 at
@@ -465,6 +475,7 @@ TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, 
   DDNM_CHECK(out_sx % 4 == 0 && out_sy % 4 == 0 && out_sn % 4 == 0 && ((uintptr_t)out & 15) == 0, "attention GEMM output misaligned");
   p.chanadd = nullptr; p.ca_ld = 0; p.residual = nullptr; p.ldr = 0; p.res_mode = 0; p.alpha = alpha;
   p.stats = nullptr; p.st_ld = 0;
+  p.terms = g_terms;
   p.desc_hi = g_desc_hi_override ? g_desc_hi_override : (64u | (1u << 14) | (2u << 29));
   p.idesc = ((1u << 4) | ((uint32_t)(L.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24)) ^ g_idesc_xor;
   const uint64_t ad[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)heads, (uint64_t)images};

@@ -33,6 +33,7 @@ struct TcParams {
   float alpha;                 // out = alpha*acc + chanadd + residual
   double* stats;               // optional GroupNorm sums of the OUTPUT: stats[(image*st_ld + co)*2 + {0,1}] += {sum, sumsq}
   int st_ld;
+  int terms;                   // 3: hi*hi + hi*lo + lo*hi (fp32-grade, default); 1: hi*hi only (plain fp16 inputs, fast mode)
   uint32_t desc_hi;            // UMMA smem descriptor high word (SW128 K-major), see tc_gemm.cu
   uint32_t idesc;              // UMMA instruction descriptor
 };
@@ -66,5 +67,8 @@ TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, 
 
 // debug knobs (tests only): override descriptor words for the NEXT launches built
 void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor);
+// number of fp16 product terms used by launches built from now on (3 = parity mode, 1 = fast mode)
+void tc_set_terms(int terms);
+int tc_get_terms();
 
 }  // namespace ddnm

@@ -25,6 +25,9 @@ class _EngineModel:
         self._sd = None
         self._engines = {}      # batch -> handle
         self.use_cuda_graph = True
+        # "fp32": fp32-grade tensor-core products (3 fp16 MMAs per MAC) — the parity mode and the default.
+        # "fp16": one fp16 product per MAC, fp32 accumulation — fast mode, NOT within the fp32 parity tolerance.
+        self.precision = "fp32"
         _lib.lib()              # fail early if the CUDA library is absent
 
     def load_state_dict(self, sd, strict=True):
@@ -63,6 +66,9 @@ class _EngineModel:
         for name, t in params.items():
             t = t.contiguous()
             _lib.check(L.ddnm_unet_set_param(h, name.encode(), _lib.ptr(t), t.numel()))
+        if self.precision not in ("fp32", "fp16"):
+            raise ValueError("precision must be 'fp32' (parity) or 'fp16' (fast)")
+        _lib.check(L.ddnm_unet_set_precision(h, 3 if self.precision == "fp32" else 1))
         _lib.check(L.ddnm_unet_finalize(h))
         _lib.check(L.ddnm_unet_set_graph(h, 1 if self.use_cuda_graph else 0))
         self._engines[batch] = h

@@ -54,6 +54,10 @@ int ddnm_unet_openai_create(const ddnm_openai_cfg* cfg, int batch, void** handle
 /* name = key of Model.state_dict() (models.py:216-299), data = fp32 host or device, reference layout (OIHW);
  * plus the pseudo-parameter "__freq" = exp(arange(ch/2) * -log(1e4)/(ch/2-1)) (models.py:16-18). */
 int ddnm_unet_set_param(void* handle, const char* name, const float* data, long long numel);
+/* Arithmetic of the tensor-core contractions, to be chosen before finalize: 3 (default) = every fp32 product as
+ * hi*hi + hi*lo + lo*hi of fp16 pairs (fp32-grade, the parity mode); 1 = one fp16 product per MAC with fp32 accumulation
+ * (fast mode; comparable to the reference's own use_fp16 torso, unet.py:619-625, NOT within rtol 1e-3 of the fp32 model). */
+int ddnm_unet_set_precision(void* handle, int fp16_terms);
 int ddnm_unet_finalize(void* handle);
 /* x [B,3,R,R] NCHW fp32, t [B] fp32 holding integer timesteps, out [B,out_ch,R,R] NCHW fp32 */
 int ddnm_unet_forward(void* handle, const float* x, const float* t, float* out, void* stream);

@@ -209,12 +209,13 @@ def group_openai(which="tiny", B=2, graph=1):
           f"violations(rtol1e-3,atol1e-4) {viol * 100:.4f}%  ->", "PASS" if viol == 0 else "FAIL", flush=True)
 
 
-def group_openai_bench(B=8, iters=3):
+def group_openai_bench(B=8, iters=3, prec="fp32"):
     from ddnm_b200.model import create_model
     from ddnm_b200.weights import random_state_dict_openai
     B, iters = int(B), int(iters)
     m = create_model(image_size=256, num_channels=256, num_res_blocks=2, learn_sigma=True, attention_resolutions="32,16,8",
                      num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True, use_fp16=True)
+    m.precision = prec
     m.load_state_dict(random_state_dict_openai(m, 1234))
     x = torch.randn(B, 3, 256, 256, device=dev)
     t = torch.full((B,), 500.0, device=dev)
@@ -260,13 +261,14 @@ def group_cpu_threads():
             print(f"   threads {nt}: {time.time() - t0:.2f} s / image-forward", flush=True)
 
 
-def group_unet_bench(which="celeba", B=16, iters=5):
+def group_unet_bench(which="celeba", B=16, iters=5, prec="fp32"):
     from oracle import unet_simple as U
     from ddnm_b200.model import Model
     B, iters = int(B), int(iters)
     cfg = U.SimpleUNetConfig.tiny() if which == "tiny" else U.SimpleUNetConfig.celeba_hq()
     sd = U.init_state_dict(cfg, 1234)
     m = Model(_cfg_ns(cfg))
+    m.precision = prec
     m.load_state_dict(sd)
     x = torch.randn(B, 3, cfg.resolution, cfg.resolution, device=dev)
     t = torch.full((B,), 500.0, device=dev)
