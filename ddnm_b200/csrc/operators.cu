@@ -444,6 +444,22 @@ __global__ void deblur_coeff_kernel(const float* __restrict__ v, const float* __
   }
 }
 
+// CS (svd_operators.py:101-159): 32x32 patches <-> rows of a [B*C*y*y, 1024] matrix (row-major inside the patch)
+template <bool TO_ROWS>
+__global__ void cs_patch_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * C * D * D;
+  if (i >= total) return;
+  const int yd = D / 32;
+  const int k = (int)(i % 1024);
+  const long long pr = i / 1024;                 // (b, c, py, px)
+  const int px = (int)(pr % yd), py = (int)((pr / yd) % yd);
+  const long long bc = pr / ((long long)yd * yd);
+  const long long img = bc * D * D + (long long)(py * 32 + k / 32) * D + (px * 32 + k % 32);
+  if (TO_ROWS) dst[i] = src[img];
+  else dst[img] = src[i];
+}
+
 // Denoising (svd_operators.py:442-476): A = I; Lambda / Lambda_noise are SCALAR rules of their own (not the table rule)
 template <int FN>
 __global__ void denoise_kernel(const float* __restrict__ in0, const float* __restrict__ in1, long long in1_stride,
@@ -549,6 +565,14 @@ Operator::Operator(int kind, int channels, int img_dim, int ratio, const float* 
     case OP_DENOISE:
       M_ = (long long)C_ * n2;   // svd_operators.py:442-476: A = identity
       break;
+    case OP_CS: {
+      // ratio field carries cs_size = int(32*32*cs_ratio) (svd_operators.py:111)
+      DDNM_CHECK(v_small && img_dim % 32 == 0 && ratio >= 1 && ratio <= 1024, "CS needs V_small [1024,1024], img_dim % 32, 1 <= cs_size <= 1024");
+      V_ = upload(owned_, v_small, (size_t)1024 * 1024);
+      cs_size_ = ratio;
+      M_ = (long long)C_ * (D_ / 32) * (D_ / 32) * cs_size_;
+      break;
+    }
     case OP_DEBLUR:
     case OP_DEBLUR2D: {
       if (kind == OP_DEBLUR) DDNM_CHECK(singulars_orig != nullptr, "Deblurring needs the un-thresholded singulars");
@@ -675,6 +699,7 @@ void Operator::sandwich(const float* L, int lr, int lc, const float* X, int B, c
 }
 
 void Operator::deblur_A(const float* x, int B, float* y, cudaStream_t s) {
+  if (kind_ == OP_CS) return cs_A(x, B, y, s);
   const int n2 = D_ * D_;
   const long long n = (long long)B * C_ * n2;
   if (kind_ == OP_DEBLUR || kind_ == OP_DEBLUR2D) {
@@ -697,6 +722,7 @@ void Operator::deblur_A(const float* x, int B, float* y, cudaStream_t s) {
 }
 
 void Operator::deblur_Apinv(const float* y, int B, float* x, cudaStream_t s) {
+  if (kind_ == OP_CS) return cs_Apinv(y, B, x, s);
   const int n2 = D_ * D_;
   const long long n = (long long)B * C_ * n2;
   if (kind_ == OP_DEBLUR || kind_ == OP_DEBLUR2D) {
@@ -721,9 +747,31 @@ void Operator::deblur_Apinv(const float* y, int B, float* x, cudaStream_t s) {
   CUDA_CHECK(cudaGetLastError());
 }
 
+void Operator::cs_A(const float* x, int B, float* y, cudaStream_t s) {
+  const long long n = (long long)B * C_ * D_ * D_;
+  const int rows = (int)(n / 1024);
+  float* P = scratch(0, n);
+  cs_patch_kernel<true><<<blocks(n), 256, 0, s>>>(x, P, B, C_, D_);
+  // first cs_size coefficients of V^T patch  ==  P [rows x 1024] . V[:, :cs]
+  sgemm_batched(false, 1, 1, rows, cs_size_, 1024, 1.0f, P, 1024, 0, 0, V_, 1024, 0, 0, y, cs_size_, 0, 0, s);
+}
+void Operator::cs_Apinv(const float* y, int B, float* x, cudaStream_t s) {
+  const long long n = (long long)B * C_ * D_ * D_;
+  const int rows = (int)(n / 1024);
+  float* P = scratch(0, n);
+  // V (c, 0, ..)  ==  Y [rows x cs] . V[:, :cs]^T
+  sgemm_batched(true, 1, 1, rows, 1024, cs_size_, 1.0f, y, cs_size_, 0, 0, V_, 1024, 0, 0, P, 1024, 0, 0, s);
+  cs_patch_kernel<false><<<blocks(n), 256, 0, s>>>(P, x, B, C_, D_);
+}
+
 void Operator::A(const float* x, int B, float* y, cudaStream_t s) {
   StepScalars sc{};
   const int n2 = D_ * D_;
+  if (kind_ == OP_CS) {
+    cs_A(x, B, y, s);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   if (kind_ == OP_DENOISE) {
     CUDA_CHECK(cudaMemcpyAsync(y, x, (size_t)B * C_ * n2 * 4, cudaMemcpyDeviceToDevice, s));
     return;
@@ -751,6 +799,11 @@ void Operator::A(const float* x, int B, float* y, cudaStream_t s) {
 void Operator::A_pinv(const float* y, int B, float* x, cudaStream_t s) {
   StepScalars sc{};
   const int n2 = D_ * D_;
+  if (kind_ == OP_CS) {
+    cs_Apinv(y, B, x, s);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   if (kind_ == OP_DENOISE) {
     CUDA_CHECK(cudaMemcpyAsync(x, y, (size_t)B * C_ * n2 * 4, cudaMemcpyDeviceToDevice, s));
     return;
@@ -822,6 +875,7 @@ void Operator::lambda(const float* v, int B, const PlusScalars& ps, float* out, 
     return;
   }
   if (kind_ == OP_DEBLUR2D) throw Error("Deblurring2D defines no Lambda (svd_operators.py:1094-1166): sigma_y > 0 is unsupported, as in the reference");
+  if (kind_ == OP_CS) throw Error("CS defines no Lambda (svd_operators.py:101-159): sigma_y > 0 is unsupported, as in the reference");
   switch (kind_) {
     case OP_SR: case OP_COLOR:
       local_dispatch<LF_LAMBDA>(kind_, ratio_, v, nullptr, 0, nullptr, nullptr, V_, u00_, s0_, sc, out, nullptr, B, C_, D_, s);
@@ -863,6 +917,7 @@ void Operator::lambda_noise(const float* v, const float* eps, int B, const PlusS
     return;
   }
   if (kind_ == OP_DEBLUR2D) throw Error("Deblurring2D defines no Lambda_noise (svd_operators.py:1094-1166)");
+  if (kind_ == OP_CS) throw Error("CS defines no Lambda_noise (svd_operators.py:101-159)");
   switch (kind_) {
     case OP_SR: case OP_COLOR:
       local_dispatch<LF_NOISE>(kind_, ratio_, v, eps, img, nullptr, nullptr, V_, u00_, s0_, sc, out, nullptr, B, C_, D_, s);

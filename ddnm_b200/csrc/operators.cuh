@@ -7,7 +7,7 @@
 
 namespace ddnm {
 
-enum OpKind : int { OP_SR = 0, OP_COLOR = 1, OP_INPAINT = 2, OP_WH = 3, OP_DEBLUR = 4, OP_SRCONV = 5, OP_DENOISE = 6, OP_DEBLUR2D = 7 };
+enum OpKind : int { OP_SR = 0, OP_COLOR = 1, OP_INPAINT = 2, OP_WH = 3, OP_DEBLUR = 4, OP_SRCONV = 5, OP_DENOISE = 6, OP_DEBLUR2D = 7, OP_CS = 8 };
 
 // scalars of one DDNM+ step (svd_ddnm.py:119-131); all fp32 exactly as the reference's 0-dim tensors / casts
 struct PlusScalars {
@@ -53,6 +53,9 @@ class Operator {
   void deblur_A(const float* x, int B, float* y, cudaStream_t s);
   void deblur_Apinv(const float* y, int B, float* x, cudaStream_t s);
 
+  void cs_A(const float* x, int B, float* y, cudaStream_t s);
+  void cs_Apinv(const float* y, int B, float* x, cudaStream_t s);
+  int cs_size_ = 0;
   int kind_, C_, D_, ratio_;
   long long M_ = 0;
   // device artefacts

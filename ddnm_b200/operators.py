@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-KIND = dict(sr=0, color=1, inpaint=2, wh=3, deblur=4, srconv=5, denoise=6, deblur2d=7)
+KIND = dict(sr=0, color=1, inpaint=2, wh=3, deblur=4, srconv=5, denoise=6, deblur2d=7, cs=8)
 
 
 def _host_f32(t):
@@ -237,6 +237,27 @@ class Deblurring2D(_Operator):
         self.U_small1, self.V_small1, self.U_small2, self.V_small2, self._singulars, self._perm = artefacts
         self._create("deblur2d", channels, img_dim, 1, self.V_small1, self.U_small1, self._singulars, None, self._perm,
                      v_small2=self.V_small2, u_small2=self.U_small2)
+
+    def Lambda(self, *a, **k):
+        raise NotImplementedError()
+
+    def Lambda_noise(self, *a, **k):
+        raise NotImplementedError()
+
+
+class CS(_Operator):
+    """svd_operators.py:101-159 — ``CS(channels, img_dim, ratio, device)`` (cs_blockbased).  The 1024x1024 basis is the V of
+    an SVD of ``torch.randn`` drawn from the global RNG, exactly as the reference constructor does.  No Lambda."""
+
+    def __init__(self, channels, img_dim, ratio, device, artefacts=None):
+        if artefacts is None:
+            A = torch.randn(32 ** 2, 32 ** 2).to(device)
+            _, _, V = torch.svd(A, some=False)
+        else:
+            V = artefacts
+        self.V_small = V
+        self.cs_size = int(32 * 32 * ratio)
+        self._create("cs", channels, img_dim, self.cs_size, self.V_small)
 
     def Lambda(self, *a, **k):
         raise NotImplementedError()

@@ -72,7 +72,8 @@ int ddnm_unet_destroy(void* handle);
  * Degradation operators: functions/svd_operators.py A_functions contract (:52-97):
  * A, A_pinv, Lambda, Lambda_noise, plus the fused projection x0 - A^+(A x0 - y) of svd_ddnm.py:59-61.
  * kind: 0 SuperResolution(:479) 1 Colorization(:627) 2 Inpainting(:324) 3 WalshHadamardCS(:211)
- *       4 Deblurring(:934) 5 SRConv(:851) 6 Denoising(:442) 7 Deblurring2D(:1094).
+ *       4 Deblurring(:934) 5 SRConv(:851) 6 Denoising(:442) 7 Deblurring2D(:1094) 8 CS(:101; `ratio` = cs_size,
+ *       v_small = the 1024x1024 basis).
  * Artefacts (V_small, perm, mask, singular tables) are inputs.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {

@@ -206,6 +206,12 @@ def build_ops(dim, rng):
     ops.append(("bicubic", r, O.SRConv(3, dim, 4, r.U_small, r.singulars_small, r.V_small),
                 dict(U_small=r.U_small, singulars_small=r.singulars_small, V_small=r.V_small)))
     ops.append(("denoise", R.Denoising(3, dim, "cpu"), O.Denoising(3, dim), dict()))
+    grng = torch.random.get_rng_state()
+    r = R.CS(3, dim, 0.25, "cpu")                     # its random basis is replaced by a machine-independent orthonormal one
+    torch.random.set_rng_state(grng)
+    r.V_small = O.hadamard_basis()
+    r.Vt_small = r.V_small.transpose(0, 1)
+    ops.append(("cs", r, O.CS(3, dim, 0.25, r.V_small), dict()))
     k1, k2 = aniso_kernels()
     r = R.Deblurring2D(k1, k2, 3, dim, "cpu")
     ops.append(("deblur2d", r, O.Deblurring2D(3, dim, r.U_small1, r.V_small1, r.U_small2, r.V_small2, r._singulars, r._perm),
@@ -251,7 +257,7 @@ def operator_fixtures():
             out[f"{tag}_{name}_A"] = sub(y).numpy()
             out[f"{tag}_{name}_Apinv"] = sub(pin).numpy()
             out[f"{tag}_{name}_proj"] = sub(proj).numpy()
-            if name not in ("bicubic", "deblur2d"):
+            if name not in ("bicubic", "deblur2d", "cs"):
                 for ci, (a, sy, st) in enumerate(LAMBDA_CASES):
                     at, stt = torch.tensor(a), torch.tensor(st)
                     L = r.Lambda(v.clone(), at, sy, stt, 0.85)

@@ -455,3 +455,44 @@ class Deblurring2D(OracleOperator):
 
     def Lambda_noise(self, *args):
         raise NotImplementedError()
+
+
+class CS(OracleOperator):
+    """svd_operators.py:101-159 (cs_blockbased): per 32x32 patch keep the first ``cs_size`` coefficients in the orthonormal
+    basis ``V_small`` (1024 x 1024; the reference draws it as the V of an SVD of torch.randn); U = I, singulars = 1; no Lambda."""
+
+    def __init__(self, channels, img_dim, ratio, V_small):
+        self.channels, self.img_dim, self.V_small = channels, img_dim, V_small
+        self.y_dim, self.p = img_dim // 32, 32
+        self.cs_size = int(32 * 32 * ratio)
+
+    def _patches(self, v):   # (B, C, y*y, 1024), row-major inside the patch (unfold order, :136-138)
+        yd, p = self.y_dim, self.p
+        x = self._img(v).reshape(-1, self.channels, yd, p, yd, p).permute(0, 1, 2, 4, 3, 5)
+        return x.reshape(-1, self.channels, yd * yd, p * p)
+
+    def A(self, v):
+        spec = self._patches(v) @ self.V_small                      # row form of Vt_small @ patch
+        return spec[..., : self.cs_size].reshape(v.shape[0], -1)
+
+    def A_pinv(self, y):
+        yd, p = self.y_dim, self.p
+        c = y.reshape(y.shape[0], self.channels, yd * yd, self.cs_size)
+        patches = c @ self.V_small[:, : self.cs_size].t()            # V_small @ (c, 0, ..)
+        x = patches.reshape(-1, self.channels, yd, yd, p, p).permute(0, 1, 2, 4, 3, 5)
+        return x.reshape(y.shape[0], -1)
+
+    def Lambda(self, *args):
+        raise NotImplementedError()
+
+    def Lambda_noise(self, *args):
+        raise NotImplementedError()
+
+
+def hadamard_basis(n=1024):
+    """A reproducible orthonormal 1024 x 1024 basis (Sylvester Hadamard / sqrt(n), exactly representable) used where tests
+    need the SAME ``V_small`` on every machine; the reference draws its own from the global RNG."""
+    H = torch.ones(1, 1)
+    while H.shape[0] < n:
+        H = torch.cat([torch.cat([H, H], 1), torch.cat([H, -H], 1)], 0)
+    return H / (n ** 0.5)

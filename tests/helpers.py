@@ -58,6 +58,7 @@ def oracle_ops(gold_ops, dim=32):
         ops["bicubic"] = O.SRConv.make(O.SRConv.bicubic_kernel(4), 3, dim, 4)
     ops["wh"] = O.WalshHadamardCS(3, dim, 4, art(gold_ops, tag, "wh", "perm"))
     ops["denoise"] = O.Denoising(3, dim)
+    ops["cs"] = O.CS(3, dim, 0.25, O.hadamard_basis())
     return ops
 
 
@@ -80,6 +81,8 @@ def engine_op(name, oop, dim, device="cuda"):
         return E.SRConv(None, 3, dim, device, stride=4, artefacts=(oop.U_small, oop.S_small, oop.V_small))
     if name == "denoise":
         return E.Denoising(3, dim, device)
+    if name == "cs":
+        return E.CS(3, dim, 0.25, device, artefacts=oop.V_small)
     if name == "deblur2d":
         return E.Deblurring2D(None, None, 3, dim, device, artefacts=(oop.U1, oop.V1, oop.U2, oop.V2, oop.S, oop.perm))
     raise KeyError(name)

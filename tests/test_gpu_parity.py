@@ -256,7 +256,7 @@ def test_operators_vs_oracle_and_golden(gold, dim):
         if golden:
             assert_close(sub(ye), g[f"{tag}_{name}_A"], 1e-4, 1e-5, f"{name} A vs reference")
             assert_close(sub(eop.project(xd, yq.to(dev))), g[f"{tag}_{name}_proj"], 1e-4, 2e-5, f"{name} project vs reference")
-        if name in ("bicubic", "deblur2d"):
+        if name in ("bicubic", "deblur2d", "cs"):
             with pytest.raises(NotImplementedError):
                 eop.Lambda(vd, 0.9, 0.1, 0.3, 0.85)
             continue
