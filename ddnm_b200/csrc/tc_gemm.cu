@@ -27,8 +27,7 @@ struct TcCfg {
   static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
   static constexpr int B_PLANE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
-  static constexpr int PART_BYTES = 2 * 4 * BN * 2 * 4;  // [acc stage][epilogue warp][column][sum, sumsq] fp32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + PART_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -48,13 +47,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  float* part = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));  // GroupNorm partial sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int KB = p.kb0 + p.kb1;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles;
+  // each CTA owns a CONTIGUOUS range of tiles: neighbouring tiles (shared halo rows, same image) run back to back on one SM and
+  // the GroupNorm sums of an image can be kept in registers across tiles
+  const int tiles_per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile_begin = blockIdx.x * tiles_per_cta;
+  const int tile_end = min(total_tiles, tile_begin + tiles_per_cta);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a0h);
@@ -97,7 +100,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     // ------------------------------------------------ TMA producer ------------------------------------------------
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         int n_idx, x0, y0, n0;
         decode(tile, n_idx, x0, y0, n0);
         const int bz = p.b_batched == 1 ? n0 : 0;
@@ -146,7 +149,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       const uint64_t hi = (uint64_t)p.desc_hi << 32;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -187,7 +190,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     const int yi = (r / p.bw) % p.bh;
     const int ni = r / (p.bw * p.bh);
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    float run_s[BN / 32], run_q[BN / 32];
+#pragma unroll
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      run_s[ch] = 0.f;
+      run_q[ch] = 0.f;
+    }
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
       int n_idx, x0, y0, n0;
       decode(tile, n_idx, x0, y0, n0);
       const int n = n0 + ni;
@@ -269,34 +278,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
               sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, k);
             }
           }
-          float* pw = part + (((size_t)acc * 4 + ew) * BN + c0 + lane) * 2;
-          pw[0] = ov[0];
-          pw[1] = sq[0];
+          run_s[c0 >> 5] += ov[0];
+          run_q[c0 >> 5] += sq[0];
         }
       }
       if (p.stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps: partial sums of this tile are in smem
-        const int rows_per_img = p.bw * p.bh;
-        for (int col = r; col < BN; col += 128) {
-          const float* pc = part + ((size_t)acc * 4 * BN + col) * 2;
-          if (rows_per_img >= 128) {  // whole tile belongs to image n0
-            const float s = (pc[0] + pc[2 * BN]) + (pc[4 * BN] + pc[6 * BN]);
-            const float q = (pc[1] + pc[2 * BN + 1]) + (pc[4 * BN + 1] + pc[6 * BN + 1]);
-            if (n0 < p.N) {
-              double* d = p.stats + ((size_t)n0 * p.st_ld + n_idx * BN + col) * 2;
-              atomicAdd(d, (double)s);
-              atomicAdd(d + 1, (double)q);
-            }
-          } else {  // 64 or 32 pixels per image: each warp's rows lie in one image
+        // the warp's 32 rows lie in one image (>= 32 pixels per image): keep running sums while consecutive tiles stay in
+        // the same image / channel block, flush with one atomic pair per column otherwise
+        const int img_w = n0 + (ew * 32) / (p.bw * p.bh);
+        int next_img = -1, next_nidx = -1;
+        if (tile + 1 < tile_end) {
+          int nx0, ny0, nn0;
+          decode(tile + 1, next_nidx, nx0, ny0, nn0);
+          next_img = nn0 + (ew * 32) / (p.bw * p.bh);
+        }
+        if (next_img != img_w || next_nidx != n_idx) {
+          if (img_w < p.N) {
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              const int nw = n0 + (w * 32) / rows_per_img;
-              if (nw < p.N) {
-                double* d = p.stats + ((size_t)nw * p.st_ld + n_idx * BN + col) * 2;
-                atomicAdd(d, (double)pc[2 * BN * w]);
-                atomicAdd(d + 1, (double)pc[2 * BN * w + 1]);
-              }
+            for (int ch = 0; ch < BN / 32; ++ch) {
+              double* d = p.stats + ((size_t)img_w * p.st_ld + n_idx * BN + ch * 32 + lane) * 2;
+              atomicAdd(d, (double)run_s[ch]);
+              atomicAdd(d + 1, (double)run_q[ch]);
             }
+          }
+#pragma unroll
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            run_s[ch] = 0.f;
+            run_q[ch] = 0.f;
           }
         }
       }
