@@ -170,10 +170,18 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
   const int p1 = min(HW, p0 + pix_per_cta);
   const float* src = x + ((size_t)n * HW + p0 + prow) * ld + c;
   const size_t step = (size_t)rows * ld;
+  // software-pipelined: the next pixel's 32 bytes are already in flight while this one is converted and stored
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (p0 + prow < p1) {
+    a = __ldg(reinterpret_cast<const float4*>(src));
+    b = __ldg(reinterpret_cast<const float4*>(src + 4));
+  }
   for (int p = p0 + prow; p < p1; p += rows, src += step) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
     float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (p + rows < p1) {
+      a = __ldg(reinterpret_cast<const float4*>(src + step));
+      b = __ldg(reinterpret_cast<const float4*>(src + step + 4));
+    }
     if (!F32OUT && raw_hi) {  // second output: the un-normalised tensor (input of the 1x1 shortcut convolution)
       __align__(16) __half rh[8];
       __align__(16) __half rl[8];

@@ -55,9 +55,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
   const int total_tiles = m_tiles * p.n_tiles;
   // each CTA owns a CONTIGUOUS range of tiles: neighbouring tiles (shared halo rows, same image) run back to back on one SM and
   // the GroupNorm sums of an image can be kept in registers across tiles
-  const int tiles_per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
-  const int tile_begin = blockIdx.x * tiles_per_cta;
-  const int tile_end = min(total_tiles, tile_begin + tiles_per_cta);
+  const int tiles_base = total_tiles / gridDim.x, tiles_rem = total_tiles % gridDim.x;
+  const int tile_begin = blockIdx.x * tiles_base + min((int)blockIdx.x, tiles_rem);
+  const int tile_end = tile_begin + tiles_base + ((int)blockIdx.x < tiles_rem ? 1 : 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a0h);
