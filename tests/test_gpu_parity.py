@@ -398,3 +398,22 @@ def test_simplified_ddnm_plus_vs_reference_runner(gold, case):
                                  noise=torch.stack(tape).to(dev))
     img = torch.clamp((xs[0] + 1.0) / 2.0, 0.0, 1.0)
     assert_close(img[:, :, ::4, ::4], g[f"{deg}_s{scale}_sy{sy}_T{T}_l{tl}_r{tr}_img_s4"], 1e-3, 5e-4, f"simplified {deg} vs reference runner")
+
+
+def test_sampler_full_size_data_consistency(gold):
+    """Size-independent property at the real 256x256 size: with sigma_y = 0 the last step has alpha-bar = 1, so the
+    returned image is exactly the projection x0_hat and must reproduce the measurement, A(x_0) = y (svd_ddnm.py:57-65)."""
+    from ddnm_b200.sampler import ddnm_diffusion
+    cfg = U.SimpleUNetConfig.celeba_hq()
+    m = _engine_model(cfg)
+    g = torch.Generator().manual_seed(77)
+    B = 2
+    x_orig = (torch.rand(B, 3, 256, 256, generator=g) * 2 - 1).to(dev)
+    x_T = torch.randn(B, 3, 256, 256, generator=g).to(dev)
+    betas = SCH.linear_betas().to(dev)
+    for name, o in oracle_ops(gold["operators"], 256).items():
+        eop = engine_op(name, o, 256)
+        y = eop.A(x_orig)
+        xs, x0s = ddnm_diffusion(x_T, m, betas, 0.85, eop, y, config=sampler_config(4, 1, 1))
+        assert torch.isfinite(xs[0]).all(), name
+        assert_close(eop.A(xs[0].to(dev)), y, 1e-3, 5e-4, f"{name}: A(x_0) = y at 256x256")
