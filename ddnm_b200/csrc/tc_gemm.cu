@@ -12,7 +12,7 @@
 //   guided_diffusion/models.py:77-189 (ResnetBlock, AttnBlock), :36-74 (Up/Downsample)
 // which the reference dispatches to cuDNN / cuBLAS.
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 UMMA issuer (+TMEM owner), warps 2-5 epilogue (TMEM -> regs -> HBM).
+// CTA = 10 warps: warp 0 TMA producer, warp 1 UMMA issuer (+TMEM owner), warps 2-9 epilogue (TMEM -> regs -> HBM).
 // Persistent over output tiles; two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "tc_gemm.cuh"
 
@@ -32,7 +32,7 @@ struct TcCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant__ CUtensorMap tm_a0l,
                const __grid_constant__ CUtensorMap tm_a1h, const __grid_constant__ CUtensorMap tm_a1l,
                const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bl, const TcParams p) {
@@ -53,11 +53,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
   const int KB = p.kb0 + p.kb1;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles;
-  // each CTA owns a CONTIGUOUS range of tiles: neighbouring tiles (shared halo rows, same image) run back to back on one SM and
-  // the GroupNorm sums of an image can be kept in registers across tiles
-  const int tiles_base = total_tiles / gridDim.x, tiles_rem = total_tiles % gridDim.x;
-  const int tile_begin = blockIdx.x * tiles_base + min((int)blockIdx.x, tiles_rem);
-  const int tile_end = tile_begin + tiles_base + ((int)blockIdx.x < tiles_rem ? 1 : 0);
+  // tiles are dealt round-robin: at any moment the 148 CTAs work on 148 consecutive tiles (adjacent rows of one image), which
+  // keeps their shared halo rows and the DRAM stream together (a contiguous range per CTA measured ~4 % slower)
+  const int tile_begin = blockIdx.x, tile_end = total_tiles, tile_step = gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a0h);
@@ -74,7 +72,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 256);
     }
     mbar_fence_init();
   }
@@ -100,7 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     // ------------------------------------------------ TMA producer ------------------------------------------------
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         int n_idx, x0, y0, n0;
         decode(tile, n_idx, x0, y0, n0);
         const int bz = p.b_batched == 1 ? n0 : 0;
@@ -149,7 +147,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       const uint64_t hi = (uint64_t)p.desc_hi << 32;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -184,19 +182,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     }
   } else {
     // ------------------------------------------------ epilogue ----------------------------------------------------
-    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    // 8 epilogue warps: warp w may touch TMEM lanes 32*(w%4)..+31; the two warps sharing a lane quarter split the columns
+    const int ew = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    constexpr int CW = BN / 2;  // columns per epilogue warp
     const int r = ew * 32 + lane;
     const int xi = r % p.bw;
     const int yi = (r / p.bw) % p.bh;
     const int ni = r / (p.bw * p.bh);
     uint32_t acc = 0, acc_phase = 0;
-    float run_s[BN / 32], run_q[BN / 32];
+    float run_s[CW / 32], run_q[CW / 32];
 #pragma unroll
-    for (int ch = 0; ch < BN / 32; ++ch) {
+    for (int ch = 0; ch < CW / 32; ++ch) {
       run_s[ch] = 0.f;
       run_q[ch] = 0.f;
     }
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       int n_idx, x0, y0, n0;
       decode(tile, n_idx, x0, y0, n0);
       const int n = n0 + ni;
@@ -225,7 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chalf * CW; c0 < (chalf + 1) * CW; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(t0 + c0, v);
         tmem_ld_wait();
@@ -278,8 +279,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
               sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, k);
             }
           }
-          run_s[c0 >> 5] += ov[0];
-          run_q[c0 >> 5] += sq[0];
+          run_s[(c0 - chalf * CW) >> 5] += ov[0];
+          run_q[(c0 - chalf * CW) >> 5] += sq[0];
         }
       }
       if (p.stats) {
@@ -287,22 +288,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
         // the same image / channel block, flush with one atomic pair per column otherwise
         const int img_w = n0 + (ew * 32) / (p.bw * p.bh);
         int next_img = -1, next_nidx = -1;
-        if (tile + 1 < tile_end) {
+        if (tile + tile_step < tile_end) {
           int nx0, ny0, nn0;
-          decode(tile + 1, next_nidx, nx0, ny0, nn0);
+          decode(tile + tile_step, next_nidx, nx0, ny0, nn0);
           next_img = nn0 + (ew * 32) / (p.bw * p.bh);
         }
         if (next_img != img_w || next_nidx != n_idx) {
           if (img_w < p.N) {
 #pragma unroll
-            for (int ch = 0; ch < BN / 32; ++ch) {
-              double* d = p.stats + ((size_t)img_w * p.st_ld + n_idx * BN + ch * 32 + lane) * 2;
+            for (int ch = 0; ch < CW / 32; ++ch) {
+              double* d = p.stats + ((size_t)img_w * p.st_ld + n_idx * BN + chalf * CW + ch * 32 + lane) * 2;
               atomicAdd(d, (double)run_s[ch]);
               atomicAdd(d + 1, (double)run_q[ch]);
             }
           }
 #pragma unroll
-          for (int ch = 0; ch < BN / 32; ++ch) {
+          for (int ch = 0; ch < CW / 32; ++ch) {
             run_s[ch] = 0.f;
             run_q[ch] = 0.f;
           }
@@ -510,7 +511,7 @@ static void launch_bn(const TcLaunch& L, cudaStream_t stream) {
     CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  conv_tc_kernel<BN><<<L.grid, 192, TcCfg<BN>::SMEM_BYTES, stream>>>(L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.p);
+  conv_tc_kernel<BN><<<L.grid, 320, TcCfg<BN>::SMEM_BYTES, stream>>>(L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.p);
   CUDA_CHECK(cudaGetLastError());
 }
 
