@@ -227,40 +227,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
       const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c0 = chalf * CW; c0 < (chalf + 1) * CW; c0 += 32) {
+        // operands of the epilogue first (all loads in flight together, none ordered behind a store), then the accumulators
+        float4 cv[8], rv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          cv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (valid) {
+          if (crow) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cv[j] = __ldg(reinterpret_cast<const float4*>(crow + c0 + 4 * j));
+          }
+          if (rrow) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = *reinterpret_cast<const float4*>(rrow + c0 + 4 * j);
+            if (p.res_mode == 2) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 q1 = *reinterpret_cast<const float4*>(rrow + r_dx + c0 + 4 * j);
+                const float4 q2 = *reinterpret_cast<const float4*>(rrow + r_dy + c0 + 4 * j);
+                const float4 q3 = *reinterpret_cast<const float4*>(rrow + r_dy + r_dx + c0 + 4 * j);
+                rv[j].x = ((rv[j].x + q1.x) + (q2.x + q3.x)) * 0.25f;
+                rv[j].y = ((rv[j].y + q1.y) + (q2.y + q3.y)) * 0.25f;
+                rv[j].z = ((rv[j].z + q1.z) + (q2.z + q3.z)) * 0.25f;
+                rv[j].w = ((rv[j].w + q1.w) + (q2.w + q3.w)) * 0.25f;
+              }
+            }
+          }
+        }
         uint32_t v[32];
         tmem_ld32(t0 + c0, v);
         tmem_ld_wait();
         float ov[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 8; ++j) {
           float4 o;
-          o.x = p.alpha * __uint_as_float(v[j + 0]);
-          o.y = p.alpha * __uint_as_float(v[j + 1]);
-          o.z = p.alpha * __uint_as_float(v[j + 2]);
-          o.w = p.alpha * __uint_as_float(v[j + 3]);
-          if (valid) {
-            if (crow) {
-              const float4 c = __ldg(reinterpret_cast<const float4*>(crow + c0 + j));
-              o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
-            }
-            if (rrow) {
-              float4 q = *reinterpret_cast<const float4*>(rrow + c0 + j);
-              if (p.res_mode == 2) {
-                const float4 q1 = *reinterpret_cast<const float4*>(rrow + r_dx + c0 + j);
-                const float4 q2 = *reinterpret_cast<const float4*>(rrow + r_dy + c0 + j);
-                const float4 q3 = *reinterpret_cast<const float4*>(rrow + r_dy + r_dx + c0 + j);
-                q.x = ((q.x + q1.x) + (q2.x + q3.x)) * 0.25f;
-                q.y = ((q.y + q1.y) + (q2.y + q3.y)) * 0.25f;
-                q.z = ((q.z + q1.z) + (q2.z + q3.z)) * 0.25f;
-                q.w = ((q.w + q1.w) + (q2.w + q3.w)) * 0.25f;
-              }
-              o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-            }
-            *reinterpret_cast<float4*>(orow + c0 + j) = o;
-          } else {
-            o = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          ov[j + 0] = o.x; ov[j + 1] = o.y; ov[j + 2] = o.z; ov[j + 3] = o.w;
+          o.x = p.alpha * __uint_as_float(v[4 * j + 0]) + cv[j].x + rv[j].x;
+          o.y = p.alpha * __uint_as_float(v[4 * j + 1]) + cv[j].y + rv[j].y;
+          o.z = p.alpha * __uint_as_float(v[4 * j + 2]) + cv[j].z + rv[j].z;
+          o.w = p.alpha * __uint_as_float(v[4 * j + 3]) + cv[j].w + rv[j].w;
+          if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          ov[4 * j + 0] = o.x; ov[4 * j + 1] = o.y; ov[4 * j + 2] = o.z; ov[4 * j + 3] = o.w;
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(orow + c0 + 4 * j) = make_float4(ov[4 * j], ov[4 * j + 1], ov[4 * j + 2], ov[4 * j + 3]);
         }
         if (p.stats) {
           // GroupNorm statistics of the tile: transpose-reduce the 32 rows x 32 columns this warp holds so that lane L
