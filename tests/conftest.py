@@ -14,6 +14,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    """The tests exercise the in-tree libddnm_b200.so; compile it first if this checkout has not been built yet
+    (nvcc cross-compiles sm_100a without a GPU).  On the GPU box the prebuilt library travels with the snapshot."""
+    from ddnm_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import shutil
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            from ddnm_b200 import build as B
+            B.build()
+    return _lib.LIB_PATH
+
+
 @pytest.fixture(scope="session")
 def gold():
     import numpy as np
