@@ -239,18 +239,32 @@ void UNetEngine::emit_stem(const std::string& wname, const View& out) {
   add_op("stem.gn_stats", "gn_stats", 0, (double)out.pixels() * out.C * 4, [=](cudaStream_t s) { gn_stats(out, s); });
 }
 
-// network head: GroupNorm + SiLU + 3x3 conv to out_ch, NCHW result
+// network head: GroupNorm + SiLU + 3x3 conv to out_ch (3 or 6), NCHW result.  The convolution runs on the tensor cores with
+// the output channels zero-padded to one 64-wide N tile (10-20x redundant columns still beat a CUDA-core kernel ~2x), then
+// the out_ch real channels are copied out as NCHW.
 void UNetEngine::emit_head(const std::string& norm, const std::string& conv, const View& fh) {
   DDNM_CHECK(fh.st != nullptr, "head input without statistics");
-  const float *g = P(norm + ".weight", fh.C), *b = P(norm + ".bias", fh.C);
-  const int groups = groups_;
-  const float eps = eps_;
-  const double ab = (double)fh.pixels() * fh.C * 4;
-  const float *w = P(conv + ".weight", (long long)out_ch_ * fh.C * 9), *bo = P(conv + ".bias", out_ch_);
+  DDNM_CHECK(out_ch_ <= 64, "head convolution: out_ch <= 64");
+  SplitView A{splitA_hi_, splitA_lo_};
+  emit_gn_split("head", fh, norm, true, SPLIT_SAME, A);
+  const int ktot = 9 * fh.C;
+  TcWeights w;
+  w.ktot = ktot;
+  w.hi = (__half*)arena_.alloc((size_t)64 * ktot * sizeof(__half));
+  w.lo = (__half*)arena_.alloc((size_t)64 * ktot * sizeof(__half));
+  CUDA_CHECK(cudaMemset(w.hi, 0, (size_t)64 * ktot * sizeof(__half)));
+  CUDA_CHECK(cudaMemset(w.lo, 0, (size_t)64 * ktot * sizeof(__half)));
+  split_conv_weight(P(conv + ".weight", (long long)out_ch_ * fh.C * 9), out_ch_, fh.C, 9, w.hi, w.lo, ktot, 0, 0);
+  std::vector<float> hb(64, 0.f);
+  CUDA_CHECK(cudaMemcpy(hb.data(), P(conv + ".bias", out_ch_), out_ch_ * sizeof(float), cudaMemcpyDeviceToHost));
+  float* bias64 = dev_copy(hb);
+  View o64;
+  o64.N = B_; o64.H = fh.H; o64.W = fh.W; o64.C = 64; o64.ld = 64;
+  o64.p = (float*)arena_.alloc((size_t)B_ * fh.H * fh.W * 64 * sizeof(float));
+  emit_tc("head.conv", A, TAPS_3X3, nullptr, w, 64, o64, bias64, 0, nullptr, 0);
   float* o = out_;
-  const int oc = out_ch_;
-  add_op("head.norm+conv", "head", 2.0 * fh.pixels() * (double)oc * fh.C * 9, ab + (double)fh.pixels() * oc * 4,
-         [=](cudaStream_t s) { head_conv_gn_silu(fh, groups, g, b, eps, w, bo, oc, o, s); });
+  const View real = o64.slice(0, out_ch_);
+  add_op("head.to_nchw", "head", 0, (double)fh.pixels() * (64 + out_ch_) * 4, [=](cudaStream_t s) { nhwc_to_nchw(real, o, s); });
 }
 
 void UNetEngine::set_terms(int t) {
