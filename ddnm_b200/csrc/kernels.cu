@@ -233,6 +233,80 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
   }
 }
 
+// Hot case of the split (same-size output, fp16 planes): one thread = 4 channels, so every warp load is a dense 512-byte
+// segment and every plane store a dense 256-byte segment; two pixels are in flight per thread.
+__global__ void gn_split_same_kernel(const float* __restrict__ x, int HW, int C, int ld, int groups, const double* __restrict__ stats,
+                                     int st_ld, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                     int pix_per_cta, __half* __restrict__ hi, __half* __restrict__ lo, const float* __restrict__ ss,
+                                     int ss_ld, __half* __restrict__ raw_hi, __half* __restrict__ raw_lo) {
+  __shared__ float sc[MAX_C], sh[MAX_C];
+  const int n = blockIdx.y;
+  if (stats) {
+    const int cpg = C / groups;
+    const double cnt = (double)HW * cpg;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / cpg;
+      const double* gs = stats + ((size_t)n * st_ld + (size_t)g * cpg) * 2;
+      double s1 = 0, s2 = 0;
+      for (int j = 0; j < cpg; ++j) {
+        s1 += gs[2 * j];
+        s2 += gs[2 * j + 1];
+      }
+      const double mean = s1 / cnt;
+      double var = s2 / cnt - mean * mean;
+      var = var < 0 ? 0 : var;
+      float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
+      float b = beta[c] - (float)mean * a;
+      if (ss) {
+        const float one_plus = 1.0f + ss[(size_t)n * ss_ld + c];
+        a *= one_plus;
+        b = fmaf(b, one_plus, ss[(size_t)n * ss_ld + C + c]);
+      }
+      sc[c] = a;
+      sh[c] = b;
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      sc[c] = 1.f;
+      sh[c] = 0.f;
+    }
+  }
+  __syncthreads();
+  const int C4 = C >> 2;
+  const int rows = blockDim.x / C4;
+  const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4;
+  if (prow >= rows) return;
+  const int c = c4 * 4;
+  const float4 A = make_float4(sc[c], sc[c + 1], sc[c + 2], sc[c + 3]);
+  const float4 Bv = make_float4(sh[c], sh[c + 1], sh[c + 2], sh[c + 3]);
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  auto emit = [&](int p, float4 v) {
+    const size_t o = ((size_t)n * HW + p) * C + c;
+    __half h[4], l[4];
+    if (raw_hi) {
+      split_f16(v.x, h[0], l[0]); split_f16(v.y, h[1], l[1]); split_f16(v.z, h[2], l[2]); split_f16(v.w, h[3], l[3]);
+      *reinterpret_cast<uint2*>(raw_hi + o) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(raw_lo + o) = *reinterpret_cast<const uint2*>(l);
+    }
+    v.x = fmaf(v.x, A.x, Bv.x); v.y = fmaf(v.y, A.y, Bv.y); v.z = fmaf(v.z, A.z, Bv.z); v.w = fmaf(v.w, A.w, Bv.w);
+    if (silu) { v.x = swishf(v.x); v.y = swishf(v.y); v.z = swishf(v.z); v.w = swishf(v.w); }
+    split_f16(v.x, h[0], l[0]); split_f16(v.y, h[1], l[1]); split_f16(v.z, h[2], l[2]); split_f16(v.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
+  };
+  const float* src = x + ((size_t)n * HW + p0 + prow) * ld + c;
+  const size_t step = (size_t)rows * ld;
+  int p = p0 + prow;
+  for (; p + rows < p1; p += 2 * rows, src += 2 * step) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + step));
+    emit(p, v0);
+    emit(p + rows, v1);
+  }
+  if (p < p1) emit(p, __ldg(reinterpret_cast<const float4*>(src)));
+}
+
 static void gn_apply_launch(const View& x, int groups, bool normalise, const float* gamma, const float* beta, float eps,
                             bool silu, int mode, __half* hi, __half* lo, float* out32, cudaStream_t st, const float* ss, int ss_ld,
                             __half* raw_hi = nullptr, __half* raw_lo = nullptr) {
@@ -249,6 +323,16 @@ static void gn_apply_launch(const View& x, int groups, bool normalise, const flo
   long long want = cdivll((long long)HW * x.N, 148 * 8);
   int ppc = (int)std::max<long long>(rows, cdivll(want, rows) * rows);
   dim3 grid(cdiv(HW, ppc), x.N);
+  if (!out32 && mode == SPLIT_SAME) {
+    const int C4 = x.C / 4;
+    const int rows4 = std::max(1, 256 / C4);
+    const int ppc4 = (int)std::max<long long>(2 * rows4, cdivll(want, 2 * rows4) * 2 * rows4);
+    dim3 grid4(cdiv(HW, ppc4), x.N);
+    gn_split_same_kernel<<<grid4, C4 * rows4, 0, st>>>(x.p, HW, x.C, x.ld, groups, stats, x.st_ld, gamma, beta, eps, silu, ppc4, hi, lo, ss,
+                                                       ss_ld, raw_hi, raw_lo);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   if (out32)
     gn_apply_kernel<true><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, x.st_ld, gamma, beta, eps, silu, mode,
                                                  ppc, nullptr, nullptr, out32, ss, ss_ld, nullptr, nullptr);
@@ -329,145 +413,6 @@ void conv3x3_small_cin(const float* x, int Cin, const float* w, const float* bia
   DDNM_CHECK(out.C % 4 == 0, "stem Cout % 4");
   dim3 grid(cdiv(out.W, 64), cdiv(out.H, 8), out.N * cdiv(out.C, 128));
   conv_small_cin_kernel<3><<<grid, 256, 0, st>>>(x, w, bias, out.p, out.H, out.W, out.C, out.ld);
-  CUDA_CHECK(cudaGetLastError());
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Head: h = nonlinearity(norm_out(h)); conv_out = Conv2d(ch, out_ch, 3, padding=1)  (models.py:338-340), fused:
-// the CTA stages a (2+2) x (32+2) pixel halo tile of the NHWC input in shared memory, applying GroupNorm affine +
-// SiLU on the way in, then 64 pixels x 4 channel-quarters accumulate the 3x3xCin dot products; NCHW result.
-// The input tensor is read from HBM once (halo rows come from L2); no activated copy is ever written.
-// ---------------------------------------------------------------------------------------------------------------
-template <int COUT>
-__global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ x, int ld, int N, int H, int W, int Cin,
-                                                        int groups, const double* __restrict__ stats, int st_ld,
-                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float eps, const float* __restrict__ w, const float* __restrict__ bias,
-                                                        float* __restrict__ out) {
-  constexpr int TW = 32, TH = 2;
-  extern __shared__ float smem[];
-  const int PS = Cin + 4;                                  // padded pixel stride (floats): conflict-free LDS.128
-  float* tile_s = smem;                                    // [(TH+2)*(TW+2)][PS]
-  float* ws = tile_s + (TH + 2) * (TW + 2) * PS;           // [9][COUT][Cin]
-  float* sc = ws + 9 * COUT * Cin;                         // [Cin]
-  float* sh = sc + Cin;                                    // [Cin]
-  float* red = sh + Cin;                                   // [4][64][COUT]
-  const int HW = H * W;
-  // weights -> smem once per (persistent) CTA, transposed to [tap][co][ci]
-  for (int co = 0; co < COUT; ++co)
-    for (int i = threadIdx.x; i < Cin * 9; i += blockDim.x) {
-      const int ci = i / 9, tap = i - ci * 9;
-      ws[(tap * COUT + co) * Cin + ci] = __ldg(&w[(size_t)co * Cin * 9 + i]);
-    }
-  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
-  const int tiles_per_img = tiles_x * tiles_y;
-  const int total = tiles_per_img * N;
-  const int C4 = Cin >> 2;
-  const int pix = threadIdx.x & 63, quarter = threadIdx.x >> 6;
-  const int py = pix >> 5, px = pix & 31;
-  const int cq = Cin >> 2;                                 // channels per quarter
-  int cur_n = -1;
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int n = tile / tiles_per_img;
-    const int tr = tile - n * tiles_per_img;
-    const int y0 = (tr / tiles_x) * TH, x0 = (tr % tiles_x) * TW;
-    __syncthreads();                                       // previous tile fully consumed (tile / red / sc / sh reusable)
-    if (n != cur_n) {
-      cur_n = n;
-      const int cpg = Cin / groups;
-      const double cnt = (double)HW * cpg;
-      for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
-        const int g = c / cpg;
-        const double* gs = stats + ((size_t)n * st_ld + (size_t)g * cpg) * 2;
-        double s1 = 0, s2 = 0;
-        for (int j = 0; j < cpg; ++j) {
-          s1 += gs[2 * j];
-          s2 += gs[2 * j + 1];
-        }
-        const double mean = s1 / cnt;
-        double var = s2 / cnt - mean * mean;
-        var = var < 0 ? 0 : var;
-        const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
-        sc[c] = a;
-        sh[c] = beta[c] - (float)mean * a;
-      }
-      __syncthreads();
-    }
-    for (int i = threadIdx.x; i < (TH + 2) * (TW + 2) * C4; i += blockDim.x) {
-      const int pp = i / C4, c4 = i - pp * C4;
-      const int ty = pp / (TW + 2), tx = pp - ty * (TW + 2);
-      const int gy = y0 + ty - 1, gx = x0 + tx - 1;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);          // zero padding applies AFTER the activation (conv pads its input)
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + gy) * W + gx) * ld + c4 * 4));
-        const int c = c4 * 4;
-        v.x = swishf(fmaf(v.x, sc[c + 0], sh[c + 0]));
-        v.y = swishf(fmaf(v.y, sc[c + 1], sh[c + 1]));
-        v.z = swishf(fmaf(v.z, sc[c + 2], sh[c + 2]));
-        v.w = swishf(fmaf(v.w, sc[c + 3], sh[c + 3]));
-      }
-      *reinterpret_cast<float4*>(tile_s + (size_t)pp * PS + c4 * 4) = v;
-    }
-    __syncthreads();
-    float acc[COUT];
-#pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const float* tp = tile_s + (size_t)((py + tap / 3) * (TW + 2) + px + tap % 3) * PS + quarter * cq;
-      const float* wp = ws + (size_t)tap * COUT * Cin + quarter * cq;
-      for (int c = 0; c < cq; c += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(tp + c);
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) {
-          const float4 ww = *reinterpret_cast<const float4*>(wp + (size_t)co * Cin + c);
-          acc[co] = fmaf(v.x, ww.x, fmaf(v.y, ww.y, fmaf(v.z, ww.z, fmaf(v.w, ww.w, acc[co]))));
-        }
-      }
-    }
-#pragma unroll
-    for (int co = 0; co < COUT; ++co) red[(quarter * 64 + pix) * COUT + co] = acc[co];
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * COUT; i += blockDim.x) {
-      const int p = i & 63, co = i >> 6;
-      const int gy = y0 + (p >> 5), gx = x0 + (p & 31);
-      if (gy < H && gx < W) {
-        const float v = (red[(0 * 64 + p) * COUT + co] + red[(1 * 64 + p) * COUT + co]) +
-                        (red[(2 * 64 + p) * COUT + co] + red[(3 * 64 + p) * COUT + co]) + bias[co];
-        out[(((size_t)n * COUT + co) * H + gy) * W + gx] = v;
-      }
-    }
-  }
-}
-
-void head_conv_gn_silu(const View& x, int groups, const float* gamma, const float* beta, float eps, const float* w,
-                       const float* bias, int Cout, float* out_nchw, cudaStream_t st) {
-  DDNM_CHECK(x.C % 16 == 0 && x.ld % 4 == 0 && x.C % groups == 0 && x.st != nullptr, "head convolution: Cin % 16, stats slot");
-  const double* stats = x.st;
-  const size_t smem = ((size_t)4 * 34 * (x.C + 4) + (size_t)9 * Cout * x.C + 2 * x.C + 4 * 64 * Cout) * sizeof(float);
-  DDNM_CHECK(smem <= 227 * 1024, "head convolution tile does not fit shared memory");
-  const int total_tiles = cdiv(x.W, 32) * cdiv(x.H, 2) * x.N;
-  int dev = 0, sms = 148;
-  CUDA_CHECK(cudaGetDevice(&dev));
-  CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
-  const int grid = std::min(total_tiles, sms * per_sm);    // persistent CTAs: weights / scale tables staged once
-  static size_t smem_set[2] = {0, 0};
-  if (Cout == 3) {
-    if (smem > smem_set[0]) {
-      CUDA_CHECK(cudaFuncSetAttribute(head_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set[0] = smem;
-    }
-    head_conv_kernel<3><<<grid, 256, smem, st>>>(x.p, x.ld, x.N, x.H, x.W, x.C, groups, stats, x.st_ld, gamma, beta, eps, w, bias, out_nchw);
-  } else if (Cout == 6) {
-    if (smem > smem_set[1]) {
-      CUDA_CHECK(cudaFuncSetAttribute(head_conv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set[1] = smem;
-    }
-    head_conv_kernel<6><<<grid, 256, smem, st>>>(x.p, x.ld, x.N, x.H, x.W, x.C, groups, stats, x.st_ld, gamma, beta, eps, w, bias, out_nchw);
-  } else {
-    throw Error("head convolution supports Cout 3 or 6");
-  }
   CUDA_CHECK(cudaGetLastError());
 }
 

@@ -25,11 +25,6 @@ void gn_apply_f32(const View& x, int groups, const float* gamma, const float* be
 
 // 3x3 pad-1 convolution with tiny Cin (the network stem): x NCHW [N,Cin,H,W] fp32, w OIHW, out NHWC view.
 void conv3x3_small_cin(const float* x_nchw, int Cin, const float* w_oihw, const float* bias, const View& out, cudaStream_t s);
-// Network head: GroupNorm affine + SiLU fused into a 3x3 pad-1 convolution with tiny Cout (3 or 6); x NHWC view,
-// stats from gn_stats, out NCHW [N,Cout,H,W].
-void head_conv_gn_silu(const View& x, int groups, const float* gamma, const float* beta, float eps, const float* w_oihw,
-                       const float* bias, int Cout, float* out_nchw, cudaStream_t s);
-
 // out[n][o] = act_out( sum_k act_in(in[n][k]) * W[o][k] + bias[o] );  act: 0 none, 1 swish
 void linear(const float* in, int N, int K, const float* W, const float* bias, int O, float* out, int ldo, int act_in,
             int act_out, cudaStream_t s);
