@@ -369,6 +369,18 @@ def test_sampler_single_steps_teacher_forced(gold):
             assert_close(xs[0], ref, 1e-3, 1e-4 * sc, f"{name} s{sy} step {i}->{j}: xt_next")
 
 
+def test_ddnm_plus_with_lambda_less_operator_raises_like_reference(gold):
+    from ddnm_b200.sampler import ddnm_plus_diffusion
+    cfg = U.SimpleUNetConfig.tiny()
+    m = _engine_model(cfg)
+    oop = oracle_ops(gold["operators"], 32)["bicubic"]
+    eop = engine_op("bicubic", oop, 32)
+    x = torch.randn(2, 3, 32, 32, device=dev)
+    y = eop.A(x)
+    with pytest.raises(NotImplementedError):
+        ddnm_plus_diffusion(x, m, SCH.linear_betas().to(dev), 0.85, eop, y, 0.1, config=sampler_config(4, 1, 1))
+
+
 def test_product_path_has_no_cpu_fallback():
     from ddnm_b200.model import Model
     cfg = U.SimpleUNetConfig.tiny()
