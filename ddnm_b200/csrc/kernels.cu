@@ -233,80 +233,6 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
   }
 }
 
-// Hot case of the split (same-size output, fp16 planes): one thread = 4 channels, so every warp load is a dense 512-byte
-// segment and every plane store a dense 256-byte segment; two pixels are in flight per thread.
-__global__ void gn_split_same_kernel(const float* __restrict__ x, int HW, int C, int ld, int groups, const double* __restrict__ stats,
-                                     int st_ld, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
-                                     int pix_per_cta, __half* __restrict__ hi, __half* __restrict__ lo, const float* __restrict__ ss,
-                                     int ss_ld, __half* __restrict__ raw_hi, __half* __restrict__ raw_lo) {
-  __shared__ float sc[MAX_C], sh[MAX_C];
-  const int n = blockIdx.y;
-  if (stats) {
-    const int cpg = C / groups;
-    const double cnt = (double)HW * cpg;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const int g = c / cpg;
-      const double* gs = stats + ((size_t)n * st_ld + (size_t)g * cpg) * 2;
-      double s1 = 0, s2 = 0;
-      for (int j = 0; j < cpg; ++j) {
-        s1 += gs[2 * j];
-        s2 += gs[2 * j + 1];
-      }
-      const double mean = s1 / cnt;
-      double var = s2 / cnt - mean * mean;
-      var = var < 0 ? 0 : var;
-      float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
-      float b = beta[c] - (float)mean * a;
-      if (ss) {
-        const float one_plus = 1.0f + ss[(size_t)n * ss_ld + c];
-        a *= one_plus;
-        b = fmaf(b, one_plus, ss[(size_t)n * ss_ld + C + c]);
-      }
-      sc[c] = a;
-      sh[c] = b;
-    }
-  } else {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      sc[c] = 1.f;
-      sh[c] = 0.f;
-    }
-  }
-  __syncthreads();
-  const int C4 = C >> 2;
-  const int rows = blockDim.x / C4;
-  const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4;
-  if (prow >= rows) return;
-  const int c = c4 * 4;
-  const float4 A = make_float4(sc[c], sc[c + 1], sc[c + 2], sc[c + 3]);
-  const float4 Bv = make_float4(sh[c], sh[c + 1], sh[c + 2], sh[c + 3]);
-  const int p0 = blockIdx.x * pix_per_cta;
-  const int p1 = min(HW, p0 + pix_per_cta);
-  auto emit = [&](int p, float4 v) {
-    const size_t o = ((size_t)n * HW + p) * C + c;
-    __half h[4], l[4];
-    if (raw_hi) {
-      split_f16(v.x, h[0], l[0]); split_f16(v.y, h[1], l[1]); split_f16(v.z, h[2], l[2]); split_f16(v.w, h[3], l[3]);
-      *reinterpret_cast<uint2*>(raw_hi + o) = *reinterpret_cast<const uint2*>(h);
-      *reinterpret_cast<uint2*>(raw_lo + o) = *reinterpret_cast<const uint2*>(l);
-    }
-    v.x = fmaf(v.x, A.x, Bv.x); v.y = fmaf(v.y, A.y, Bv.y); v.z = fmaf(v.z, A.z, Bv.z); v.w = fmaf(v.w, A.w, Bv.w);
-    if (silu) { v.x = swishf(v.x); v.y = swishf(v.y); v.z = swishf(v.z); v.w = swishf(v.w); }
-    split_f16(v.x, h[0], l[0]); split_f16(v.y, h[1], l[1]); split_f16(v.z, h[2], l[2]); split_f16(v.w, h[3], l[3]);
-    *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
-  };
-  const float* src = x + ((size_t)n * HW + p0 + prow) * ld + c;
-  const size_t step = (size_t)rows * ld;
-  int p = p0 + prow;
-  for (; p + rows < p1; p += 2 * rows, src += 2 * step) {
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
-    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + step));
-    emit(p, v0);
-    emit(p + rows, v1);
-  }
-  if (p < p1) emit(p, __ldg(reinterpret_cast<const float4*>(src)));
-}
-
 static void gn_apply_launch(const View& x, int groups, bool normalise, const float* gamma, const float* beta, float eps,
                             bool silu, int mode, __half* hi, __half* lo, float* out32, cudaStream_t st, const float* ss, int ss_ld,
                             __half* raw_hi = nullptr, __half* raw_lo = nullptr) {
@@ -323,16 +249,6 @@ static void gn_apply_launch(const View& x, int groups, bool normalise, const flo
   long long want = cdivll((long long)HW * x.N, 148 * 8);
   int ppc = (int)std::max<long long>(rows, cdivll(want, rows) * rows);
   dim3 grid(cdiv(HW, ppc), x.N);
-  if (!out32 && mode == SPLIT_SAME) {
-    const int C4 = x.C / 4;
-    const int rows4 = std::max(1, 256 / C4);
-    const int ppc4 = (int)std::max<long long>(2 * rows4, cdivll(want, 2 * rows4) * 2 * rows4);
-    dim3 grid4(cdiv(HW, ppc4), x.N);
-    gn_split_same_kernel<<<grid4, C4 * rows4, 0, st>>>(x.p, HW, x.C, x.ld, groups, stats, x.st_ld, gamma, beta, eps, silu, ppc4, hi, lo, ss,
-                                                       ss_ld, raw_hi, raw_lo);
-    CUDA_CHECK(cudaGetLastError());
-    return;
-  }
   if (out32)
     gn_apply_kernel<true><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, x.st_ld, gamma, beta, eps, silu, mode,
                                                  ppc, nullptr, nullptr, out32, ss, ss_ld, nullptr, nullptr);
