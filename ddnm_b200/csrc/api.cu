@@ -146,13 +146,27 @@ int ddnm_conv_tc(const float* x, int N, int H, int W, int Cin, const float* w, c
   int oH = H, oW = W;
   int smode = SPLIT_SAME;
   if (mode == TAPS_3X3_S2) { oH = H / 2; oW = W / 2; smode = SPLIT_S2D; DDNM_CHECK(!up2, "stride 2 with upsample"); }
-  if (up2) { oH = 2 * H; oW = 2 * W; smode = SPLIT_UP2; }
-  const size_t pe = (size_t)N * H * W * Cin * (up2 ? 4 : 1);
+  if (up2) { oH = 2 * H; oW = 2 * W; DDNM_CHECK(mode == TAPS_3X3 && !side_x && !residual, "upsample path: plain 3x3 only"); }
+  const size_t pe = (size_t)N * H * W * Cin;
   SplitView A;
   A.hi = tmp.get<__half>(pe); A.lo = tmp.get<__half>(pe); A.C = Cin;
-  if (smode == SPLIT_S2D) { A.N = 4 * N; A.H = oH; A.W = oW; } else { A.N = N; A.H = oH; A.W = oW; }
+  if (smode == SPLIT_S2D) { A.N = 4 * N; A.H = oH; A.W = oW; } else { A.N = N; A.H = H; A.W = W; }
   View xv = mkview(const_cast<float*>(x), N, H, W, Cin);
   gn_apply_split(xv, 1, false, nullptr, nullptr, 0.f, false, smode, A.hi, A.lo, s);
+  View ov = mkview(out, N, oH, oW, Cout);
+  if (up2) {
+    // conv3x3(nearest_upsample_x2(x)): four parity-phase 2x2 convolutions on the low-res split (the engine's path)
+    const size_t per_phase = (size_t)Cout * 4 * Cin;
+    __half* wh = tmp.get<__half>(4 * per_phase);
+    __half* wl = tmp.get<__half>(4 * per_phase);
+    presum_up2_weights(w, Cout, Cin, wh, wl, s);
+    for (int ph = 0; ph < 4; ++ph) {
+      TcLaunch L = tc_make_up2_launch(A, wh + ph * per_phase, wl + ph * per_phase, Cout, ov, bias, 0, ph >> 1, ph & 1, sm_count());
+      tc_run(L, s);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    return 0;
+  }
   SplitView S;
   if (side_x) {
     const size_t se = (size_t)N * oH * oW * CinSide;
@@ -165,7 +179,6 @@ int ddnm_conv_tc(const float* x, int N, int H, int W, int Cin, const float* w, c
   __half* wl = tmp.get<__half>((size_t)Cout * ktot);
   split_conv_weight(w, Cout, Cin, taps, wh, wl, ktot, 0, s);
   if (side_x) split_conv_weight(side_w, Cout, CinSide, 1, wh, wl, ktot, taps * Cin, s);
-  View ov = mkview(out, N, oH, oW, Cout);
   TcLaunch L = tc_make_launch(A, mode, side_x ? &S : nullptr, wh, wl, 1, Cout, ov, bias, 0, residual, Cout, 1.0f, sm_count());
   tc_run(L, s);
   CUDA_CHECK(cudaStreamSynchronize(s));

@@ -175,6 +175,20 @@ void UNetEngine::alloc_common(size_t split_elems, size_t hbuf_elems) {
   out_ = (float*)arena_.alloc((size_t)B_ * out_ch_ * R_ * R_ * 4);
 }
 
+void UNetEngine::emit_up2_conv(const std::string& name, const SplitView& a, const std::string& wname, int Cout, const View& out,
+                               const float* chanadd, int ca_ld) {
+  const int Cin = a.C;
+  const size_t per_phase = (size_t)Cout * 4 * Cin;
+  __half* wh = (__half*)arena_.alloc(4 * per_phase * sizeof(__half));
+  __half* wl = (__half*)arena_.alloc(4 * per_phase * sizeof(__half));
+  presum_up2_weights(P(wname, (long long)Cout * Cin * 9), Cout, Cin, wh, wl, 0);
+  for (int ph = 0; ph < 4; ++ph) {
+    TcLaunch L = tc_make_up2_launch(a, wh + ph * per_phase, wl + ph * per_phase, Cout, out, chanadd, ca_ld, ph >> 1, ph & 1, num_sms_);
+    const double bytes = (double)a.N * a.H * a.W * Cin * 4 + (double)per_phase * 4 + (double)a.N * a.H * a.W * Cout * 4;
+    add_op(name + ".ph" + std::to_string(ph), "tc", L.flops, bytes, [L](cudaStream_t s) { tc_run(L, s); });
+  }
+}
+
 void UNetEngine::alloc_attention(size_t qkv_elems, size_t s_elems, size_t o_elems) {
   qkv_ = (float*)arena_.alloc(qkv_elems * 4);
   attS_ = (float*)arena_.alloc(s_elems * 4);

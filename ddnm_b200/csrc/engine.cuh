@@ -105,6 +105,10 @@ class UNetEngine {
   void emit_attention_core(const std::string& name, int T, int heads, int ch, int qkv_ld, int head_stride, int q_off, int k_off,
                            int v_off, float alpha);
   void alloc_attention(size_t qkv_elems, size_t s_elems, size_t o_elems);
+  // conv3x3(nearest_upsample_x2(a)) + bias as 4 parity-phase 2x2 convolutions on the low-res split `a` (4/9 of the MACs,
+  // no upsampled copy); wname: OIHW 3x3 weight parameter
+  void emit_up2_conv(const std::string& name, const SplitView& a, const std::string& wname, int Cout, const View& out,
+                     const float* chanadd, int ca_ld);
   void emit_stem(const std::string& wname, const View& out);
   void emit_head(const std::string& norm, const std::string& conv, const View& h);
   void alloc_common(size_t split_elems, size_t hbuf_elems);

@@ -562,6 +562,35 @@ __global__ void split_weight_kernel(const float* __restrict__ w, int Cout, int C
   hi[o] = h;
   lo[o] = l;
 }
+// Phase weights of conv3x3(nearest_upsample_x2(.)): output parity (py, px) sees a 2x2 stencil on the low-res input whose
+// taps are sums of the 3x3 taps that land on the same source pixel (rows: py=0 -> {0},{1,2}; py=1 -> {0,1},{2}; same for columns).
+// dst[((py*2+px)*Cout + co)*4*Cin + (dy*2+dx)*Cin + ci]
+__global__ void presum_up2_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_phase = (long long)Cout * 4 * Cin;
+  if (i >= 4 * per_phase) return;
+  const int ci = (int)(i % Cin);
+  const int tap = (int)((i / Cin) % 4);
+  const int co = (int)((i / (4LL * Cin)) % Cout);
+  const int ph = (int)(i / per_phase);
+  const int py = ph >> 1, px = ph & 1, dy = tap >> 1, dx = tap & 1;
+  const int r0 = py == 0 ? (dy == 0 ? 0 : 1) : (dy == 0 ? 0 : 2), r1 = py == 0 ? (dy == 0 ? 0 : 2) : (dy == 0 ? 1 : 2);
+  const int c0 = px == 0 ? (dx == 0 ? 0 : 1) : (dx == 0 ? 0 : 2), c1 = px == 0 ? (dx == 0 ? 0 : 2) : (dx == 0 ? 1 : 2);
+  const float* wp = w + ((long long)co * Cin + ci) * 9;
+  float acc = 0.f;
+  for (int r = r0; r <= r1; ++r)
+    for (int c = c0; c <= c1; ++c) acc += wp[r * 3 + c];
+  __half h, l;
+  split_f16(acc, h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+void presum_up2_weights(const float* w_oihw, int Cout, int Cin, __half* hi, __half* lo, cudaStream_t st) {
+  const long long total = 4LL * Cout * 4 * Cin;
+  presum_up2_kernel<<<(int)cdivll(total, 256), 256, 0, st>>>(w_oihw, Cout, Cin, hi, lo);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 void split_conv_weight(const float* w, int Cout, int Cin, int taps, __half* hi, __half* lo, int ktot, int koff, cudaStream_t st) {
   const long long total = (long long)Cout * Cin * taps;
   split_weight_kernel<<<(int)cdivll(total, 256), 256, 0, st>>>(w, Cout, Cin, taps, hi, lo, ktot, koff);

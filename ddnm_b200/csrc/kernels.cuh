@@ -48,6 +48,9 @@ void transpose_split(const float* src, int ld, int head_stride, int off, int ima
 void split_conv_weight(const float* w_oihw, int Cout, int Cin, int taps, __half* hi, __half* lo, int ktot, int koff,
                        cudaStream_t s);
 
+// 4 parity-phase weight matrices [4][Cout][4*Cin] (fp16 hi/lo) of conv3x3(nearest_upsample_x2(.)) from its OIHW 3x3 weight
+void presum_up2_weights(const float* w_oihw, int Cout, int Cin, __half* hi, __half* lo, cudaStream_t s);
+
 // Reference-quality direct convolution on CUDA cores (tests / validation of the tensor-core path only).
 //   mode: TcTapMode; up2: input is nearest-upsampled 2x on the fly.  x, out: NHWC views; w: OIHW.
 void conv_direct_ref(const View& x, const float* w_oihw, const float* bias, int taps_mode, bool up2, const View& out,

@@ -115,6 +115,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
             if (p.mode0 == TAPS_3X3) {
               cy += tap / 3 - 1;
               cx += tap % 3 - 1;
+            } else if (p.mode0 == TAPS_UP2X2) {
+              cy += tap / 2 + p.up_py - 1;
+              cx += tap % 2 + p.up_px - 1;
             } else if (p.mode0 == TAPS_3X3_S2) {
               const int dy = tap / 3, dx = tap % 3;
               cy += dy >> 1;
@@ -394,7 +397,7 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
                         int ldr, float alpha, int num_sms, int res_mode) {
   TcLaunch L;
   TcParams& p = L.p;
-  const int taps = (mode0 == TAPS_1X1) ? 1 : 9;
+  const int taps = (mode0 == TAPS_1X1) ? 1 : (mode0 == TAPS_UP2X2 ? 4 : 9);
   DDNM_CHECK(src0.C % BK == 0, "tensor-core conv needs Cin % 64 == 0");
   DDNM_CHECK(Cout % 64 == 0, "tensor-core conv needs Cout % 64 == 0");
   p.H = out.H; p.W = out.W; p.N = out.N;
@@ -426,6 +429,7 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   p.kb1 = src1 ? src1->C / BK : 0;
   if (src1) DDNM_CHECK(src1->C % BK == 0 && src1->H == out.H && src1->W == out.W && src1->N == out.N, "bad 1x1 side input");
   p.phase_stride = 0;
+  p.up_py = p.up_px = 0;
   p.b_batched = w_batches > 1 ? 1 : 0;
   if (p.b_batched) DDNM_CHECK(p.bn == 1 && w_batches == out.N, "batched B operand needs one image per tile");
   if (mode0 == TAPS_3X3_S2) {
@@ -471,6 +475,23 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   return L;
 }
 
+TcLaunch tc_make_up2_launch(const SplitView& src, const __half* w_hi, const __half* w_lo, int Cout, const View& out, const float* chanadd,
+                            int ca_ld, int py, int px, int num_sms) {
+  DDNM_CHECK(out.H == 2 * src.H && out.W == 2 * src.W && out.N == src.N, "upsample phase: output must be twice the source size");
+  View lr = out;   // tile over the low-res pixel grid; every tile pixel (y, x) lands on output pixel (2y+py, 2x+px)
+  lr.H = src.H;
+  lr.W = src.W;
+  TcLaunch L = tc_make_launch(src, TAPS_UP2X2, nullptr, w_hi, w_lo, 1, Cout, lr, chanadd, ca_ld, nullptr, 0, 1.0f, num_sms, 0);
+  TcParams& p = L.p;
+  p.up_py = py;
+  p.up_px = px;
+  p.out = out.p + ((size_t)py * out.W + px) * out.ld;
+  p.out_sx = 2LL * out.ld;
+  p.out_sy = 2LL * out.W * out.ld;
+  p.out_sn = (long long)out.H * out.W * out.ld;
+  return L;
+}
+
 TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int heads, int images, float* out,
                              long long out_sn, long long out_sy, long long out_sx, float alpha, int num_sms) {
   TcLaunch L;
@@ -491,6 +512,7 @@ TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, 
   p.mode0 = TAPS_1X1;
   p.cb0 = K / BK; p.kb0 = K / BK; p.kb1 = 0;
   p.phase_stride = 0;
+  p.up_py = p.up_px = 0;
   p.b_batched = 2;
   p.Cout = N; p.ldc = (int)out_sx; p.out = out;
   p.out_sn = out_sn; p.out_sy = out_sy; p.out_sx = out_sx;

@@ -9,6 +9,7 @@ enum TcTapMode : int {
   TAPS_3X3 = 0,     // 3x3, stride 1, zero pad 1 (pad comes from TMA out-of-bounds zero fill)
   TAPS_1X1 = 1,     // 1x1 / plain GEMM rows
   TAPS_3X3_S2 = 2,  // 3x3, stride 2, pad (0,1,0,1): source is stored as 4 parity phases (space-to-depth)
+  TAPS_UP2X2 = 3,   // one output parity phase of (nearest x2 upsample -> 3x3 pad 1): a 2x2 stencil on the LOW-res source
 };
 
 struct TcParams {
@@ -20,6 +21,7 @@ struct TcParams {
   int cb0, kb0;                // source 0: 64-channel blocks per tap, total k-blocks (= taps * cb0)
   int kb1;                     // source 1 (always 1x1, e.g. the nin_shortcut input): k-blocks, 0 = absent
   int phase_stride;            // TAPS_3X3_S2: images per parity phase in the source's outer dim
+  int up_py, up_px;            // TAPS_UP2X2: output parity (row, column) this launch produces
   int b_batched;               // 1: B has one matrix per image (3D map, z = image); 2: B is a 4D map sharing the A tile's
                                //    two outer coordinates (attention: y = head, n = image)
   long long out_sn, out_sy, out_sx;  // output element strides per image / row / column of the M tile's pixel grid
@@ -52,6 +54,10 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
                         int w_batches, int Cout, const View& out, const float* chanadd, int ca_ld, const float* residual,
                         int ldr, float alpha, int num_sms, int res_mode = 0);
 void tc_run(const TcLaunch& L, cudaStream_t stream);
+// One parity phase (py, px) of conv3x3(nearest_upsample_x2(src)): src is the LOW-res split, w_* the phase's pre-summed
+// [Cout][4*Cin] weights (see presum_up2_weights), out the FULL-res view; writes out[:, 2y+py, 2x+px, :].
+TcLaunch tc_make_up2_launch(const SplitView& src, const __half* w_hi, const __half* w_lo, int Cout, const View& out, const float* chanadd,
+                            int ca_ld, int py, int px, int num_sms);
 
 // Strided fp16 (hi, lo) operand for the batched-GEMM builder: element (k, row, head, image) at
 // base[k + row*s_row + head*s_head + image*s_img]; k extent = K (multiple of 64).

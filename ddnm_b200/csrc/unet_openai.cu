@@ -20,14 +20,19 @@ void UNetOpenAI::emit_resblock(const std::string& p, const View& x, const View& 
   DDNM_CHECK((size_t)(out.pixels() * Cout) <= hbuf_elems_, "hbuf too small");
   if (kind != RES_PLAIN) DDNM_CHECK(Cin == Cout, "up/down ResBlocks keep the channel count");
   SplitView A{splitA_hi_, splitA_lo_}, Bs{splitB_hi_, splitB_lo_};
-  const int mode1 = kind == RES_DOWN ? SPLIT_AVG2 : (kind == RES_UP ? SPLIT_UP2 : SPLIT_SAME);
+  const int mode1 = kind == RES_DOWN ? SPLIT_AVG2 : SPLIT_SAME;
   const bool has_skip_conv = has_param(p + ".skip_connection.weight");
   emit_gn_split(p + ".in", x, p + ".in_layers.0", true, mode1, A, nullptr, 0, has_skip_conv ? &Bs : nullptr);
-  TcWeights w1 = prep_weights(p + ".in_layers.2.weight", Cout, Cin, 9, "", 0);
   View h;
   h.p = hbuf_; h.N = B_; h.H = out.H; h.W = out.W; h.C = Cout; h.ld = Cout;
   h.st = new_stats(Cout); h.st_ld = Cout;   // conv1's epilogue accumulates the sums out_layers.0 needs
-  emit_tc(p + ".conv1", A, TAPS_3X3, nullptr, w1, Cout, h, P(p + ".in_layers.2.bias", Cout), 0, nullptr, 0);
+  if (kind == RES_UP) {
+    // in_conv(nearest_up(SiLU(GN(x)))) as four 2x2 parity-phase convolutions on the low-res activation
+    emit_up2_conv(p + ".conv1", A, p + ".in_layers.2.weight", Cout, h, P(p + ".in_layers.2.bias", Cout), 0);
+  } else {
+    TcWeights w1 = prep_weights(p + ".in_layers.2.weight", Cout, Cin, 9, "", 0);
+    emit_tc(p + ".conv1", A, TAPS_3X3, nullptr, w1, Cout, h, P(p + ".in_layers.2.bias", Cout), 0, nullptr, 0);
+  }
   // out_norm(h) * (1 + scale) + shift -> SiLU -> conv  (:250-253); scale|shift = emb_layers(emb) computed once per forward
   emit_gn_split(p + ".out", h, p + ".out_layers.0", true, SPLIT_SAME, A, ss_all_ + ss_off_.at(p), ss_total_);
   if (has_skip_conv) {

@@ -74,9 +74,8 @@ void UNetSimple::emit_downsample(const std::string& p, const View& x, const View
 // Upsample (models.py:47-52): nearest x2 + 3x3
 void UNetSimple::emit_upsample(const std::string& p, const View& x, const View& out) {
   SplitView A{splitA_hi_, splitA_lo_};
-  emit_gn_split(p + ".up2", x, "", false, SPLIT_UP2, A);
-  TcWeights w = prep_weights(p + ".conv.weight", x.C, x.C, 9, "", 0);
-  emit_tc(p + ".conv", A, TAPS_3X3, nullptr, w, x.C, out, P(p + ".conv.bias", x.C), 0, nullptr, 0);
+  emit_gn_split(p + ".split", x, "", false, SPLIT_SAME, A);
+  emit_up2_conv(p + ".conv", A, p + ".conv.weight", x.C, out, P(p + ".conv.bias", x.C), 0);
 }
 
 void UNetSimple::build_program() {
