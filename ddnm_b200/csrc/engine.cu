@@ -124,11 +124,10 @@ void UNetEngine::add_op(const std::string& name, const std::string& kind, double
 // GroupNorm(+SiLU) + fp16 split of x into scratch planes dst (dims as the consuming convolution sees them)
 void UNetEngine::emit_gn_split(const std::string& name, const View& x, const std::string& norm, bool silu, int mode,
                                SplitView& dst, const float* ss, int ss_ld, SplitView* raw) {
-  const long long out_elems = mode == SPLIT_UP2 ? x.pixels() * x.C * 4 : (mode == SPLIT_AVG2 ? x.pixels() * x.C / 4 : x.pixels() * x.C);
+  const long long out_elems = mode == SPLIT_AVG2 ? x.pixels() * x.C / 4 : x.pixels() * x.C;
   DDNM_CHECK((size_t)out_elems <= split_elems_, "split scratch too small");
   dst.C = x.C;
   if (mode == SPLIT_SAME) { dst.N = x.N; dst.H = x.H; dst.W = x.W; }
-  else if (mode == SPLIT_UP2) { dst.N = x.N; dst.H = 2 * x.H; dst.W = 2 * x.W; }
   else if (mode == SPLIT_AVG2) { dst.N = x.N; dst.H = x.H / 2; dst.W = x.W / 2; }
   else { dst.N = 4 * x.N; dst.H = x.H / 2; dst.W = x.W / 2; }
   const double in_bytes = (double)x.pixels() * x.C * 4;

@@ -82,7 +82,7 @@ void gn_stats(const View& x, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------
 // Normalise (+ SiLU) and split to fp16 hi/lo.  Produces the A operand of the tensor-core convolution, i.e. fuses
 //   h = nonlinearity(norm(x))            models.py:117-118,124-125   (x * sigmoid(x), GN eps 1e-6)
-//   F.interpolate(x, 2, 'nearest')       models.py:48-49   (SPLIT_UP2)
+//   (nearest x2 upsampling needs no copy: the consumer convolution runs as 4 parity phases on this low-res split)
 //   F.pad(x, (0,1,0,1)) + stride 2       models.py:67-71   (SPLIT_S2D: parity phases; pad = TMA zero fill)
 // Each thread converts 8 channels of one pixel: 2 x float4 in, 16 B out per plane.
 // ---------------------------------------------------------------------------------------------------------------
@@ -213,15 +213,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
         *reinterpret_cast<uint4*>(lo + o) = lv;
       } else {
         const int y = p / W, xx = p - y * W;
-        if (mode == SPLIT_UP2) {
-          const int W2 = 2 * W;
-#pragma unroll
-          for (int d = 0; d < 4; ++d) {
-            const size_t o = (((size_t)n * 2 * H + (2 * y + (d >> 1))) * W2 + (2 * xx + (d & 1))) * C + c;
-            *reinterpret_cast<uint4*>(hi + o) = hv;
-            *reinterpret_cast<uint4*>(lo + o) = lv;
-          }
-        } else {  // SPLIT_S2D
+        {  // SPLIT_S2D
           const int ph = (y & 1) * 2 + (xx & 1);
           const int Hh = H >> 1, Wh = W >> 1;
           const size_t o = ((((size_t)ph * N + n) * Hh + (y >> 1)) * Wh + (xx >> 1)) * C + c;

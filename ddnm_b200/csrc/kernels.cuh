@@ -6,13 +6,13 @@
 
 namespace ddnm {
 
-enum SplitMode : int { SPLIT_SAME = 0, SPLIT_UP2 = 1, SPLIT_S2D = 2, SPLIT_AVG2 = 3 };
+enum SplitMode : int { SPLIT_SAME = 0, SPLIT_S2D = 2, SPLIT_AVG2 = 3 };
 
 // Per-channel GroupNorm sums of x into x.st (see View); only for tensors not produced by the tensor-core kernel.
 void gn_stats(const View& x, cudaStream_t s);
 
 // y = [GN affine](x) -> [SiLU] -> fp16 (hi, lo) planes.  normalise == false: raw split; true: uses x.st.
-// mode SPLIT_UP2 writes a nearest-neighbour 2x upsampled plane, SPLIT_S2D writes 4 parity phases
+// mode SPLIT_S2D writes 4 parity phases
 // (plane index = phase*N + n, phase = (y&1)*2 + (x&1)) for the stride-2 convolution, SPLIT_AVG2 writes the 2x2 average
 // pool of the activated tensor (ResBlock(down=True), unet.py:237-241).  ss != nullptr: use_scale_shift_norm —
 // y = GN(x) * (1 + ss[n*ss_ld + c]) + ss[n*ss_ld + C + c]   (unet.py:250-252).
