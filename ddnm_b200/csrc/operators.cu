@@ -518,6 +518,7 @@ Operator::Operator(int kind, int channels, int img_dim, int ratio, const float* 
     : kind_(kind), C_(channels), D_(img_dim), ratio_(ratio) {
   const int n2 = D_ * D_;
   DDNM_CHECK(channels >= 1 && img_dim >= 2, "bad operator geometry");
+  N_ = (long long)C_ * n2;
   switch (kind) {
     case OP_SR: {
       DDNM_CHECK(ratio == 2 || ratio == 4 || ratio == 8, "SuperResolution: ratio must be 2, 4 or 8");
@@ -634,6 +635,25 @@ Operator::Operator(int kind, int channels, int img_dim, int ratio, const float* 
       M_ = (long long)C_ * sm * sm;
       break;
     }
+    case OP_GENERAL: {
+      // GeneralA (svd_operators.py:173-208): dense A = U diag(s) V^T with FULL factors U [m,m], V [n,n]; only the first m
+      // columns of V ever meet a non-zero coefficient (A(): temp[:, :m]; A_pinv(): add_zeros pads m..n with zeros).
+      // geometry: x is a flat vector of n = img_dim entries per row (channels must be 1)
+      DDNM_CHECK(C_ == 1, "GeneralA: pass channels = 1 and img_dim = n (columns of A)");
+      const long long n = N_ = D_;
+      const int m = ratio;
+      DDNM_CHECK(v_small && u_small && singulars && m >= 1 && m <= n, "GeneralA needs U [m,m], V [n,n], singulars [m] with m <= n");
+      std::vector<float> vm((size_t)n * m), sinv(m);
+      for (long long i = 0; i < n; ++i)
+        for (int j = 0; j < m; ++j) vm[(size_t)i * m + j] = v_small[(size_t)i * n + j];
+      for (int j = 0; j < m; ++j) sinv[j] = singulars[j] == 0.f ? 0.f : 1.0f / singulars[j];   // A_pinv's factors (:74-75)
+      V_ = upload(owned_, vm.data(), vm.size());          // n x m
+      U_ = upload(owned_, u_small, (size_t)m * m);
+      tabD_ = upload(owned_, singulars, (size_t)m);
+      tabDinv_ = upload(owned_, sinv.data(), (size_t)m);
+      M_ = m;
+      break;
+    }
     default:
       throw Error("unknown operator kind");
   }
@@ -700,6 +720,7 @@ void Operator::sandwich(const float* L, int lr, int lc, const float* X, int B, c
 
 void Operator::deblur_A(const float* x, int B, float* y, cudaStream_t s) {
   if (kind_ == OP_CS) return cs_A(x, B, y, s);
+  if (kind_ == OP_GENERAL) return general_A(x, B, y, s);
   const int n2 = D_ * D_;
   const long long n = (long long)B * C_ * n2;
   if (kind_ == OP_DEBLUR || kind_ == OP_DEBLUR2D) {
@@ -723,6 +744,7 @@ void Operator::deblur_A(const float* x, int B, float* y, cudaStream_t s) {
 
 void Operator::deblur_Apinv(const float* y, int B, float* x, cudaStream_t s) {
   if (kind_ == OP_CS) return cs_Apinv(y, B, x, s);
+  if (kind_ == OP_GENERAL) return general_Apinv(y, B, x, s);
   const int n2 = D_ * D_;
   const long long n = (long long)B * C_ * n2;
   if (kind_ == OP_DEBLUR || kind_ == OP_DEBLUR2D) {
@@ -745,6 +767,22 @@ void Operator::deblur_Apinv(const float* y, int B, float* x, cudaStream_t s) {
     sgemm_batched(false, nb, 1, D_, D_, sm, 1.0f, T, sm, (long long)D_ * sm, 0, Vt_, D_, 0, 0, x, D_, (long long)D_ * D_, 0, s);
   }
   CUDA_CHECK(cudaGetLastError());
+}
+
+// GeneralA: y = U (s * (V^T x)[:m]),  x = V add_zeros((1/s) * (U^T y))  — three small fp32 GEMMs over the batch
+void Operator::general_A(const float* x, int B, float* y, cudaStream_t s) {
+  const int n = (int)x_dim(), m = (int)M_;
+  float* T = scratch(0, (size_t)B * m);
+  sgemm_batched(false, 1, 1, B, m, n, 1.0f, x, n, 0, 0, V_, m, 0, 0, T, m, 0, 0, s);          // T = X Vm
+  mul_table_kernel<<<blocks((long long)B * m), 256, 0, s>>>(T, tabD_, 0, 1, m, (long long)B * m);
+  sgemm_batched(true, 1, 1, B, m, m, 1.0f, T, m, 0, 0, U_, m, 0, 0, y, m, 0, 0, s);           // y[b][k] = sum_j U[k][j] T[b][j]
+}
+void Operator::general_Apinv(const float* y, int B, float* x, cudaStream_t s) {
+  const int n = (int)x_dim(), m = (int)M_;
+  float* T = scratch(0, (size_t)B * m);
+  sgemm_batched(false, 1, 1, B, m, m, 1.0f, y, m, 0, 0, U_, m, 0, 0, T, m, 0, 0, s);          // T[b][j] = sum_k y[b][k] U[k][j]
+  mul_table_kernel<<<blocks((long long)B * m), 256, 0, s>>>(T, tabDinv_, 0, 1, m, (long long)B * m);
+  sgemm_batched(true, 1, 1, B, n, m, 1.0f, T, m, 0, 0, V_, m, 0, 0, x, n, 0, 0, s);           // x[b][i] = sum_j V[i][j] T[b][j]
 }
 
 void Operator::cs_A(const float* x, int B, float* y, cudaStream_t s) {
@@ -827,7 +865,7 @@ void Operator::A_pinv(const float* y, int B, float* x, cudaStream_t s) {
 void Operator::project(const float* x0, const float* y, int B, float* out, cudaStream_t s) {
   StepScalars sc{};
   const int n2 = D_ * D_;
-  const long long n = (long long)B * C_ * n2;
+  const long long n = (long long)B * N_;
   if (kind_ == OP_DENOISE) {   // x0 - (x0 - y)
     float* R = scratch(4, n);
     sub_kernel<<<blocks(n), 256, 0, s>>>(x0, y, R, n);
@@ -876,6 +914,7 @@ void Operator::lambda(const float* v, int B, const PlusScalars& ps, float* out, 
   }
   if (kind_ == OP_DEBLUR2D) throw Error("Deblurring2D defines no Lambda (svd_operators.py:1094-1166): sigma_y > 0 is unsupported, as in the reference");
   if (kind_ == OP_CS) throw Error("CS defines no Lambda (svd_operators.py:101-159): sigma_y > 0 is unsupported, as in the reference");
+  if (kind_ == OP_GENERAL) throw Error("GeneralA defines no Lambda (svd_operators.py:173-208): sigma_y > 0 is unsupported, as in the reference");
   switch (kind_) {
     case OP_SR: case OP_COLOR:
       local_dispatch<LF_LAMBDA>(kind_, ratio_, v, nullptr, 0, nullptr, nullptr, V_, u00_, s0_, sc, out, nullptr, B, C_, D_, s);
@@ -918,6 +957,7 @@ void Operator::lambda_noise(const float* v, const float* eps, int B, const PlusS
   }
   if (kind_ == OP_DEBLUR2D) throw Error("Deblurring2D defines no Lambda_noise (svd_operators.py:1094-1166)");
   if (kind_ == OP_CS) throw Error("CS defines no Lambda_noise (svd_operators.py:101-159)");
+  if (kind_ == OP_GENERAL) throw Error("GeneralA defines no Lambda_noise (svd_operators.py:173-208)");
   switch (kind_) {
     case OP_SR: case OP_COLOR:
       local_dispatch<LF_NOISE>(kind_, ratio_, v, eps, img, nullptr, nullptr, V_, u00_, s0_, sc, out, nullptr, B, C_, D_, s);
@@ -945,7 +985,7 @@ void Operator::lambda_noise(const float* v, const float* eps, int B, const PlusS
 void Operator::step(const float* xt, const float* et, long long et_stride, const float* noise, const float* y, int B,
                     const StepScalars& sc, float* x0_t, float* xt_next, cudaStream_t s) {
   const int n2 = D_ * D_;
-  const long long img = (long long)C_ * n2;
+  const long long img = N_;
   const long long n = (long long)B * img;
   if (kind_ == OP_SR || kind_ == OP_COLOR) {
     local_dispatch<LF_STEP>(kind_, ratio_, xt, et, et_stride, noise, y, V_, u00_, s0_, sc, x0_t, xt_next, B, C_, D_, s);

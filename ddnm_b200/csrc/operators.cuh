@@ -7,7 +7,7 @@
 
 namespace ddnm {
 
-enum OpKind : int { OP_SR = 0, OP_COLOR = 1, OP_INPAINT = 2, OP_WH = 3, OP_DEBLUR = 4, OP_SRCONV = 5, OP_DENOISE = 6, OP_DEBLUR2D = 7, OP_CS = 8 };
+enum OpKind : int { OP_SR = 0, OP_COLOR = 1, OP_INPAINT = 2, OP_WH = 3, OP_DEBLUR = 4, OP_SRCONV = 5, OP_DENOISE = 6, OP_DEBLUR2D = 7, OP_CS = 8, OP_GENERAL = 9 };
 
 // scalars of one DDNM+ step (svd_ddnm.py:119-131); all fp32 exactly as the reference's 0-dim tensors / casts
 struct PlusScalars {
@@ -32,7 +32,7 @@ class Operator {
            const float* u_small2 = nullptr);
   ~Operator();
   long long y_dim() const { return M_; }
-  long long x_dim() const { return (long long)C_ * D_ * D_; }
+  long long x_dim() const { return N_; }
   int kind() const { return kind_; }
   void A(const float* x, int B, float* y, cudaStream_t s);
   void A_pinv(const float* y, int B, float* x, cudaStream_t s);
@@ -53,11 +53,13 @@ class Operator {
   void deblur_A(const float* x, int B, float* y, cudaStream_t s);
   void deblur_Apinv(const float* y, int B, float* x, cudaStream_t s);
 
+  void general_A(const float* x, int B, float* y, cudaStream_t s);
+  void general_Apinv(const float* y, int B, float* x, cudaStream_t s);
   void cs_A(const float* x, int B, float* y, cudaStream_t s);
   void cs_Apinv(const float* y, int B, float* x, cudaStream_t s);
   int cs_size_ = 0;
   int kind_, C_, D_, ratio_;
-  long long M_ = 0;
+  long long M_ = 0, N_ = 0;   // per-image lengths of y and x
   // device artefacts
   float *V_ = nullptr, *Vt_ = nullptr, *U_ = nullptr, *Ut_ = nullptr;
   float *Vr_ = nullptr, *Vrt_ = nullptr, *Ur_ = nullptr, *Urt_ = nullptr;   // right-hand factors (== left ones unless Deblurring2D)

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-KIND = dict(sr=0, color=1, inpaint=2, wh=3, deblur=4, srconv=5, denoise=6, deblur2d=7, cs=8)
+KIND = dict(sr=0, color=1, inpaint=2, wh=3, deblur=4, srconv=5, denoise=6, deblur2d=7, cs=8, general=9)
 
 
 def _host_f32(t):
@@ -39,7 +39,7 @@ class _Operator:
         self._h = C.c_void_p()
         _lib.check(_lib.lib().ddnm_operator_create(C.byref(d), C.byref(self._h)))
         self.y_dim = _lib.lib().ddnm_operator_y_dim(self._h)
-        self.x_dim = channels * img_dim * img_dim
+        self.x_dim = img_dim if kind == "general" else channels * img_dim * img_dim
 
     @staticmethod
     def _prep(vec, dim):
@@ -258,6 +258,31 @@ class CS(_Operator):
         self.V_small = V
         self.cs_size = int(32 * 32 * ratio)
         self._create("cs", channels, img_dim, self.cs_size, self.V_small)
+
+    def Lambda(self, *a, **k):
+        raise NotImplementedError()
+
+    def Lambda_noise(self, *a, **k):
+        raise NotImplementedError()
+
+
+class GeneralA(_Operator):
+    """svd_operators.py:173-208 — ``GeneralA(A)``: any dense degradation matrix A [m, n] (m <= n) through its full SVD
+    (``torch.svd(A, some=False)``, singular values below 1e-3 zeroed, as the reference constructor does).  The
+    reference calls it "memory inefficient": V is n x n, so it is only usable for small n.  No Lambda."""
+
+    def __init__(self, A, artefacts=None):
+        if artefacts is None:
+            U, S, V = torch.svd(A, some=False)
+            S = S.clone()
+            S[S < 1e-3] = 0
+        else:
+            U, S, V = artefacts
+        m, n = int(U.shape[0]), int(V.shape[0])
+        if m > n:
+            raise ValueError("GeneralA needs m <= n (the reference's mat_by_vec shapes only work for wide A)")
+        self._U, self._singulars, self._V = U, S, V
+        self._create("general", 1, n, m, V, U, S)
 
     def Lambda(self, *a, **k):
         raise NotImplementedError()

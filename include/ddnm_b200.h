@@ -73,7 +73,8 @@ int ddnm_unet_destroy(void* handle);
  * A, A_pinv, Lambda, Lambda_noise, plus the fused projection x0 - A^+(A x0 - y) of svd_ddnm.py:59-61.
  * kind: 0 SuperResolution(:479) 1 Colorization(:627) 2 Inpainting(:324) 3 WalshHadamardCS(:211)
  *       4 Deblurring(:934) 5 SRConv(:851) 6 Denoising(:442) 7 Deblurring2D(:1094) 8 CS(:101; `ratio` = cs_size,
- *       v_small = the 1024x1024 basis).
+ *       v_small = the 1024x1024 basis)  9 GeneralA(:173; dense A = U diag(s) V^T: `ratio` = m rows of A,
+ *       v_small = V [n,n] with n = channels*img_dim^2, u_small = U [m,m], singulars [m] already thresholded; no Lambda).
  * Artefacts (V_small, perm, mask, singular tables) are inputs.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -139,6 +140,25 @@ int ddnm_simplified_Ap(const ddnm_simple_deg* deg, const float* y, int B, float*
 /* schedule->sigma_y is the doubled level (diffusion.py:292); schedule->plus is ignored */
 int ddnm_sample_simplified(void* unet, const ddnm_simple_deg* deg, const ddnm_schedule* sched, const float* x_T, const float* y,
                            const float* noise, int B, float* out_x0, float* out_x0_pred, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The runner's I/O step either side of the loop (guided_diffusion/diffusion.py:533-603), device pointers throughout.
+ * ddnm_data_transform         = datasets/__init__.py:201-213 data_transform.  uniform_noise / gauss_noise: the torch.rand_like /
+ *                               torch.randn_like draws of config.data.{uniform,gaussian}_dequantization, NULL when the flag is off;
+ *                               rescaled / logit = config.data.rescaled / logit_transform (rescaled wins, as in the reference).
+ * ddnm_inverse_data_transform = datasets/__init__.py:216-227 (sigmoid | (x+1)/2, clamp to [0,1]).
+ * (`config.image_mean` is set by no shipped config; the Python shim rejects it.)
+ * ddnm_finish_images: one pass over the restored batch x [B,C,H,W] (model space):
+ *   out01      [B,C,H,W] fp32 = inverse_data_transform(x)                                    (NULL to skip)
+ *   out_u8_hwc [B,H,W,C] uint8 = the bytes torchvision.utils.save_image encodes,
+ *              mul(255).add_(0.5).clamp_(0,255).to(uint8)  (diffusion.py:596-598)              (NULL to skip)
+ *   psnr       [B] = 10*log10(1 / mean((out01 - inverse_data_transform(orig))^2))  (diffusion.py:599-601); orig, psnr both NULL to skip
+ * ---------------------------------------------------------------------------------------------- */
+int ddnm_data_transform(const float* x, long long n, const float* uniform_noise, const float* gauss_noise, int rescaled, int logit,
+                        float* out, void* stream);
+int ddnm_inverse_data_transform(const float* x, long long n, int rescaled, int logit, float* out, void* stream);
+int ddnm_finish_images(const float* x, const float* orig, int B, int C, int H, int W, int rescaled, int logit, float* out01,
+                       unsigned char* out_u8_hwc, float* psnr, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Op-level entry points (unit tests, micro-benchmarks).  NHWC fp32 tensors, OIHW weights.

@@ -381,9 +381,89 @@ def simplified_fixtures():
     np.savez_compressed(os.path.join(GOLD, "simplified.npz"), **out)
 
 
+def runner_fixtures():
+    """datasets/__init__.py data_transform / inverse_data_transform, tvu.save_image bytes (decoded back with PIL) and the PSNR
+    line of diffusion.py:599-601, all executed from the reference / torchvision."""
+    import io
+    import torchvision.utils as tvu
+    from PIL import Image
+    from datasets import data_transform, inverse_data_transform
+    from oracle import runner_io as RIO
+    out = {}
+    rng = torch.Generator().manual_seed(2718)
+    X = torch.rand(2, 3, 16, 16, generator=rng)
+    xm = torch.randn(2, 3, 16, 16, generator=rng) * 0.8          # "restored" images in model space, partly out of range
+    out["X"], out["xm"] = X.numpy(), xm.numpy()
+    cases = dict(rescaled=(True, False, False, False), logit=(False, True, False, False), deq=(True, False, True, True),
+                 plain=(False, False, False, False))
+    for name, (resc, logit, udq, gdq) in cases.items():
+        cfg = ns(data=ns(rescaled=resc, logit_transform=logit, uniform_dequantization=udq, gaussian_dequantization=gdq))
+        torch.manual_seed(99)
+        un = torch.rand_like(X) if udq else None
+        gn = torch.randn_like(X) if gdq else None
+        torch.manual_seed(99)
+        T = data_transform(cfg, X)
+        close(RIO.data_transform(X, resc, logit, un, gn), T, 1e-6, f"data_transform {name}")
+        out[f"{name}_T"] = T.numpy()
+        if udq:
+            out[f"{name}_un"], out[f"{name}_gn"] = un.numpy(), gn.numpy()
+        inv = inverse_data_transform(cfg, xm)
+        close(RIO.inverse_data_transform(xm, resc, logit), inv, 1e-6, f"inverse {name}")
+        out[f"{name}_inv"] = inv.numpy()
+        orig = inverse_data_transform(cfg, T)
+        u8, ps = [], []
+        for j in range(xm.shape[0]):
+            buf = io.BytesIO()
+            tvu.save_image(inv[j], buf, format="png")                      # diffusion.py:596-598
+            buf.seek(0)
+            img = np.array(Image.open(buf).convert("RGB"))
+            assert np.array_equal(img, RIO.to_uint8_hwc(inv[j]).numpy()), "uint8 quantisation"
+            u8.append(img)
+            mse = torch.mean((inv[j] - orig[j]) ** 2)                      # :600
+            psnr = 10 * torch.log10(1 / mse)                               # :601
+            close(RIO.psnr(inv[j], orig[j]), psnr, 1e-6, "psnr")
+            ps.append(float(psnr))
+        out[f"{name}_u8"] = np.stack(u8)
+        out[f"{name}_psnr"] = np.array(ps, dtype=np.float32)
+    np.savez_compressed(os.path.join(GOLD, "runner_io.npz"), **out)
+    print("runner I/O: ok")
+
+
+def general_fixtures():
+    """GeneralA (svd_operators.py:173-208): a dense 48 x 192 degradation with two singular values pushed under the
+    1e-3 threshold so the zeroing branch (:185) is exercised."""
+    import contextlib
+    import io
+    from functions import svd_operators as R
+    rng = torch.Generator().manual_seed(97)
+    A = torch.randn(48, 192, generator=rng) / 192 ** 0.5
+    U0, S0, V0 = torch.svd(A, some=True)
+    S0[-2:] = torch.tensor([5e-4, 1e-5])
+    A = (U0 * S0) @ V0.t()
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = R.GeneralA(A)
+    o = O.GeneralA(r._U, r._singulars, r._V)
+    assert int((r._singulars == 0).sum()) == 2
+    x = torch.rand(3, 192, generator=rng) * 2 - 1
+    y = r.A(x)
+    close(o.A(x), y, 2e-6, "general A")
+    yq = y * 0.9 + 0.05
+    pin = r.A_pinv(yq.clone())
+    close(o.A_pinv(yq.clone()), pin, 2e-6, "general A_pinv")
+    proj = x - r.A_pinv(r.A(x) - yq)
+    close(o.project(x, yq), proj, 4e-6, "general project")
+    np.savez_compressed(os.path.join(GOLD, "general_a.npz"), A=A.numpy(), U=r._U.numpy(), S=r._singulars.numpy(), V=r._V.numpy(),
+                        x=x.numpy(), yq=yq.numpy(), y=y.numpy(), pinv=pin.numpy(), proj=proj.numpy())
+    print("operator general: ok")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["unet", "openai", "ops", "sampler", "simplified"]
+    which = sys.argv[1:] or ["unet", "openai", "ops", "sampler", "simplified", "general", "runner"]
+    if "general" in which:
+        general_fixtures()
+    if "runner" in which:
+        runner_fixtures()
     if "unet" in which:
         unet_fixtures()
     if "openai" in which:

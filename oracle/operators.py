@@ -489,6 +489,35 @@ class CS(OracleOperator):
         raise NotImplementedError()
 
 
+class GeneralA(OracleOperator):
+    """svd_operators.py:173-208: dense A = U diag(s) V^T from ``torch.svd(A, some=False)`` with s < 1e-3 zeroed; batched
+    mat-vec products (:174-179); add_zeros pads the m coefficients to n (:203-206).  No Lambda."""
+
+    def __init__(self, U, S, V):
+        self._U, self._S, self._V = U, S, V
+        self.m, self.n = U.shape[0], V.shape[0]
+
+    def A(self, v):
+        v = v.reshape(v.shape[0], -1)
+        temp = torch.matmul(self._V.t(), v.reshape(v.shape[0], self.n, 1)).reshape(v.shape[0], self.n)
+        return torch.matmul(self._U, (self._S * temp[:, : self.m]).reshape(-1, self.m, 1)).reshape(v.shape[0], self.m)
+
+    def A_pinv(self, y):
+        y = y.reshape(y.shape[0], -1)
+        temp = torch.matmul(self._U.t(), y.reshape(y.shape[0], self.m, 1)).reshape(y.shape[0], self.m)
+        factors = 1.0 / self._S
+        factors[self._S == 0] = 0.0
+        out = torch.zeros(y.shape[0], self.n)
+        out[:, : self.m] = temp * factors
+        return torch.matmul(self._V, out.reshape(-1, self.n, 1)).reshape(y.shape[0], self.n)
+
+    def Lambda(self, *args):
+        raise NotImplementedError()
+
+    def Lambda_noise(self, *args):
+        raise NotImplementedError()
+
+
 def hadamard_basis(n=1024):
     """A reproducible orthonormal 1024 x 1024 basis (Sylvester Hadamard / sqrt(n), exactly representable) used where tests
     need the SAME ``V_small`` on every machine; the reference draws its own from the global RNG."""

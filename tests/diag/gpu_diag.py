@@ -1,4 +1,5 @@
-"""GPU diagnostics for the tensor-core path (run on the B200 box; each group in its own process)."""
+"""GPU diagnostics for the tensor-core path (run on the B200 box; each group in its own process).
+Lives under tests/ because several groups use the oracle as their checker (oracle/ is test infrastructure only)."""
 import ctypes as C
 import json
 import os
@@ -8,7 +9,8 @@ import time
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 from ddnm_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
@@ -181,7 +183,7 @@ def group_unet(which="tiny", B=2, graph=1):
 def group_openai(which="tiny", B=2, graph=1):
     from oracle import unet_openai as UO
     from ddnm_b200.model import create_model
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import openai_model_kwargs
     cfg = UO.OpenAIUNetConfig.tiny() if which == "tiny" else UO.OpenAIUNetConfig.imagenet_256()
     sd = UO.init_state_dict(cfg, 1234)

@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --for
 for g in "$@"; do
   echo "===== $g =====" >> $LOG
   IFS=: read -ra parts <<< "$g"
-  timeout 600 python tools/gpu_diag.py "${parts[@]}" >> $LOG 2>&1
+  timeout 600 python tests/diag/gpu_diag.py "${parts[@]}" >> $LOG 2>&1
   echo "exit=$?" >> $LOG
 done
 tail -c 6000 $LOG

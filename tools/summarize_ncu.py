@@ -59,5 +59,36 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst):
+    """Per-launch DRAM traffic of the captured conv_tc_kernel launches -> the JSON bench.py reads for roofline.traffic."""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+
+    def val(r, name, want):
+        x, u = float(r[idx[name]].replace(",", "")), units[idx[name]]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1, "%": 1, "Ghz": 1, "Mhz": 1e-3}[u]
+        return x * scale
+
+    ls = []
+    for r in rows[2:]:
+        ls.append(dict(kernel=r[idx["Kernel Name"]][:28], ms=val(r, "gpu__time_duration.sum", "ms"),
+                       dram_read=val(r, "dram__bytes_read.sum", "byte"), dram_write=val(r, "dram__bytes_write.sum", "byte"),
+                       tensor_active_pct=val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "%"),
+                       l2_hit_pct=val(r, "lts__t_sector_hit_rate.pct", "%"), sm_ghz=val(r, "sm__cycles_elapsed.avg.per_second", "Ghz")))
+    # the dominant launch of the celeba B=16 forward: up.0 conv1 (3x3, 256 -> 128 channels at 256x256), the longest captured
+    top = max(ls, key=lambda l: l["ms"])
+    B, H, Cin, Cout = 16, 256, 256, 128
+    alg = B * H * H * Cin * 2 * 2 + B * H * H * Cout * 4 + 9 * Cin * Cout * 2 * 2   # fp16 hi+lo planes in, fp32 out, hi+lo weights
+    doc = dict(source=" ".join(sys.argv[4:]) or src, launches=ls,
+               algorithmic_bytes={"conv1_256to128_at_256x256_B16": alg},
+               top_launch=dict(name="up.0.block.N.conv1 (3x3, 256->128 @256x256, B=16)", traffic_bytes=top["dram_read"] + top["dram_write"],
+                               algorithmic_bytes=alg, tensor_pipe_active_pct=top["tensor_active_pct"], ms=top["ms"]))
+    json.dump(doc, open(dst, "w"), indent=1)
+    print(json.dumps(doc["top_launch"], indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
