@@ -77,6 +77,7 @@ _SIGS = {
     "ddnm_conv_tc_bench": (C.c_int, [_I, _I, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_D)]),
     "ddnm_groupnorm": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P]),
     "ddnm_tc_debug_override": (C.c_int, [C.c_uint, C.c_uint]),
+    "ddnm_tc_debug_force_bn": (C.c_int, [_I]),
 }
 EXPORTS = ["ddnm_last_error"] + list(_SIGS)
 

@@ -246,6 +246,11 @@ int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const
   DDNM_API_END
 }
 
+int ddnm_tc_debug_force_bn(int bn) {
+  DDNM_API_BEGIN
+  tc_debug_force_bn(bn);
+  DDNM_API_END
+}
 int ddnm_tc_debug_override(unsigned desc_hi, unsigned idesc_xor) {
   DDNM_API_BEGIN
   tc_debug_override(desc_hi, idesc_xor);

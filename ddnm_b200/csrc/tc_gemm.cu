@@ -387,6 +387,11 @@ void tc_set_terms(int terms) {
   g_terms = terms;
 }
 int tc_get_terms() { return g_terms; }
+static int g_force_bn = 0;
+void tc_debug_force_bn(int bn) {
+  DDNM_CHECK(bn == 0 || bn == 64 || bn == 128 || bn == 256, "BN must be 0 (heuristic), 64, 128 or 256");
+  g_force_bn = bn;
+}
 void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor) {
   g_desc_hi_override = desc_hi;
   g_idesc_xor = idesc_xor;
@@ -421,6 +426,7 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
         break;
       }
     }
+    if (g_force_bn && Cout % g_force_bn == 0) L.BN = g_force_bn;   // tuning experiments only (ddnm_tc_debug_force_bn)
   }
   p.n_tiles = Cout / L.BN;
   p.mode0 = mode0;

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from .model import _EngineModel
-from .operators import CS, Deblurring2D, SRConv, _Operator
+from .operators import CS, Deblurring2D, GeneralA, SRConv, _Operator
 from .schedule import alpha_bar_table, time_pairs
 
 class_num = 951
@@ -30,7 +30,7 @@ def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, n
         model = getattr(model, "module", model)          # tolerate nn.DataParallel-style wrappers
     if not isinstance(model, _EngineModel) or not isinstance(A_funcs, _Operator):
         raise TypeError("ddnm_b200.sampler needs a ddnm_b200.model denoiser and a ddnm_b200.operators operator")
-    if plus and isinstance(A_funcs, (SRConv, Deblurring2D, CS)):
+    if plus and isinstance(A_funcs, (SRConv, Deblurring2D, CS, GeneralA)):
         # these operators define no Lambda / Lambda_noise: the reference fails at its first step with the base class's
         # NotImplementedError (svd_operators.py:93-97)
         raise NotImplementedError()

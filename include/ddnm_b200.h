@@ -172,6 +172,8 @@ int ddnm_conv_tc_bench(int N, int H, int W, int Cin, int Cout, int mode, int ite
 int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const float* gamma, const float* beta, float eps,
                    int silu, float* out, void* stream);
 int ddnm_tc_debug_override(unsigned desc_hi, unsigned idesc_xor);
+/* tuning experiments: force the N-tile width of conv launches built afterwards (0 = heuristic) */
+int ddnm_tc_debug_force_bn(int bn);
 
 #ifdef __cplusplus
 }

@@ -126,6 +126,29 @@ def group_bench():
         print(f"[bench] N{N} {H}x{W} {Cin}->{Cout} mode{mode}: {ms.value:.3f} ms  {fl.value / ms.value / 1e9:.1f} TFLOP/s (algorithmic)", flush=True)
 
 
+def group_bn_sweep():
+    """N-tile width vs layer shape (all conv shapes of the two networks' low / mid resolution levels): data for the BN heuristic."""
+    ms, fl = C.c_float(), C.c_double()
+    shapes = [(16, 8, 8, 512, 512, 0), (16, 8, 8, 1024, 512, 0), (16, 16, 16, 512, 512, 0), (16, 16, 16, 1024, 512, 0),
+              (16, 16, 16, 256, 512, 0), (16, 16, 16, 512, 512, 1), (16, 16, 16, 512, 1536, 1), (16, 32, 32, 256, 256, 0),
+              (16, 32, 32, 512, 256, 0), (16, 32, 32, 768, 256, 0), (16, 64, 64, 256, 256, 0), (16, 64, 64, 512, 256, 0),
+              (16, 128, 128, 128, 128, 0), (16, 128, 128, 256, 128, 0), (16, 256, 256, 256, 128, 0),
+              (8, 8, 8, 1024, 1024, 0), (8, 8, 8, 2048, 1024, 0), (8, 16, 16, 1024, 1024, 0), (8, 16, 16, 2048, 1024, 0),
+              (8, 32, 32, 512, 512, 0), (8, 32, 32, 1024, 512, 0), (8, 64, 64, 512, 512, 0), (8, 128, 128, 256, 256, 0)]
+    for (N, H, W, Cin, Cout, mode) in shapes:
+        row = []
+        for bn in (64, 128, 256):
+            if Cout % bn:
+                row.append("   -   ")
+                continue
+            _lib.check(L.ddnm_tc_debug_force_bn(bn))
+            _lib.check(L.ddnm_conv_tc_bench(N, H, W, Cin, Cout, mode, 20, C.byref(ms), C.byref(fl)))
+            row.append(f"{ms.value * 1e3:7.1f}")
+        _lib.check(L.ddnm_tc_debug_force_bn(0))
+        _lib.check(L.ddnm_conv_tc_bench(N, H, W, Cin, Cout, mode, 20, C.byref(ms), C.byref(fl)))
+        print(f"[bn_sweep] N{N} {H}x{W} {Cin}->{Cout} mode{mode}: us @BN64/128/256 = {' '.join(row)}   heuristic {ms.value * 1e3:7.1f}", flush=True)
+
+
 def _cfg_ns(cfg):
     import types
     ns = types.SimpleNamespace
@@ -300,6 +323,45 @@ def group_unet_bench(which="celeba", B=16, iters=5, prec="fp32"):
         print(f"   top {p['name']:28s} {p['ms']:.3f} ms  {p['flops'] / max(p['ms'], 1e-9) / 1e9:.1f} TF/s  {p['bytes'] / max(p['ms'], 1e-9) / 1e6:.1f} GB/s")
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(prof, open(f"gpurun_out/unet_profile_{which}_B{B}.json", "w"))
+
+
+def group_eager(which="celeba", B=16, iters=3):
+    """The competitor SURVEY §8d names: the reference's network as plain PyTorch eager on this GPU (the oracle restatement is
+    the reference's op sequence, bit-exact on CPU), with the reference's own settings (main.py:145 cudnn.benchmark = True; TF32
+    convolutions allowed, torch's default) and with TF32 off (strict fp32, the precision class ddnm_b200's parity mode delivers)."""
+    B, iters = int(B), int(iters)
+    if which == "openai":
+        from oracle import unet_openai as UM
+        cfg = UM.OpenAIUNetConfig.imagenet_256()
+    else:
+        from oracle import unet_simple as UM
+        cfg = UM.SimpleUNetConfig.celeba_hq()
+    sd = {k: v.to(dev) for k, v in UM.init_state_dict(cfg, 1234).items()}
+    res = cfg.image_size if which == "openai" else cfg.resolution
+    x = torch.randn(B, 3, res, res, device=dev)
+    t = torch.full((B,), 500.0, device=dev)
+    torch.backends.cudnn.benchmark = True
+    out = {}
+    for tf32 in (True, False):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        with torch.no_grad():
+            for _ in range(3):
+                UM.forward(sd, x, t, cfg)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                UM.forward(sd, x, t, cfg)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out["tf32_conv" if tf32 else "fp32_strict"] = ms
+        print(f"[eager torch {which} B{B}] cudnn TF32 convs {'on ' if tf32 else 'off'}: {ms:.2f} ms/forward = {B / ms * 1e3:.1f} image-forwards/s", flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(dict(model=which, batch=B, ms_per_forward=out, torch=torch.__version__, cudnn=torch.backends.cudnn.version(),
+                   note="oracle restatement of the reference network run as PyTorch eager on the GPU; cudnn.benchmark=True"),
+              open(f"gpurun_out/eager_torch_{which}_B{B}.json", "w"))
 
 
 if __name__ == "__main__":
