@@ -246,6 +246,11 @@ int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const
   DDNM_API_END
 }
 
+int ddnm_tc_debug_pair_mode(int mode) {
+  DDNM_API_BEGIN
+  tc_debug_pair_mode(mode);
+  DDNM_API_END
+}
 int ddnm_tc_debug_force_bn(int bn) {
   DDNM_API_BEGIN
   tc_debug_force_bn(bn);

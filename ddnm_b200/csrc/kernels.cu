@@ -327,45 +327,70 @@ void conv3x3_small_cin(const float* x, int Cin, const float* w, const float* bia
 // ---------------------------------------------------------------------------------------------------------------
 // Timestep MLP pieces (models.py:6-24, 305-308, 121).  One warp per output element.
 // ---------------------------------------------------------------------------------------------------------------
-// one warp per output feature o; the weight row is read once and reused for every image of the batch
-__global__ void linear_kernel(const float* __restrict__ in, int N, int K, const float* __restrict__ W,
-                              const float* __restrict__ bias, int O, float* __restrict__ out, int ldo, int act_in, int act_out) {
-  const int o = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (o >= O) return;
-  const float* w = W + (long long)o * K;
-  constexpr int NB = 8;
-  for (int n0 = 0; n0 < N; n0 += NB) {
-    float acc[NB];
+// The activations (N x K, act_in applied once) are staged in shared memory; each warp then produces LIN_OPW output features,
+// reading each weight row exactly once with 16-byte loads and reusing it for every image of the batch.
+constexpr int LIN_NB = 16;    // images per accumulator pass
+constexpr int LIN_OPW = 8;    // output features per warp
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, int N, int K, const float* __restrict__ W,
+                                                     const float* __restrict__ bias, int O, float* __restrict__ out, int ldo,
+                                                     int act_in, int act_out) {
+  extern __shared__ float lin_in[];
+  for (int i = threadIdx.x; i < N * K; i += 256) {
+    float v = in[i];
+    if (act_in) v = swishf(v);
+    lin_in[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o0 = (blockIdx.x * 8 + warp) * LIN_OPW;
+  const int K4 = K >> 2;
+  for (int oo = 0; oo < LIN_OPW; ++oo) {
+    const int o = o0 + oo;
+    if (o >= O) return;
+    const float4* w4 = reinterpret_cast<const float4*>(W + (long long)o * K);
+    for (int n0 = 0; n0 < N; n0 += LIN_NB) {
+      float acc[LIN_NB];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) acc[j] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float wv = __ldg(w + k);
+      for (int j = 0; j < LIN_NB; ++j) acc[j] = 0.f;
+      for (int k4 = lane; k4 < K4; k4 += 32) {
+        const float4 wv = __ldg(w4 + k4);
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        if (n0 + j < N) {
-          float v = in[(long long)(n0 + j) * K + k];
-          if (act_in) v = swishf(v);
-          acc[j] = fmaf(v, wv, acc[j]);
+        for (int j = 0; j < LIN_NB; ++j) {
+          if (n0 + j < N) {
+            const float4 v = reinterpret_cast<const float4*>(lin_in + (long long)(n0 + j) * K)[k4];
+            acc[j] = fmaf(v.x, wv.x, fmaf(v.y, wv.y, fmaf(v.z, wv.z, fmaf(v.w, wv.w, acc[j]))));
+          }
         }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      float a = acc[j];
+      for (int j = 0; j < LIN_NB; ++j) {
+        float a = acc[j];
 #pragma unroll
-      for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-      if (lane == 0 && n0 + j < N) {
-        float r = a + (bias ? bias[o] : 0.f);
-        if (act_out) r = swishf(r);
-        out[(long long)(n0 + j) * ldo + o] = r;
+        for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+        if (lane == 0 && n0 + j < N) {
+          float r = a + (bias ? bias[o] : 0.f);
+          if (act_out) r = swishf(r);
+          out[(long long)(n0 + j) * ldo + o] = r;
+        }
       }
     }
   }
 }
 void linear(const float* in, int N, int K, const float* W, const float* bias, int O, float* out, int ldo, int act_in,
             int act_out, cudaStream_t st) {
-  linear_kernel<<<(int)cdivll((long long)O * 32, 256), 256, 0, st>>>(in, N, K, W, bias, O, out, ldo, act_in, act_out);
+  DDNM_CHECK(K % 4 == 0, "linear: K must be a multiple of 4");
+  static bool attr = false;
+  constexpr int kMaxSmem = 160 * 1024;
+  if (!attr) {
+    CUDA_CHECK(cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr = true;
+  }
+  const int rows_max = std::max(1, kMaxSmem / (K * 4));
+  for (int n0 = 0; n0 < N; n0 += rows_max) {     // batches whose activations exceed the staging buffer go in row chunks
+    const int n = std::min(rows_max, N - n0);
+    linear_kernel<<<cdiv(O, 8 * LIN_OPW), 256, (size_t)n * K * 4, st>>>(in + (long long)n0 * K, n, K, W, bias, O,
+                                                                         out + (long long)n0 * ldo, ldo, act_in, act_out);
+  }
   CUDA_CHECK(cudaGetLastError());
 }
 

@@ -22,21 +22,26 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;                      // fp16 elements = 128 bytes = one swizzle row
 static constexpr int A_PLANE_BYTES = BM * BK * 2;  // 16 KiB
 
-template <int BN>
+// PAIR: two CTAs of a cluster (one TPC) run ONE 256-row MMA (tcgen05 cta_group::2): each CTA stages its own 128-pixel A tile and
+// HALF of the B tile (BN/2 weight rows), the leader CTA issues the MMAs for both, every CTA drains its own 128 TMEM lanes.
+// Per MMA a CTA's shared memory now serves 128 + BN/2 operand rows instead of 128 + BN, which is what lets the Cout = 128
+// layers (BN = 128, the bulk of the celeba network) run the tensor pipe past the ~76 % the single-CTA form reaches.
+template <int BN, bool PAIR>
 struct TcCfg {
-  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
-  static constexpr int B_PLANE_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;       // B rows staged by one CTA
+  static constexpr int B_PLANE_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
+  static constexpr int STAGES = STAGE_BYTES <= 48 * 1024 ? 4 : (STAGE_BYTES <= 64 * 1024 ? 3 : 2);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant__ CUtensorMap tm_a0l,
                const __grid_constant__ CUtensorMap tm_a1h, const __grid_constant__ CUtensorMap tm_a1l,
                const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bl, const TcParams p) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -55,7 +60,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
   const int total_tiles = m_tiles * p.n_tiles;
   // tiles are dealt round-robin: at any moment the 148 CTAs work on 148 consecutive tiles (adjacent rows of one image), which
   // keeps their shared halo rows and the DRAM stream together (a contiguous range per CTA measured ~4 % slower)
-  const int tile_begin = blockIdx.x, tile_end = total_tiles, tile_step = gridDim.x;
+  // PAIR: the scheduling unit is a pair of M-adjacent tiles sharing one N tile; CTA `rank` of the cluster owns tile 2*mp + rank.
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit_begin = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int unit_end = PAIR ? total_tiles / 2 : total_tiles;
+  const int unit_step = PAIR ? (int)(gridDim.x / 2) : (int)gridDim.x;
+  auto tile_of = [&](int u) {
+    if (!PAIR) return u;
+    const int mp = u / p.n_tiles;
+    return (2 * mp + (int)rank) * p.n_tiles + (u - mp * p.n_tiles);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a0h);
@@ -72,13 +87,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 256);
+      mbar_init(tempty_bar(a), PAIR ? 512 : 256);   // every epilogue thread (of both CTAs) arrives once per tile
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers exist before any remote arrive / TMA completion can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -98,15 +117,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     // ------------------------------------------------ TMA producer ------------------------------------------------
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      // PAIR: both CTAs stage their halves; all bytes are credited to the LEADER's full barrier, which alone is armed
+      auto load4 = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+        if (PAIR) tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
+        else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+      };
+      const uint32_t stage_tx = (PAIR ? 2u : 1u) * (uint32_t)(p.terms == 1 ? Cfg::STAGE_BYTES / 2 : Cfg::STAGE_BYTES);
+      for (int u = unit_begin; u < unit_end; u += unit_step) {
+        const int tile = tile_of(u);
         int n_idx, x0, y0, n0;
         decode(tile, n_idx, x0, y0, n0);
         const int bz = p.b_batched == 1 ? n0 : 0;
+        const int brow = n_idx * BN + (int)rank * Cfg::B_ROWS;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t fb = full_bar(stage);
-          mbar_expect_tx(fb, p.terms == 1 ? Cfg::STAGE_BYTES / 2 : Cfg::STAGE_BYTES);
+          if (leader) mbar_expect_tx(fb, stage_tx);
           const bool lo = p.terms != 1;
           if (kb < p.kb0) {
             const int tap = kb / p.cb0;
@@ -124,14 +151,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
               cx += dx >> 1;
               cn += ((dy & 1) * 2 + (dx & 1)) * p.phase_stride;
             }
-            tma_load_4d(sa, &tm_a0h, fb, c, cx, cy, cn);
-            if (lo) tma_load_4d(sa + A_PLANE_BYTES, &tm_a0l, fb, c, cx, cy, cn);
+            load4(sa, &tm_a0h, fb, c, cx, cy, cn);
+            if (lo) load4(sa + A_PLANE_BYTES, &tm_a0l, fb, c, cx, cy, cn);
           } else {
             const int c = (kb - p.kb0) * BK;
-            tma_load_4d(sa, &tm_a1h, fb, c, x0, y0, n0);
-            if (lo) tma_load_4d(sa + A_PLANE_BYTES, &tm_a1l, fb, c, x0, y0, n0);
+            load4(sa, &tm_a1h, fb, c, x0, y0, n0);
+            if (lo) load4(sa + A_PLANE_BYTES, &tm_a1l, fb, c, x0, y0, n0);
           }
-          if (p.b_batched == 2) {
+          if (PAIR) {
+            tma_load_3d_pair(sa + 2 * A_PLANE_BYTES, &tm_bh, fb, kb * BK, brow, bz);
+            if (lo) tma_load_3d_pair(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tm_bl, fb, kb * BK, brow, bz);
+          } else if (p.b_batched == 2) {
             tma_load_4d(sa + 2 * A_PLANE_BYTES, &tm_bh, fb, kb * BK, n_idx * BN, y0, n0);
             if (lo) tma_load_4d(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tm_bl, fb, kb * BK, n_idx * BN, y0, n0);
           } else {
@@ -147,10 +177,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------ UMMA issuer -------------------------------------------------
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       const uint64_t hi = (uint64_t)p.desc_hi << 32;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
+        if (PAIR) umma_f16_pair(d, a, b, p.idesc, accumulate);
+        else umma_f16(d, a, b, p.idesc, accumulate);
+      };
+      auto commit = [&](uint32_t bar) {
+        if (PAIR) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
+      for (int u = unit_begin; u < unit_end; u += unit_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -166,19 +204,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint32_t adv = 2u * k;  // 16 fp16 = 32 bytes = 2 x 16-byte units inside the swizzle row
-            umma_f16(d_tmem, hi | (ah + adv), hi | (bh + adv), p.idesc, (uint32_t)((kb | k) != 0));
+            mma(d_tmem, hi | (ah + adv), hi | (bh + adv), (uint32_t)((kb | k) != 0));
             if (p.terms != 1) {
-              umma_f16(d_tmem, hi | (ah + adv), hi | (bl + adv), p.idesc, 1u);
-              umma_f16(d_tmem, hi | (al + adv), hi | (bh + adv), p.idesc, 1u);
+              mma(d_tmem, hi | (ah + adv), hi | (bl + adv), 1u);
+              mma(d_tmem, hi | (al + adv), hi | (bh + adv), 1u);
             }
           }
-          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          commit(empty_bar(stage));  // smem slot (of both CTAs) reusable once these MMAs have read it
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        commit(tfull_bar(acc));  // accumulator complete -> epilogue (of both CTAs)
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -200,7 +238,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
       run_s[ch] = 0.f;
       run_q[ch] = 0.f;
     }
-    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+    for (int u = unit_begin; u < unit_end; u += unit_step) {
+      const int tile = tile_of(u);
       int n_idx, x0, y0, n0;
       decode(tile, n_idx, x0, y0, n0);
       const int n = n0 + ni;
@@ -304,9 +343,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
         // the same image / channel block, flush with one atomic pair per column otherwise
         const int img_w = n0 + (ew * 32) / (p.bw * p.bh);
         int next_img = -1, next_nidx = -1;
-        if (tile + tile_step < tile_end) {
+        if (u + unit_step < unit_end) {
           int nx0, ny0, nn0;
-          decode(tile + tile_step, next_nidx, nx0, ny0, nn0);
+          decode(tile_of(u + unit_step), next_nidx, nx0, ny0, nn0);
           next_img = nn0 + (ew * 32) / (p.bw * p.bh);
         }
         if (next_img != img_w || next_nidx != n_idx) {
@@ -326,7 +365,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      if (PAIR) mbar_arrive_leader(tempty_bar(acc));
+      else mbar_arrive(tempty_bar(acc));
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -334,9 +374,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the leader's MMAs / commits no longer touch the peer's smem, TMEM or barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -387,6 +429,12 @@ void tc_set_terms(int terms) {
   g_terms = terms;
 }
 int tc_get_terms() { return g_terms; }
+static int g_pair_mode = -1;   // -1: cost model decides (default), 0: never, 1: CTA pairs wherever legal
+static double g_pair_tkb[2] = {940.0, 1560.0};   // modelled clocks per k-block of the pair kernel at BN = 128 / 256
+void tc_debug_pair_mode(int mode) {
+  DDNM_CHECK(mode == -1 || mode == 0 || mode == 1, "pair mode must be -1 (cost model), 0 (off) or 1 (wherever legal)");
+  g_pair_mode = mode;
+}
 static int g_force_bn = 0;
 void tc_debug_force_bn(int bn) {
   DDNM_CHECK(bn == 0 || bn == 64 || bn == 128 || bn == 256, "BN must be 0 (heuristic), 64, 128 or 256");
@@ -415,18 +463,36 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   p.tiles_x = out.W / p.bw;
   p.tiles_y = out.H / p.bh;
   p.tiles_n = cdiv(out.N, p.bn);
-  // N tile: the widest that still gives every SM a tile.  Low-resolution layers (8x8, 16x16) have few M tiles but a long
-  // K loop (up to 144 k-blocks), so narrow N tiles spread them over more SMs at no extra HBM cost (A stays in L2).
+  // Tile shape by a small cost model fitted to the B200 sweep in profiles/r01_bn_sweep.md.  Every configuration turned out to be
+  // paced by SHARED-MEMORY bandwidth, not by the MMA rate: per 64-deep k-block a CTA's smem serves the 12 MMAs' operand reads
+  // (128 + BN rows x 32 B each) plus the TMA fill of the next stage, ~128 B/clk in total.  Wider N tiles amortise the A rows,
+  // CTA pairs halve the B rows per CTA; rounds = ceil(units / resident CTAs or pairs) adds the wave quantisation and a fixed
+  // per-round cost covers pipeline fill + the last tile's exposed epilogue.
   {
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int kblocks = taps * (src0.C / BK) + (src1 ? src1->C / BK : 0);
+    struct Cand { int bn; bool pair; double t_kb; };
+    // clocks per k-block (measured single-CTA: 1000 / 1130 / 2100; pairs: see the sweep)
+    const Cand cands[] = {{64, false, 1000.0}, {128, false, 1130.0}, {256, false, 2100.0}, {128, true, g_pair_tkb[0]}, {256, true, g_pair_tkb[1]}};
+    double best = 1e300;
     L.BN = 64;
-    for (int bn : {256, 128}) {
-      if (Cout % bn == 0 && (long long)m_tiles * (Cout / bn) >= num_sms) {
-        L.BN = bn;
-        break;
+    L.pair = false;
+    for (const Cand& c : cands) {
+      if (Cout % c.bn) continue;
+      if (g_force_bn && c.bn != g_force_bn && Cout % g_force_bn == 0) continue;   // tuning experiments only
+      const long long tiles = (long long)m_tiles * (Cout / c.bn);
+      if (c.pair && (g_pair_mode == 0 || w_batches != 1 || m_tiles % 2 != 0)) continue;
+      if (!c.pair && g_pair_mode == 1 && w_batches == 1 && m_tiles % 2 == 0 && c.bn >= 128) continue;   // forced pairs
+      const long long units = c.pair ? tiles / 2 : tiles;
+      const long long slots = c.pair ? num_sms / 2 : num_sms;
+      const double rounds = (double)((units + slots - 1) / slots);
+      const double cost = rounds * (kblocks * c.t_kb + 1500.0);
+      if (cost < best) {
+        best = cost;
+        L.BN = c.bn;
+        L.pair = c.pair;
       }
     }
-    if (g_force_bn && Cout % g_force_bn == 0) L.BN = g_force_bn;   // tuning experiments only (ddnm_tc_debug_force_bn)
   }
   p.n_tiles = Cout / L.BN;
   p.mode0 = mode0;
@@ -456,7 +522,7 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   // [46,48), layout SWIZZLE_128B (= 2) at [61,64).  (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
   p.desc_hi = g_desc_hi_override ? g_desc_hi_override : (64u | (1u << 14) | (2u << 29));
   // Instruction descriptor: D = f32 (1 << 4), A = B = f16 (0), K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
-  p.idesc = ((1u << 4) | ((uint32_t)(L.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24)) ^ g_idesc_xor;
+  p.idesc = ((1u << 4) | ((uint32_t)(L.BN >> 3) << 17) | ((uint32_t)((L.pair ? 2 * BM : BM) >> 4) << 24)) ^ g_idesc_xor;
 
   const uint64_t ad[4] = {(uint64_t)src0.C, (uint64_t)src0.W, (uint64_t)src0.H, (uint64_t)src0.N};
   const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
@@ -472,11 +538,11 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   }
   const int Ktot = (p.kb0 + p.kb1) * BK;
   const uint64_t bd[3] = {(uint64_t)Ktot, (uint64_t)Cout, (uint64_t)w_batches};
-  const uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)L.BN, 1u};
+  const uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)(L.pair ? L.BN / 2 : L.BN), 1u};
   L.bh = make_map_f16(w_hi, 3, bd, bbox);
   L.bl = make_map_f16(w_lo, 3, bd, bbox);
   const int total = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
-  L.grid = std::min(total, num_sms);
+  L.grid = L.pair ? 2 * std::min(total / 2, num_sms / 2) : std::min(total, num_sms);
   L.flops = 2.0 * (double)out.pixels() * Cout * Ktot;
   return L;
 }
@@ -545,22 +611,45 @@ TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, 
   return L;
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static void launch_bn(const TcLaunch& L, cudaStream_t stream) {
+  using Cfg = TcCfg<BN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  conv_tc_kernel<BN><<<L.grid, 320, TcCfg<BN>::SMEM_BYTES, stream>>>(L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.p);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(L.grid);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, PAIR>, L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.p));
+  } else {
+    conv_tc_kernel<BN, PAIR><<<L.grid, 320, Cfg::SMEM_BYTES, stream>>>(L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.p);
+  }
   CUDA_CHECK(cudaGetLastError());
 }
 
 void tc_run(const TcLaunch& L, cudaStream_t stream) {
   switch (L.BN) {
-    case 256: launch_bn<256>(L, stream); break;
-    case 128: launch_bn<128>(L, stream); break;
-    case 64: launch_bn<64>(L, stream); break;
+    case 256:
+      if (L.pair) launch_bn<256, true>(L, stream);
+      else launch_bn<256, false>(L, stream);
+      break;
+    case 128:
+      if (L.pair) launch_bn<128, true>(L, stream);
+      else launch_bn<128, false>(L, stream);
+      break;
+    case 64: launch_bn<64, false>(L, stream); break;
     default: throw Error("bad BN");
   }
 }

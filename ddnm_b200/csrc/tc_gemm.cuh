@@ -44,6 +44,7 @@ struct TcLaunch {
   CUtensorMap a0h, a0l, a1h, a1l, bh, bl;
   TcParams p;
   int BN = 128;
+  bool pair = false;           // CTA-pair kernel (cta_group::2, 256-row MMAs, cluster of 2)
   int grid = 0;
   double flops = 0;            // algorithmic flops (2*M*N*K, counted once)
 };
@@ -74,6 +75,7 @@ TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, 
 // debug knobs (tests only): override descriptor words for the NEXT launches built
 void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor);
 void tc_debug_force_bn(int bn);
+void tc_debug_pair_mode(int mode);   // -1: cost model decides (default), 0: never, 1: CTA pairs wherever legal
 // number of fp16 product terms used by launches built from now on (3 = parity mode, 1 = fast mode)
 void tc_set_terms(int terms);
 int tc_get_terms();

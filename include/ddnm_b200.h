@@ -174,6 +174,9 @@ int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const
 int ddnm_tc_debug_override(unsigned desc_hi, unsigned idesc_xor);
 /* tuning experiments: force the N-tile width of conv launches built afterwards (0 = heuristic) */
 int ddnm_tc_debug_force_bn(int bn);
+/* CTA-pair kernel (tcgen05 cta_group::2) for conv launches built afterwards: -1 (default) the cost model decides,
+ * 0 never, 1 wherever legal */
+int ddnm_tc_debug_pair_mode(int mode);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,55 @@ def test_tc_conv_fusions(lib):
     assert_close(_conv_tc(lib, x, w, b), out.permute(0, 3, 1, 2), 1e-4, 5e-5, "tc vs direct")
 
 
+@pytest.mark.parametrize("shape", [(2, 256, 256, 64, 128, 0), (4, 128, 128, 128, 256, 0), (4, 128, 128, 64, 128, 1), (8, 128, 128, 64, 128, 2),
+                                   (2, 128, 128, 64, 384, 0)], ids=str)
+def test_tc_conv_cta_pair_vs_fp64_and_single_cta(lib, shape):
+    """Layers with >= 148 tiles and Cout % 128 == 0 run the CTA-pair kernel (tcgen05 cta_group::2, 256-row MMAs): it must agree
+    with the fp64 reference AND with the single-CTA kernel on the same inputs."""
+    N, H, W, Cin, Cout, mode = shape
+    torch.manual_seed(5)
+    k = 1 if mode == 1 else 3
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, k, k, device=dev) / (k * k * Cin) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    L = lib.lib()
+    try:
+        lib.check(L.ddnm_tc_debug_pair_mode(0))
+        single = _conv_tc(lib, x, w, b, mode=mode).clone()
+        lib.check(L.ddnm_tc_debug_pair_mode(1))
+        pair = _conv_tc(lib, x, w, b, mode=mode)
+    finally:
+        L.ddnm_tc_debug_pair_mode(-1)
+    torch.cuda.synchronize()
+    assert_close(pair, single, 1e-6, 1e-6, f"pair vs single-CTA {shape}")
+    assert_close(pair, _conv_ref(x, w, b, mode=mode), rtol=1e-4, atol=5e-5, what=f"pair conv {shape}")
+
+
+def test_tc_conv_cta_pair_fusions(lib):
+    torch.manual_seed(6)
+    L = lib.lib()
+    lib.check(L.ddnm_tc_debug_pair_mode(1))
+    try:
+        _pair_fusions(lib)
+    finally:
+        L.ddnm_tc_debug_pair_mode(-1)
+
+
+def _pair_fusions(lib):
+    N, H, W, Cin, Cout = 8, 64, 64, 64, 128
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    assert_close(_conv_tc(lib, x, w, b, up2=True), _conv_ref(x, w, b, up2=True), 1e-4, 5e-5, "pair: upsample conv (four parity phases)")
+    N, H, W = 4, 128, 128
+    x = torch.randn(N, Cin, H, W, device=dev)
+    res = torch.randn(N, Cout, H, W, device=dev)
+    side = torch.randn(N, 128, H, W, device=dev)
+    sw = torch.randn(Cout, 128, 1, 1, device=dev) / 128 ** 0.5
+    assert_close(_conv_tc(lib, x, w, b, res=res), _conv_ref(x, w, b, res=res), 1e-4, 5e-5, "pair: residual epilogue")
+    assert_close(_conv_tc(lib, x, w, b, side=side, side_w=sw), _conv_ref(x, w, b, side=side, side_w=sw), 1e-4, 5e-5, "pair: 1x1 side input")
+
+
 def test_groupnorm_silu(lib):
     torch.manual_seed(3)
     for (N, H, W, Cc) in [(2, 16, 16, 64), (1, 32, 32, 384), (2, 8, 8, 1024)]:

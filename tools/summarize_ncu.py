@@ -40,7 +40,10 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_th
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg.per_second", "lts__t_bytes.sum",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg"]
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg",
+        # shared-memory side of the tensor pipe: operand wavefronts read by tcgen05.mma, bank reads (MMA operands) / writes (TMA fill)
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed"]
 
 
 def full(src, dst):
