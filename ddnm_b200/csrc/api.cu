@@ -196,8 +196,28 @@ int ddnm_conv_direct(const float* x, int N, int H, int W, int Cin, const float* 
   DDNM_API_END
 }
 
+namespace {
+__device__ __forceinline__ float bench_hash(unsigned long long i, unsigned seed) {   // uniform in [-1, 1)
+  unsigned x = (unsigned)(i * 2654435761ull) ^ seed;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return (float)(int)x * (1.0f / 2147483648.0f);
+}
+__global__ void bench_fill_f32(float* p, long long n, unsigned seed) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = bench_hash(i, seed);
+}
+__global__ void bench_fill_split(__half* hi, __half* lo, long long n, unsigned seed, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) split_f16(bench_hash(i, seed) * scale, hi[i], lo[i]);
+}
+}  // namespace
+
+// iters > 0: all-zero operands (no data-dependent switching power: the kernel's clock-for-clock pace);
+// iters < 0: |iters| iterations on pseudo-random operands (what the kernel sustains under the board's power cap)
 int ddnm_conv_tc_bench(int N, int H, int W, int Cin, int Cout, int mode, int iters, float* ms_per_iter, double* flops) {
   DDNM_API_BEGIN
+  const bool random = iters < 0;
+  if (random) iters = -iters;
   Tmp tmp;
   const int taps = mode == TAPS_1X1 ? 1 : 9;
   const size_t pe = (size_t)N * H * W * Cin;
@@ -205,12 +225,17 @@ int ddnm_conv_tc_bench(int N, int H, int W, int Cin, int Cout, int mode, int ite
   A.hi = tmp.get<__half>(pe); A.lo = tmp.get<__half>(pe); A.N = N; A.H = H; A.W = W; A.C = Cin;
   float* xf = tmp.get<float>(pe);
   CUDA_CHECK(cudaMemset(xf, 0, pe * 4));
+  if (random) bench_fill_f32<<<(unsigned)cdivll((long long)pe, 256), 256>>>(xf, (long long)pe, 0x1234u);
   gn_apply_split(mkview(xf, N, H, W, Cin), 1, false, nullptr, nullptr, 0.f, false, SPLIT_SAME, A.hi, A.lo, 0);
   const int ktot = taps * Cin;
   __half* wh = tmp.get<__half>((size_t)Cout * ktot);
   __half* wl = tmp.get<__half>((size_t)Cout * ktot);
   CUDA_CHECK(cudaMemset(wh, 0, (size_t)Cout * ktot * 2));
   CUDA_CHECK(cudaMemset(wl, 0, (size_t)Cout * ktot * 2));
+  if (random) {
+    const long long wn = (long long)Cout * ktot;
+    bench_fill_split<<<(unsigned)cdivll(wn, 256), 256>>>(wh, wl, wn, 0x9876u, 1.0f / sqrtf((float)ktot));
+  }
   float* o = tmp.get<float>((size_t)N * H * W * Cout);
   TcLaunch L = tc_make_launch(A, mode, nullptr, wh, wl, 1, Cout, mkview(o, N, H, W, Cout), nullptr, 0, nullptr, 0, 1.0f, sm_count());
   for (int i = 0; i < 3; ++i) tc_run(L, 0);
@@ -249,6 +274,11 @@ int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const
 int ddnm_tc_debug_pair_mode(int mode) {
   DDNM_API_BEGIN
   tc_debug_pair_mode(mode);
+  DDNM_API_END
+}
+int ddnm_tc_debug_dual_mode(int mode) {
+  DDNM_API_BEGIN
+  tc_debug_dual_mode(mode);
   DDNM_API_END
 }
 int ddnm_tc_debug_force_bn(int bn) {

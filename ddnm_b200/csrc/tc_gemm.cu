@@ -26,22 +26,28 @@ static constexpr int A_PLANE_BYTES = BM * BK * 2;  // 16 KiB
 // HALF of the B tile (BN/2 weight rows), the leader CTA issues the MMAs for both, every CTA drains its own 128 TMEM lanes.
 // Per MMA a CTA's shared memory now serves 128 + BN/2 operand rows instead of 128 + BN, which is what lets the Cout = 128
 // layers (BN = 128, the bulk of the celeba network) run the tensor pipe past the ~76 % the single-CTA form reaches.
-template <int BN, bool PAIR>
+// DUAL (single-CTA, BN <= 128): two partial accumulators per TMEM stage, columns [0, BN) and [BN, 2BN), summed by the epilogue.
+// It lets hi*hi and hi*lo ride ONE N = 2*BN instruction (the hi and lo planes of the B tile are adjacent in shared memory, so
+// a single descriptor spans both): per 16-deep k-step the A_hi rows are read once instead of twice and 2 instructions are
+// issued instead of 3.
+template <int BN, bool PAIR, bool DUAL = false>
 struct TcCfg {
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;       // B rows staged by one CTA
   static constexpr int B_PLANE_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
   static constexpr int STAGES = STAGE_BYTES <= 48 * 1024 ? 4 : (STAGE_BYTES <= 64 * 1024 ? 3 : 2);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int ACC_COLS = DUAL ? 2 * BN : BN;    // TMEM columns of one accumulator stage
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static_assert(TMEM_COLS <= 512 && !(PAIR && DUAL), "TMEM capacity / unsupported combination");
 };
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool DUAL>
 __global__ void __launch_bounds__(320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant__ CUtensorMap tm_a0l,
                const __grid_constant__ CUtensorMap tm_a1h, const __grid_constant__ CUtensorMap tm_a1l,
                const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bl, const TcParams p) {
-  using Cfg = TcCfg<BN, PAIR>;
+  using Cfg = TcCfg<BN, PAIR, DUAL>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -191,7 +197,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
       for (int u = unit_begin; u < unit_end; u += unit_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
+        // DUAL: instruction descriptor of the N = 2*BN product A_hi x [B_hi; B_lo]
+        const uint32_t idesc_wide = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -204,10 +212,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint32_t adv = 2u * k;  // 16 fp16 = 32 bytes = 2 x 16-byte units inside the swizzle row
-            mma(d_tmem, hi | (ah + adv), hi | (bh + adv), (uint32_t)((kb | k) != 0));
-            if (p.terms != 1) {
-              mma(d_tmem, hi | (ah + adv), hi | (bl + adv), 1u);
-              mma(d_tmem, hi | (al + adv), hi | (bh + adv), 1u);
+            if (DUAL && p.terms != 1) {
+              // columns [0,BN) += A_hi*B_hi, [BN,2BN) += A_hi*B_lo in one instruction; then [0,BN) += A_lo*B_hi
+              umma_f16(d_tmem, hi | (ah + adv), hi | (bh + adv), idesc_wide, (uint32_t)((kb | k) != 0));
+              umma_f16(d_tmem, hi | (al + adv), hi | (bh + adv), p.idesc, 1u);
+            } else {
+              mma(d_tmem, hi | (ah + adv), hi | (bh + adv), (uint32_t)((kb | k) != 0));
+              if (p.terms != 1) {
+                mma(d_tmem, hi | (ah + adv), hi | (bl + adv), 1u);
+                mma(d_tmem, hi | (al + adv), hi | (bh + adv), 1u);
+              }
             }
           }
           commit(empty_bar(stage));  // smem slot (of both CTAs) reusable once these MMAs have read it
@@ -266,7 +280,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
       const float* crow = p.chanadd ? p.chanadd + (long long)n * p.ca_ld + n_idx * BN : nullptr;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN;
+      const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * Cfg::ACC_COLS;
+      const bool dual_sum = DUAL && p.terms != 1;
 #pragma unroll 1
       for (int c0 = chalf * CW; c0 < (chalf + 1) * CW; c0 += 32) {
         // operands of the epilogue first (all loads in flight together, none ordered behind a store), then the accumulators
@@ -301,6 +316,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
         uint32_t v[32];
         tmem_ld32(t0 + c0, v);
         tmem_ld_wait();
+        if (dual_sum) {   // add the hi*lo partial sums kept in the stage's second half
+          uint32_t v2[32];
+          tmem_ld32(t0 + BN + c0, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        }
         float ov[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -430,11 +452,13 @@ void tc_set_terms(int terms) {
 }
 int tc_get_terms() { return g_terms; }
 static int g_pair_mode = -1;   // -1: cost model decides (default), 0: never, 1: CTA pairs wherever legal
-static double g_pair_tkb[2] = {940.0, 1560.0};   // modelled clocks per k-block of the pair kernel at BN = 128 / 256
+static double g_pair_tkb[2] = {1300.0, 1770.0};   // clocks per k-block of the pair kernel at BN = 128 / 256 (sweep)
 void tc_debug_pair_mode(int mode) {
   DDNM_CHECK(mode == -1 || mode == 0 || mode == 1, "pair mode must be -1 (cost model), 0 (off) or 1 (wherever legal)");
   g_pair_mode = mode;
 }
+static int g_dual_mode = 1;   // 1: single-CTA launches with BN <= 128 use the DUAL kernel (default), 0: never
+void tc_debug_dual_mode(int mode) { g_dual_mode = mode; }
 static int g_force_bn = 0;
 void tc_debug_force_bn(int bn) {
   DDNM_CHECK(bn == 0 || bn == 64 || bn == 128 || bn == 256, "BN must be 0 (heuristic), 64, 128 or 256");
@@ -472,8 +496,11 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
     const int kblocks = taps * (src0.C / BK) + (src1 ? src1->C / BK : 0);
     struct Cand { int bn; bool pair; double t_kb; };
-    // clocks per k-block (measured single-CTA: 1000 / 1130 / 2100; pairs: see the sweep)
-    const Cand cands[] = {{64, false, 1000.0}, {128, false, 1130.0}, {256, false, 2100.0}, {128, true, g_pair_tkb[0]}, {256, true, g_pair_tkb[1]}};
+    // clocks per k-block from the sweep (zero operands, 1.9 GHz): single-CTA 64 / 128 run the DUAL form (two instructions per
+    // k-step), 256 the three-instruction form; pairs pay off only at BN = 256 (at BN = 128 they match the single-CTA pace on zeros
+    // and lose 14 % on real data under the power cap)
+    const Cand cands[] = {{64, false, 1000.0}, {128, false, g_dual_mode ? 1000.0 : 1100.0}, {256, false, 2060.0},
+                          {128, true, g_pair_tkb[0]}, {256, true, g_pair_tkb[1]}};
     double best = 1e300;
     L.BN = 64;
     L.pair = false;
@@ -494,6 +521,7 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
       }
     }
   }
+  L.dual = g_dual_mode != 0 && !L.pair && L.BN <= 128;
   p.n_tiles = Cout / L.BN;
   p.mode0 = mode0;
   p.cb0 = src0.C / BK;
@@ -573,13 +601,10 @@ TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, 
   p.bw = 128; p.bh = 1; p.bn = 1;
   p.tiles_x = M / 128; p.tiles_y = heads; p.tiles_n = images;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  // same sweep as the convolutions: BN = 128 beats 64 (fewer, larger instructions) unless it leaves most SMs idle
   L.BN = 64;
-  for (int bn : {256, 128}) {
-    if (N % bn == 0 && (long long)m_tiles * (N / bn) >= num_sms) {
-      L.BN = bn;
-      break;
-    }
-  }
+  if (N % 128 == 0 && (long long)m_tiles * (N / 128) >= num_sms / 2) L.BN = 128;
+  L.dual = g_dual_mode != 0;
   p.n_tiles = N / L.BN;
   p.mode0 = TAPS_1X1;
   p.cb0 = K / BK; p.kb0 = K / BK; p.kb1 = 0;
@@ -611,12 +636,12 @@ TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, 
   return L;
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool DUAL>
 static void launch_bn(const TcLaunch& L, cudaStream_t stream) {
-  using Cfg = TcCfg<BN, PAIR>;
+  using Cfg = TcCfg<BN, PAIR, DUAL>;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, PAIR, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   if (PAIR) {
@@ -632,9 +657,9 @@ static void launch_bn(const TcLaunch& L, cudaStream_t stream) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, PAIR>, L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.p));
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, PAIR, DUAL>, L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.p));
   } else {
-    conv_tc_kernel<BN, PAIR><<<L.grid, 320, Cfg::SMEM_BYTES, stream>>>(L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.p);
+    conv_tc_kernel<BN, PAIR, DUAL><<<L.grid, 320, Cfg::SMEM_BYTES, stream>>>(L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.p);
   }
   CUDA_CHECK(cudaGetLastError());
 }
@@ -642,14 +667,18 @@ static void launch_bn(const TcLaunch& L, cudaStream_t stream) {
 void tc_run(const TcLaunch& L, cudaStream_t stream) {
   switch (L.BN) {
     case 256:
-      if (L.pair) launch_bn<256, true>(L, stream);
-      else launch_bn<256, false>(L, stream);
+      if (L.pair) launch_bn<256, true, false>(L, stream);
+      else launch_bn<256, false, false>(L, stream);
       break;
     case 128:
-      if (L.pair) launch_bn<128, true>(L, stream);
-      else launch_bn<128, false>(L, stream);
+      if (L.pair) launch_bn<128, true, false>(L, stream);
+      else if (L.dual) launch_bn<128, false, true>(L, stream);
+      else launch_bn<128, false, false>(L, stream);
       break;
-    case 64: launch_bn<64, false>(L, stream); break;
+    case 64:
+      if (L.dual) launch_bn<64, false, true>(L, stream);
+      else launch_bn<64, false, false>(L, stream);
+      break;
     default: throw Error("bad BN");
   }
 }

@@ -168,12 +168,15 @@ int ddnm_conv_tc(const float* x, int N, int H, int W, int Cin, const float* w, c
                  const float* side_x, int CinSide, const float* side_w, const float* residual, float* out, void* stream);
 int ddnm_conv_direct(const float* x, int N, int H, int W, int Cin, const float* w, const float* bias, int Cout, int mode, int up2,
                      float* out, void* stream);
+/* iters > 0: all-zero operands; iters < 0: |iters| iterations on pseudo-random operands (power-realistic) */
 int ddnm_conv_tc_bench(int N, int H, int W, int Cin, int Cout, int mode, int iters, float* ms_per_iter, double* flops);
 int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const float* gamma, const float* beta, float eps,
                    int silu, float* out, void* stream);
 int ddnm_tc_debug_override(unsigned desc_hi, unsigned idesc_xor);
 /* tuning experiments: force the N-tile width of conv launches built afterwards (0 = heuristic) */
 int ddnm_tc_debug_force_bn(int bn);
+/* 1 (default): single-CTA launches with BN <= 128 issue hi*hi and hi*lo as one N = 2*BN instruction (two partial accumulators); 0: never */
+int ddnm_tc_debug_dual_mode(int mode);
 /* CTA-pair kernel (tcgen05 cta_group::2) for conv launches built afterwards: -1 (default) the cost model decides,
  * 0 never, 1 wherever legal */
 int ddnm_tc_debug_pair_mode(int mode);

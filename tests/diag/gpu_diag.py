@@ -135,25 +135,33 @@ def group_bn_sweep():
               (16, 128, 128, 128, 128, 0), (16, 128, 128, 256, 128, 0), (16, 256, 256, 256, 128, 0),
               (8, 8, 8, 1024, 1024, 0), (8, 8, 8, 2048, 1024, 0), (8, 16, 16, 1024, 1024, 0), (8, 16, 16, 2048, 1024, 0),
               (8, 32, 32, 512, 512, 0), (8, 32, 32, 1024, 512, 0), (8, 64, 64, 512, 512, 0), (8, 128, 128, 256, 256, 0)]
-    def run(bn, pair):
+    def run(bn, pair, dual, iters):
         _lib.check(L.ddnm_tc_debug_force_bn(bn))
         _lib.check(L.ddnm_tc_debug_pair_mode(pair))
-        _lib.check(L.ddnm_conv_tc_bench(N, H, W, Cin, Cout, mode, 20, C.byref(ms), C.byref(fl)))
+        _lib.check(L.ddnm_tc_debug_dual_mode(dual))
+        _lib.check(L.ddnm_conv_tc_bench(N, H, W, Cin, Cout, mode, iters, C.byref(ms), C.byref(fl)))
         return ms.value * 1e3
 
-    print("[bn_sweep] us per launch: single BN64 / BN128 / BN256 | pair BN128 / BN256 | cost model's choice", flush=True)
+    key = {(16, 256, 256, 256, 128, 0), (16, 128, 128, 256, 128, 0), (16, 64, 64, 512, 256, 0), (16, 16, 16, 512, 512, 0),
+           (8, 128, 128, 256, 256, 0), (8, 64, 64, 512, 512, 0)}
+    print("[bn_sweep] us per launch: single BN64 / BN128 / BN256 | dual BN64 / BN128 | pair BN128 / BN256 | cost model's choice", flush=True)
     for (N, H, W, Cin, Cout, mode) in shapes:
         m_tiles = N * H * W // 128
-        row = []
-        for bn, pair in ((64, 0), (128, 0), (256, 0), (128, 1), (256, 1)):
-            if Cout % bn or (pair and m_tiles % 2):
-                row.append("   -   ")
+        for label, iters in (("zeros ", 20), ("random", -20)):
+            if label == "random" and (N, H, W, Cin, Cout, mode) not in key:
                 continue
-            row.append(f"{run(bn, pair):7.1f}")
-        model = run(0, -1)
-        print(f"[bn_sweep] N{N} {H}x{W} {Cin}->{Cout} mode{mode}: {' '.join(row[:3])} | {' '.join(row[3:])} | {model:7.1f}", flush=True)
+            row = []
+            for bn, pair, dual in ((64, 0, 0), (128, 0, 0), (256, 0, 0), (64, 0, 1), (128, 0, 1), (128, 1, 0), (256, 1, 0)):
+                if Cout % bn or (pair and m_tiles % 2):
+                    row.append("   -   ")
+                    continue
+                row.append(f"{run(bn, pair, dual, iters):7.1f}")
+            model = run(0, -1, 1, iters)
+            print(f"[bn_sweep] {label} N{N} {H}x{W} {Cin}->{Cout} mode{mode}: {' '.join(row[:3])} | {' '.join(row[3:5])} | {' '.join(row[5:])} | {model:7.1f}",
+                  flush=True)
     _lib.check(L.ddnm_tc_debug_force_bn(0))
     _lib.check(L.ddnm_tc_debug_pair_mode(-1))
+    _lib.check(L.ddnm_tc_debug_dual_mode(1))
 
 
 def _cfg_ns(cfg):

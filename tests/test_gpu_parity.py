@@ -107,8 +107,33 @@ def test_tc_conv_cta_pair_vs_fp64_and_single_cta(lib, shape):
     finally:
         L.ddnm_tc_debug_pair_mode(-1)
     torch.cuda.synchronize()
-    assert_close(pair, single, 1e-6, 1e-6, f"pair vs single-CTA {shape}")
+    assert_close(pair, single, 2e-5, 1e-5, f"pair vs single-CTA {shape}")   # same products, sums re-associated
     assert_close(pair, _conv_ref(x, w, b, mode=mode), rtol=1e-4, atol=5e-5, what=f"pair conv {shape}")
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 128, 128, 0), (1, 64, 64, 128, 256, 0), (3, 8, 8, 128, 64, 0), (2, 64, 64, 192, 128, 1)], ids=str)
+def test_tc_conv_dual_accumulator_vs_three_instruction_form(lib, shape):
+    """DUAL kernel (hi*hi and hi*lo issued as one N = 2*BN instruction, partial sums added in the epilogue) against the plain
+    three-instruction form: the same products, two fp32 additions re-associated."""
+    N, H, W, Cin, Cout, mode = shape
+    torch.manual_seed(7)
+    k = 1 if mode == 1 else 3
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, k, k, device=dev) / (k * k * Cin) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    L = lib.lib()
+    try:
+        lib.check(L.ddnm_tc_debug_dual_mode(0))
+        lib.check(L.ddnm_tc_debug_pair_mode(0))
+        plain = _conv_tc(lib, x, w, b, mode=mode).clone()
+        lib.check(L.ddnm_tc_debug_dual_mode(1))
+        dual = _conv_tc(lib, x, w, b, mode=mode)
+    finally:
+        L.ddnm_tc_debug_dual_mode(1)
+        L.ddnm_tc_debug_pair_mode(-1)
+    torch.cuda.synchronize()
+    assert_close(dual, plain, 2e-5, 1e-5, f"dual vs plain {shape}")
+    assert_close(dual, _conv_ref(x, w, b, mode=mode), rtol=1e-4, atol=5e-5, what=f"dual conv {shape}")
 
 
 def test_tc_conv_cta_pair_fusions(lib):
