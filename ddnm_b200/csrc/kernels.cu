@@ -93,19 +93,31 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
                                 __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ out32,
                                 const float* __restrict__ ss, int ss_ld, __half* __restrict__ raw_hi,
                                 __half* __restrict__ raw_lo) {
-  __shared__ float sc[MAX_C], sh[MAX_C];
+  // dynamic smem: [2*C] doubles (the image's per-channel sums, staged with ONE independent load per channel) then sc[C], sh[C].
+  // (Summing a group's sums straight from global memory made every thread walk a chain of 2*cpg dependent-issue loads,
+  // ~10-16 us of latency in front of every CTA's first pixel.)
+  extern __shared__ double gn_smem[];
+  double* sd = gn_smem;
+  float* sc = reinterpret_cast<float*>(gn_smem + 2 * (size_t)C);
+  float* sh = sc + C;
   const int n = blockIdx.y;
   const int HW = H * W;
   if (stats) {
     const int cpg = C / groups;
     const double cnt = (double)HW * cpg;
+    const double2* gsrc = reinterpret_cast<const double2*>(stats + (size_t)n * st_ld * 2);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const int g = c / cpg;
-      const double* gs = stats + ((size_t)n * st_ld + (size_t)g * cpg) * 2;   // the group's channels are adjacent
+      const double2 v = gsrc[c];
+      sd[2 * c] = v.x;
+      sd[2 * c + 1] = v.y;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g0 = (c / cpg) * cpg;   // the group's channels are adjacent
       double s1 = 0, s2 = 0;
       for (int j = 0; j < cpg; ++j) {
-        s1 += gs[2 * j];
-        s2 += gs[2 * j + 1];
+        s1 += sd[2 * (g0 + j)];
+        s2 += sd[2 * (g0 + j) + 1];
       }
       const double mean = s1 / cnt;
       double var = s2 / cnt - mean * mean;
@@ -241,11 +253,12 @@ static void gn_apply_launch(const View& x, int groups, bool normalise, const flo
   long long want = cdivll((long long)HW * x.N, 148 * 8);
   int ppc = (int)std::max<long long>(rows, cdivll(want, rows) * rows);
   dim3 grid(cdiv(HW, ppc), x.N);
+  const size_t smem = (size_t)x.C * 24;   // 2 doubles + 2 floats per channel (<= 48 KiB at MAX_C)
   if (out32)
-    gn_apply_kernel<true><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, x.st_ld, gamma, beta, eps, silu, mode,
+    gn_apply_kernel<true><<<grid, threads, smem, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, x.st_ld, gamma, beta, eps, silu, mode,
                                                  ppc, nullptr, nullptr, out32, ss, ss_ld, nullptr, nullptr);
   else
-    gn_apply_kernel<false><<<grid, threads, 0, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, x.st_ld, gamma, beta, eps, silu, mode,
+    gn_apply_kernel<false><<<grid, threads, smem, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, x.st_ld, gamma, beta, eps, silu, mode,
                                                   ppc, hi, lo, nullptr, ss, ss_ld, raw_hi, raw_lo);
   CUDA_CHECK(cudaGetLastError());
 }
@@ -331,6 +344,7 @@ void conv3x3_small_cin(const float* x, int Cin, const float* w, const float* bia
 // reading each weight row exactly once with 16-byte loads and reusing it for every image of the batch.
 constexpr int LIN_NB = 16;    // images per accumulator pass
 constexpr int LIN_OPW = 8;    // output features per warp
+constexpr int LIN_WREG = 8;   // float4 weight registers per lane loaded ahead (K <= 1024 in one go)
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, int N, int K, const float* __restrict__ W,
                                                      const float* __restrict__ bias, int O, float* __restrict__ out, int ldo,
                                                      int act_in, int act_out) {
@@ -352,13 +366,25 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ i
       float acc[LIN_NB];
 #pragma unroll
       for (int j = 0; j < LIN_NB; ++j) acc[j] = 0.f;
-      for (int k4 = lane; k4 < K4; k4 += 32) {
-        const float4 wv = __ldg(w4 + k4);
+      // the whole weight row first (independent loads, one latency), then the products
+      for (int kbase = 0; kbase < K4; kbase += 32 * LIN_WREG) {
+        float4 wv[LIN_WREG];
 #pragma unroll
-        for (int j = 0; j < LIN_NB; ++j) {
-          if (n0 + j < N) {
-            const float4 v = reinterpret_cast<const float4*>(lin_in + (long long)(n0 + j) * K)[k4];
-            acc[j] = fmaf(v.x, wv.x, fmaf(v.y, wv.y, fmaf(v.z, wv.z, fmaf(v.w, wv.w, acc[j]))));
+        for (int i = 0; i < LIN_WREG; ++i) {
+          const int k4 = kbase + lane + 32 * i;
+          wv[i] = k4 < K4 ? __ldg(w4 + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < LIN_WREG; ++i) {
+          const int k4 = kbase + lane + 32 * i;
+          if (k4 < K4) {
+#pragma unroll
+            for (int j = 0; j < LIN_NB; ++j) {
+              if (n0 + j < N) {
+                const float4 v = reinterpret_cast<const float4*>(lin_in + (long long)(n0 + j) * K)[k4];
+                acc[j] = fmaf(v.x, wv[i].x, fmaf(v.y, wv[i].y, fmaf(v.z, wv[i].z, fmaf(v.w, wv[i].w, acc[j]))));
+              }
+            }
           }
         }
       }

@@ -14,6 +14,10 @@
 //
 // CTA = 10 warps: warp 0 TMA producer, warp 1 UMMA issuer (+TMEM owner), warps 2-9 epilogue (TMEM -> regs -> HBM).
 // Persistent over output tiles; two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Three instantiations (picked per layer by the cost model in tc_make_launch, constants from profiles/r01_bn_sweep.md):
+//   <BN, false, false>  three instructions per k-step (hi*hi, hi*lo, lo*hi) into one accumulator;
+//   <BN, false, true>   DUAL: A_hi x [B_hi; B_lo] as one N = 2*BN instruction + A_lo x B_hi, two partial accumulators;
+//   <BN, true,  false>  PAIR: cluster of two CTAs, 256-row tcgen05.mma.cta_group::2, each CTA stages half of the B tile.
 #include "tc_gemm.cuh"
 
 namespace ddnm {
