@@ -210,3 +210,58 @@ def test_restore_batch_matches_oracle_composition(gold, tmp_path):
         for pat, key in (("{}_0.png", "images"), ("Apy/Apy_{}.png", "Apy"), ("Apy/orig_{}.png", "orig")):
             blob = (tmp_path / pat.format(7 + i)).read_bytes()
             assert np.array_equal(R.decode_png(blob), out[key][i])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("deg,opname,sigma_y", [("colorization", "color", 0.0), ("deblur_gauss", "deblur", 0.0), ("inpainting", "inpaint", 0.1)])
+def test_restore_batch_preview_branches_and_noisy_path(gold, deg, opname, sigma_y):
+    """The runner's per-degradation preview rules (diffusion.py:558-564: deblur shows y, colorization the repeated gray image,
+    inpainting adds A^+A(1) - 1) and its noise / DDNM+ switch (:550-551, :587-590), against the oracle composition.  The noise
+    added to y is drawn on the device, so the oracle replays the engine's own y."""
+    from oracle import sampler as S, schedule as SCH, unet_simple as U
+    from ddnm_b200 import runner as R
+    from ddnm_b200.model import Model
+    from helpers import engine_op, model_config, oracle_ops, sampler_config
+    cfg = U.SimpleUNetConfig.tiny()
+    sd = U.init_state_dict(cfg, 1234)
+    res = cfg.resolution
+    T = 4
+    conf = sampler_config(T, 1, 1)
+    conf.data = _cfg(True, False, channels=3, size=res).data
+    oop = oracle_ops(gold["operators"], 32)[opname]
+    eop = engine_op(opname, oop, 32)
+    mdl = Model(model_config(cfg))
+    mdl.load_state_dict(sd)
+    rng = torch.Generator().manual_seed(21)
+    x01 = torch.rand(2, 3, res, res, generator=rng)
+    x_T = torch.randn(2, 3, res, res, generator=rng)
+    npairs = len(SCH.time_pairs(1000, T, 1, 1))
+    tape = [torch.randn(2, 3, res, res, generator=rng) for _ in range(npairs)]
+    betas = SCH.linear_betas()
+    out = R.restore_batch(conf, mdl, eop, deg, x01, betas.cuda(), 0.85, sigma_y=sigma_y, add_noise=sigma_y > 0, x_T=x_T.cuda(),
+                          noise=torch.stack(tape).cuda())
+    xo = RIO.data_transform(x01, True, False)
+    y_clean = oop.A(xo.reshape(2, -1))
+    y = out["y"].cpu()
+    if sigma_y == 0:
+        assert_close(y, y_clean, 1e-5, 2e-6, "y")
+    else:   # y = A x + sigma_y * N(0, 1): right scale, and not the clean signal
+        d = (y - y_clean) / sigma_y
+        assert 0.8 < d.std().item() < 1.2 and abs(d.mean().item()) < 0.1
+    with torch.no_grad():
+        ox, _ = S.ddnm_sample(x_T, lambda a, b: U.forward(sd, a, b, cfg), betas, 0.85, oop, y, tape, t_sampling=T, travel_length=1,
+                              travel_repeat=1, sigma_y=sigma_y)
+    inv, orig = RIO.inverse_data_transform(ox, True, False), RIO.inverse_data_transform(xo, True, False)
+    ps = torch.stack([RIO.psnr(inv[j], orig[j]) for j in range(2)])
+    assert_close(out["psnr"], ps, 5e-3, 5e-3, "psnr")
+    assert np.abs(out["images"].astype(int) - RIO.to_uint8_hwc(inv).numpy().astype(int)).max() <= 1
+    # preview image rule of the degradation
+    if deg[:6] == "deblur":
+        apy = y.view(2, 3, res, res)
+    elif deg == "colorization":
+        apy = y.view(2, 1, res, res).repeat(1, 3, 1, 1)
+    else:
+        apy = oop.A_pinv(y).view(2, 3, res, res)
+        apy = apy + oop.A_pinv(oop.A(torch.ones_like(apy).reshape(2, -1))).reshape(apy.shape) - 1
+    want = RIO.to_uint8_hwc(RIO.inverse_data_transform(apy, True, False)).numpy()
+    assert np.abs(out["Apy"].astype(int) - want.astype(int)).max() <= 1
