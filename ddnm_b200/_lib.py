@@ -21,7 +21,7 @@ class OpenAICfg(C.Structure):
     _fields_ = [("image_size", C.c_int), ("model_channels", C.c_int), ("num_res_blocks", C.c_int), ("n_levels", C.c_int),
                 ("channel_mult", C.c_int * 8), ("n_attn_ds", C.c_int), ("attn_ds", C.c_int * 4),
                 ("num_head_channels", C.c_int), ("out_channels", C.c_int), ("in_channels", C.c_int), ("groups", C.c_int),
-                ("eps", C.c_float)]
+                ("eps", C.c_float), ("num_classes", C.c_int)]
 
 
 class OperatorDesc(C.Structure):
@@ -44,6 +44,9 @@ class Schedule(C.Structure):
 _lib = None
 
 _P, _I, _LL, _F, _D = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+# classifier-guidance callback of ddnm_sample_guided: (user, pair_index, t, stream) -> 0 on success
+GuidanceFn = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p)
+
 _SIGS = {
     "ddnm_version": (C.c_int, []),
     "ddnm_unet_simple_create": (C.c_int, [C.POINTER(SimpleCfg), _I, C.POINTER(_P)]),
@@ -52,6 +55,7 @@ _SIGS = {
     "ddnm_unet_set_precision": (C.c_int, [_P, _I]),
     "ddnm_unet_finalize": (C.c_int, [_P]),
     "ddnm_unet_forward": (C.c_int, [_P, _P, _P, _P, _P]),
+    "ddnm_unet_forward_cond": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ddnm_unet_set_graph": (C.c_int, [_P, _I]),
     "ddnm_unet_read_tap": (C.c_int, [_P, C.c_char_p, _P, _LL, _P]),
     "ddnm_unet_info": (C.c_int, [_P, C.POINTER(_LL), C.POINTER(_I), C.POINTER(_D)]),
@@ -66,6 +70,7 @@ _SIGS = {
     "ddnm_operator_lambda_noise": (C.c_int, [_P, _P, _P, _I, _F, _F, _F, _F, _P, _P]),
     "ddnm_operator_destroy": (C.c_int, [_P]),
     "ddnm_sample": (C.c_int, [_P, _P, C.POINTER(Schedule), _P, _P, _P, _I, _P, _P, _P]),
+    "ddnm_sample_guided": (C.c_int, [_P, _P, C.POINTER(Schedule), _P, _P, _P, _I, _P, _P, GuidanceFn, _P, _P, _P, _P]),
     "ddnm_simplified_A": (C.c_int, [C.POINTER(SimpleDeg), _P, _I, _P, _P]),
     "ddnm_simplified_Ap": (C.c_int, [C.POINTER(SimpleDeg), _P, _I, _P, _P]),
     "ddnm_sample_simplified": (C.c_int, [_P, C.POINTER(SimpleDeg), C.POINTER(Schedule), _P, _P, _P, _I, _P, _P, _P]),

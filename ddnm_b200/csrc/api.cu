@@ -47,7 +47,8 @@ int ddnm_unet_openai_create(const ddnm_openai_cfg* c, int batch, void** handle) 
   cfg.n_attn_ds = c->n_attn_ds;
   for (int i = 0; i < 4; ++i) cfg.attn_ds[i] = c->attn_ds[i];
   cfg.num_head_channels = c->num_head_channels; cfg.out_channels = c->out_channels; cfg.in_channels = c->in_channels;
-  cfg.groups = c->groups; cfg.eps = c->eps;
+  cfg.groups = c->groups; cfg.eps = c->eps; cfg.num_classes = c->num_classes;
+  DDNM_CHECK(c->num_classes >= 0, "bad num_classes");
   *handle = static_cast<UNetEngine*>(new UNetOpenAI(cfg, batch));
   DDNM_API_END
 }
@@ -65,6 +66,13 @@ int ddnm_unet_finalize(void* h) {
 int ddnm_unet_forward(void* h, const float* x, const float* t, float* out, void* stream) {
   DDNM_API_BEGIN
   static_cast<UNetEngine*>(h)->forward(x, t, out, (cudaStream_t)stream);
+  DDNM_API_END
+}
+int ddnm_unet_forward_cond(void* h, const float* x, const float* t, const int* labels, float* out, void* stream) {
+  DDNM_API_BEGIN
+  UNetEngine* u = static_cast<UNetEngine*>(h);
+  u->set_labels(labels, (cudaStream_t)stream);
+  u->forward(x, t, out, (cudaStream_t)stream);
   DDNM_API_END
 }
 int ddnm_unet_set_precision(void* h, int fp16_terms) {

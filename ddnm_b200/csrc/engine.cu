@@ -171,6 +171,8 @@ void UNetEngine::alloc_common(size_t split_elems, size_t hbuf_elems) {
   hbuf_ = (float*)arena_.alloc(hbuf_elems * 4);
   x_in_ = (float*)arena_.alloc((size_t)B_ * in_ch_ * R_ * R_ * 4);
   t_in_ = (float*)arena_.alloc((size_t)B_ * 4);
+  labels_in_ = (int*)arena_.alloc((size_t)B_ * 4);
+  CUDA_CHECK(cudaMemset(labels_in_, 0, (size_t)B_ * 4));
   out_ = (float*)arena_.alloc((size_t)B_ * out_ch_ * R_ * R_ * 4);
 }
 
@@ -312,6 +314,12 @@ void UNetEngine::finalize() {
 
 void UNetEngine::run_ops(cudaStream_t s) {
   for (auto& op : ops_) op.run(s);
+}
+
+void UNetEngine::set_labels(const int* labels_dev, cudaStream_t stream) {
+  DDNM_CHECK(class_cond_, "set_labels on a network without a label embedding");
+  DDNM_CHECK(labels_dev != nullptr, "null labels");
+  if (labels_dev != labels_in_) CUDA_CHECK(cudaMemcpyAsync(labels_in_, labels_dev, (size_t)B_ * sizeof(int), cudaMemcpyDeviceToDevice, stream));
 }
 
 void UNetEngine::forward(const float* x, const float* t, float* out, cudaStream_t stream) {

@@ -51,6 +51,7 @@ struct OpenAICfg {
   int num_head_channels = 64;
   int out_channels = 6, in_channels = 3, groups = 32;
   float eps = 1e-5f;
+  int num_classes = 0;   // > 0: class-conditional (label_emb [num_classes, 4*model_channels], unet.py:478-479)
 };
 
 class UNetEngine {
@@ -71,6 +72,10 @@ class UNetEngine {
   int resolution() const { return R_; }
   float* x_in() const { return x_in_; }
   float* t_in() const { return t_in_; }
+  // class labels of the next forward (device int32 [B]); only meaningful for class-conditional networks
+  int* labels_in() const { return labels_in_; }
+  bool class_conditional() const { return class_cond_; }
+  void set_labels(const int* labels_dev, cudaStream_t stream);
   float* out_buf() const { return out_; }
   void set_use_graph(bool on) { use_graph_ = on; }
   // 3 = fp32-grade products (parity mode, default); 1 = single fp16 product per MAC (fast, NOT parity-grade). Before finalize.
@@ -126,6 +131,8 @@ class UNetEngine {
   std::map<std::string, View> taps_;
   // fixed I/O staging (graph replays need stable addresses)
   float *x_in_ = nullptr, *t_in_ = nullptr, *out_ = nullptr;
+  int* labels_in_ = nullptr;
+  bool class_cond_ = false;
   // scratch
   __half *splitA_hi_ = nullptr, *splitA_lo_ = nullptr, *splitB_hi_ = nullptr, *splitB_lo_ = nullptr;
   size_t split_elems_ = 0;

@@ -420,6 +420,23 @@ void linear(const float* in, int N, int K, const float* W, const float* bias, in
   CUDA_CHECK(cudaGetLastError());
 }
 
+__global__ void add_label_swish_kernel(float* __restrict__ v, const float* __restrict__ table, const int* __restrict__ labels, int N,
+                                       int D, int num_classes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * D) return;
+  const int n = i / D, d = i - n * D;
+  const int y = labels[n];
+  if (y < 0 || y >= num_classes) {
+    if (d == 0) printf("ddnm_b200: class label %d of image %d is outside [0, %d)\n", y, n, num_classes);
+    __trap();
+  }
+  v[i] = swishf(v[i] + table[(size_t)y * D + d]);
+}
+void add_label_swish(float* v, const float* table, const int* labels, int N, int D, int num_classes, cudaStream_t st) {
+  add_label_swish_kernel<<<cdiv(N * D, 256), 256, 0, st>>>(v, table, labels, N, D, num_classes);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 __global__ void sinusoid_kernel(const float* __restrict__ t, int N, const float* __restrict__ freq, int dim, int sin_first,
                                 float* __restrict__ emb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

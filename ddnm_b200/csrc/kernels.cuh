@@ -28,6 +28,9 @@ void conv3x3_small_cin(const float* x_nchw, int Cin, const float* w_oihw, const 
 // out[n][o] = act_out( sum_k act_in(in[n][k]) * W[o][k] + bias[o] );  act: 0 none, 1 swish
 void linear(const float* in, int N, int K, const float* W, const float* bias, int O, float* out, int ldo, int act_in,
             int act_out, cudaStream_t s);
+// v[n][d] = swish(v[n][d] + table[labels[n]][d])  (UNetModel.forward: emb + label_emb(y), unet.py:651-653, then the blocks' SiLU);
+// a label outside [0, num_classes) traps (nn.Embedding raises)
+void add_label_swish(float* v, const float* table, const int* labels, int N, int D, int num_classes, cudaStream_t s);
 // emb[n][:] = [sin(t*f) | cos(t*f)] (sin_first) or [cos | sin]; f has dim/2 entries
 void sinusoid(const float* t, int N, const float* freq, int dim, bool sin_first, float* emb, cudaStream_t s);
 

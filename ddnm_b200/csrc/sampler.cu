@@ -22,9 +22,23 @@ __global__ void travel_back_kernel(const float* __restrict__ x0, const float* __
   if (i < n) xn[i] = __fadd_rn(__fmul_rn(sa, x0[i]), __fmul_rn(z[i], s1));
 }
 
+// et[b, 0..2] -= sqrt(1 - at) * grad[b]   (svd_ddnm.py:52, :113: et = et - (1 - at).sqrt()[0,0,0,0] * cls_fn(x, t, classes))
+__global__ void guide_kernel(float* __restrict__ et, long long et_stride, const float* __restrict__ grad, float s1, long long img,
+                             long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long b = i / img, r = i - b * img;
+  float* e = et + b * et_stride + r;
+  *e = __fsub_rn(*e, __fmul_rn(s1, grad[i]));
+}
+
 static void sample(UNetEngine* unet, Operator* op, const ddnm_schedule* sc, const float* x_T, const float* y, const float* noise,
-                   int B, float* out_x0, float* out_x0_pred, cudaStream_t st) {
+                   int B, float* out_x0, float* out_x0_pred, cudaStream_t st, const int* labels = nullptr,
+                   const float* grad_buf = nullptr, ddnm_guidance_fn guide = nullptr, void* user = nullptr) {
   DDNM_CHECK(unet && op && sc && x_T && y && noise && out_x0, "null argument");
+  DDNM_CHECK((labels != nullptr) == unet->class_conditional(), "class labels go with a class-conditional denoiser, and only with one");
+  DDNM_CHECK((guide != nullptr) == (grad_buf != nullptr), "guidance callback and gradient buffer go together");
+  if (labels) unet->set_labels(labels, st);
   DDNM_CHECK(unet->batch() == B, "engine was built for a different batch size");
   const int R = unet->resolution();
   DDNM_CHECK(op->x_dim() == (long long)unet->in_channels() * R * R, "operator / denoiser image size mismatch");
@@ -50,6 +64,13 @@ static void sample(UNetEngine* unet, Operator* op, const ddnm_schedule* sc, cons
       const float at = sc->abar[i + 1];
       fill_kernel<<<cdiv(B, 128), 128, 0, st>>>(unet->t_in(), B, (float)i);
       unet->forward(xt, unet->t_in(), et, st);
+      if (guide) {
+        // the caller fills grad_buf (its classifier's autograd gradient) with work enqueued on this stream
+        const int rc = guide(user, k, i, (void*)st);
+        DDNM_CHECK(rc == 0, "classifier-guidance callback failed");
+        guide_kernel<<<(int)cdivll(n, 256), 256, 0, st>>>(et, et_stride, grad_buf, std::sqrt(1.0f - at), img, n);
+        CUDA_CHECK(cudaGetLastError());
+      }
       StepScalars s{};
       s.sqrt_at = std::sqrt(at);
       s.sqrt_1m_at = std::sqrt(1.0f - at);
@@ -82,5 +103,13 @@ extern "C" int ddnm_sample(void* unet, void* op, const ddnm_schedule* sched, con
   DDNM_API_BEGIN
   sample(static_cast<UNetEngine*>(unet), static_cast<Operator*>(op), sched, x_T, y, noise, B, out_x0, out_x0_pred,
          (cudaStream_t)stream);
+  DDNM_API_END
+}
+extern "C" int ddnm_sample_guided(void* unet, void* op, const ddnm_schedule* sched, const float* x_T, const float* y, const float* noise,
+                                  int B, const int* labels, const float* grad_buf, ddnm_guidance_fn fn, void* user, float* out_x0,
+                                  float* out_x0_pred, void* stream) {
+  DDNM_API_BEGIN
+  sample(static_cast<UNetEngine*>(unet), static_cast<Operator*>(op), sched, x_T, y, noise, B, out_x0, out_x0_pred,
+         (cudaStream_t)stream, labels, grad_buf, fn, user);
   DDNM_API_END
 }

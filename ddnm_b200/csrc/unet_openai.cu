@@ -11,7 +11,9 @@
 namespace ddnm {
 
 UNetOpenAI::UNetOpenAI(const OpenAICfg& cfg, int batch)
-    : UNetEngine(batch, cfg.in_channels, cfg.out_channels, cfg.image_size, cfg.groups, cfg.eps), cfg_(cfg) {}
+    : UNetEngine(batch, cfg.in_channels, cfg.out_channels, cfg.image_size, cfg.groups, cfg.eps), cfg_(cfg) {
+  class_cond_ = cfg.num_classes > 0;
+}
 
 // ResBlock._forward (unet.py:236-256), use_scale_shift_norm = True.
 //   kind DOWN: h = avg_pool(SiLU(GN(x))), x = avg_pool(x);  kind UP: nearest x2 of both (h_upd / x_upd, :170-177)
@@ -189,11 +191,19 @@ void UNetOpenAI::build_program() {
     float *t = t_in_, *emb = emb_, *t0 = temb0_, *t1 = temb_, *fr = freq_, *ss = ss_all_, *W = embW_all_, *Bv = embB_all_;
     const float *w0 = P("time_embed.0.weight", (long long)tdim * mc), *b0 = P("time_embed.0.bias", tdim);
     const float *w1 = P("time_embed.2.weight", (long long)tdim * tdim), *b1 = P("time_embed.2.bias", tdim);
-    const int Bn = B_, mcn = mc, tot = ss_total_;
+    const int Bn = B_, mcn = mc, tot = ss_total_, ncls = cfg_.num_classes;
+    // class-conditional (imagenet_256_cc.yml): emb = time_embed(t) + label_emb(y) (unet.py:651-653) before the blocks' SiLU
+    const float* lab = ncls > 0 ? P("label_emb.weight", (long long)ncls * tdim) : nullptr;
+    const int* labels = labels_in_;
     add_op("time_embed", "temb", 0, 0, [=](cudaStream_t s) {
       sinusoid(t, Bn, fr, mcn, false, emb, s);               // [cos | sin]
       linear(emb, Bn, mcn, w0, b0, tdim, t0, tdim, 0, 1, s);  // SiLU between the two Linears, applied at the producer
-      linear(t0, Bn, tdim, w1, b1, tdim, t1, tdim, 0, 1, s);  // emb is only consumed through emb_layers' SiLU
+      if (lab) {
+        linear(t0, Bn, tdim, w1, b1, tdim, t1, tdim, 0, 0, s);
+        add_label_swish(t1, lab, labels, Bn, tdim, ncls, s);  // t1 = SiLU(emb + label_emb[y])
+      } else {
+        linear(t0, Bn, tdim, w1, b1, tdim, t1, tdim, 0, 1, s);  // emb is only consumed through emb_layers' SiLU
+      }
       linear(t1, Bn, tdim, W, Bv, tot, ss, tot, 0, 0, s);     // emb_layers Linear for all blocks at once
     });
   }

@@ -77,15 +77,23 @@ class _EngineModel:
     def __call__(self, x, t, y=None):
         return self.forward(x, t, y)
 
+    num_classes = None       # class-conditional UNetModel only (unet.py:464)
+
     def forward(self, x, t, y=None):
-        assert y is None, "class-conditional sampling is outside the ddnm_b200 hot path"
+        # unet.py:644-646
+        assert (y is not None) == (self.num_classes is not None), "must specify y if and only if the model is class-conditional"
         assert x.is_cuda and x.dtype == torch.float32, "ddnm_b200 denoisers run on CUDA fp32 tensors"
         assert x.shape[2] == x.shape[3] == self.resolution     # models.py:302
         x = x.contiguous()
         t = t.to(device=x.device, dtype=torch.float32).contiguous()
         out = torch.empty(x.shape[0], self.out_ch, self.resolution, self.resolution, device=x.device, dtype=torch.float32)
         h = self.engine(x.shape[0])
-        _lib.check(_lib.lib().ddnm_unet_forward(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(out), _lib.cur_stream()))
+        if y is None:
+            _lib.check(_lib.lib().ddnm_unet_forward(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(out), _lib.cur_stream()))
+        else:
+            assert y.shape == (x.shape[0],)                     # unet.py:652
+            labels = y.to(device=x.device, dtype=torch.int32).contiguous()
+            _lib.check(_lib.lib().ddnm_unet_forward_cond(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(labels), _lib.ptr(out), _lib.cur_stream()))
         return out
 
     # --- extras ---
@@ -158,14 +166,13 @@ class Model(_EngineModel):
 
 class UNetModel(_EngineModel):
     """guided_diffusion.unet.UNetModel (unet.py:396-664) for the variant the shipped configs build
-    (use_scale_shift_norm, resblock_updown, legacy attention order, no class conditioning)."""
+    (use_scale_shift_norm, resblock_updown, legacy attention order; optional class conditioning: ``model(x, t, y)``)."""
 
     def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
                  dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
                  use_fp16=False, num_heads=1, num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=False,
                  resblock_updown=False, use_new_attention_order=False):
-        if num_classes is not None:
-            raise NotImplementedError("class-conditional UNetModel (imagenet_256_cc.yml) is outside the ddnm_b200 hot path")
+        self.num_classes = None if num_classes is None else int(num_classes)   # label_emb (unet.py:478-479), imagenet_256_cc.yml
         if not (use_scale_shift_norm and resblock_updown) or use_new_attention_order or num_head_channels <= 0 or dims != 2:
             raise NotImplementedError("ddnm_b200 builds the imagenet_256.yml UNetModel variant: use_scale_shift_norm, "
                                       "resblock_updown, legacy attention order, num_head_channels > 0")
@@ -198,6 +205,7 @@ class UNetModel(_EngineModel):
         for i, v in enumerate(self.attention_resolutions):
             c.attn_ds[i] = v
         c.num_head_channels, c.out_channels, c.in_channels, c.groups, c.eps = self.num_head_channels, self.out_ch, self.in_channels, 32, 1e-5
+        c.num_classes = self.num_classes or 0
         h = C.c_void_p()
         _lib.check(_lib.lib().ddnm_unet_openai_create(C.byref(c), batch, C.byref(h)))
         return h

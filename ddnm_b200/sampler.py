@@ -24,8 +24,6 @@ def sample_device(x, model, b, eta, A_funcs, y, sigma_y, plus, config, noise=Non
 
 
 def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, noise=None, to_host=True):
-    if cls_fn is not None:
-        raise NotImplementedError("classifier guidance (imagenet_256_cc.yml) is outside the ddnm_b200 hot path")
     if not isinstance(model, _EngineModel):
         model = getattr(model, "module", model)          # tolerate nn.DataParallel-style wrappers
     if not isinstance(model, _EngineModel) or not isinstance(A_funcs, _Operator):
@@ -59,11 +57,46 @@ def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, n
         s.plus = 1 if plus else 0
         out = torch.empty_like(x)
         x0p = torch.empty_like(x)
-        _lib.check(_lib.lib().ddnm_sample(model.engine(n), A_funcs._h, C.byref(s), _lib.ptr(x), _lib.ptr(yv), _lib.ptr(noise), n,
-                                         _lib.ptr(out), _lib.ptr(x0p), _lib.cur_stream()))
+        if cls_fn is None:
+            _lib.check(_lib.lib().ddnm_sample(model.engine(n), A_funcs._h, C.byref(s), _lib.ptr(x), _lib.ptr(yv), _lib.ptr(noise), n,
+                                             _lib.ptr(out), _lib.ptr(x0p), _lib.cur_stream()))
+        else:
+            _guided(x, model, A_funcs, s, yv, noise, n, cls_fn, out, x0p)
         if not to_host:
             return out, x0p
         return [out.to("cpu")], [x0p.to("cpu")]
+
+
+CLASS_NUM = 951   # functions/svd_ddnm.py:7
+
+
+def _guided(x, model, A_funcs, sched, yv, noise, n, cls_fn, out, x0p):
+    """Classifier-guided loop (svd_ddnm.py:48-52, :109-113).  As in the reference, the caller's ``classes`` are replaced by
+    ``class_num`` for every row, the denoiser is called as ``model(xt, t, classes)``, only channels 0..2 of its output are
+    kept, and ``cls_fn`` is evaluated at ``x`` — the function's INPUT, not the current iterate.  ``cls_fn`` (the classifier's
+    autograd gradient, diffusion.py:181-189) is the caller's PyTorch callable; everything else runs in libddnm_b200.so."""
+    assert model.num_classes is not None, "must specify y if and only if the model is class-conditional"   # unet.py:644-646
+    classes = torch.ones(n, dtype=torch.long, device=x.device) * CLASS_NUM
+    labels = classes.to(torch.int32)
+    grad = torch.empty_like(x)
+    failure = []
+
+    def cb(_user, _k, t, _stream):
+        try:
+            tt = torch.ones(n, device=x.device) * t
+            with torch.enable_grad():
+                g = cls_fn(x, tt, classes)
+            grad.copy_(g.reshape(grad.shape))
+            return 0
+        except BaseException as e:   # noqa: BLE001 — re-raised after the C call returns
+            failure.append(e)
+            return 1
+    fn = _lib.GuidanceFn(cb)
+    rc = _lib.lib().ddnm_sample_guided(model.engine(n), A_funcs._h, C.byref(sched), _lib.ptr(x), _lib.ptr(yv), _lib.ptr(noise), n,
+                                       _lib.ptr(labels), _lib.ptr(grad), fn, None, _lib.ptr(out), _lib.ptr(x0p), _lib.cur_stream())
+    if failure:
+        raise failure[0]
+    _lib.check(rc)
 
 
 def ddnm_diffusion(x, model, b, eta, A_funcs, y, cls_fn=None, classes=None, config=None, noise=None):

@@ -49,6 +49,8 @@ typedef struct {
   int attn_ds[4];             /* image_size // attention resolution, as create_model computes (:163-165) */
   int num_head_channels, out_channels, in_channels, groups;
   float eps;
+  int num_classes;            /* 0 = unconditional; > 0 = class_cond (imagenet_256_cc.yml): label_emb.weight [num_classes, 4*ch],
+                                 emb = time_embed(t) + label_emb(y) (unet.py:478-479, 651-653) */
 } ddnm_openai_cfg;
 int ddnm_unet_openai_create(const ddnm_openai_cfg* cfg, int batch, void** handle);
 /* name = key of Model.state_dict() (models.py:216-299), data = fp32 host or device, reference layout (OIHW);
@@ -61,6 +63,8 @@ int ddnm_unet_set_precision(void* handle, int fp16_terms);
 int ddnm_unet_finalize(void* handle);
 /* x [B,3,R,R] NCHW fp32, t [B] fp32 holding integer timesteps, out [B,out_ch,R,R] NCHW fp32 */
 int ddnm_unet_forward(void* handle, const float* x, const float* t, float* out, void* stream);
+/* class-conditional networks: `model(x, t, y)` (UNetModel.forward(x, timesteps, y), unet.py:635-653); labels = device int32 [B] */
+int ddnm_unet_forward_cond(void* handle, const float* x, const float* t, const int* labels, float* out, void* stream);
 int ddnm_unet_set_graph(void* handle, int use_cuda_graph);
 int ddnm_unet_read_tap(void* handle, const char* name, float* dst_nchw, long long capacity, void* stream);
 int ddnm_unet_info(void* handle, long long* workspace_bytes, int* launches, double* flops_per_forward);
@@ -123,6 +127,17 @@ typedef struct {
  * out_x0 [B,3,R,R] = xs[-1]; out_x0_pred [B,3,R,R] = x0_preds[-1] (may be NULL). */
 int ddnm_sample(void* unet, void* op, const ddnm_schedule* sched, const float* x_T, const float* y, const float* noise, int B,
                 float* out_x0, float* out_x0_pred, void* stream);
+
+/* Class-conditional / classifier-guided sampling (svd_ddnm.py:48-52, :109-113; imagenet_256_cc.yml):
+ *   et = model(xt, t, classes)[:, :3];  et = et - sqrt(1 - at) * cls_fn(x, t, classes)
+ * labels: device int32 [B] handed to the class-conditional denoiser (NULL for an unconditional one).
+ * fn (may be NULL): called on the calling thread once per denoising pair, after the denoiser was enqueued; it must leave
+ * cls_fn's result in grad_buf (device [B,3,R,R]) using work enqueued on `stream` and return 0.  The classifier and its
+ * backward pass stay with the caller (the reference builds them from PyTorch autograd, diffusion.py:181-189). */
+typedef int (*ddnm_guidance_fn)(void* user, int pair_index, int t, void* stream);
+int ddnm_sample_guided(void* unet, void* op, const ddnm_schedule* sched, const float* x_T, const float* y, const float* noise, int B,
+                       const int* labels, const float* grad_buf, ddnm_guidance_fn fn, void* user, float* out_x0, float* out_x0_pred,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * "Simplified" DDNM+ (guided_diffusion/diffusion.py:211-415, the README quick-start path): image-space operators composed

@@ -50,8 +50,13 @@ class cpu_shim:
         self.tape = list(tape)
 
     def __enter__(self):
-        self._to, self._rl = torch.Tensor.to, torch.randn_like
-        orig_to = self._to
+        self._to, self._rl, self._ones = torch.Tensor.to, torch.randn_like, torch.ones
+        orig_to, orig_ones = self._to, self._ones
+
+        def ones(*a, **k):          # svd_ddnm.py:49,110 build the label vector with device=torch.device("cuda")
+            k.pop("device", None)
+            return orig_ones(*a, **k)
+        torch.ones = ones
 
         def to(t, *a, **k):
             if a and isinstance(a[0], str) and a[0].startswith("cuda"):
@@ -68,7 +73,7 @@ class cpu_shim:
         return self
 
     def __exit__(self, *exc):
-        torch.Tensor.to, torch.randn_like = self._to, self._rl
+        torch.Tensor.to, torch.randn_like, torch.ones = self._to, self._rl, self._ones
 
 
 def close(a, b, tol, what):
@@ -110,7 +115,8 @@ def ref_openai(cfg, seed):
     from guided_diffusion.script_util import create_model
     torch.manual_seed(seed)
     m = create_model(image_size=cfg.image_size, num_channels=cfg.model_channels, num_res_blocks=cfg.num_res_blocks,
-                     channel_mult=",".join(str(c) for c in cfg.channel_mult), learn_sigma=(cfg.out_channels == 6), class_cond=False,
+                     channel_mult=",".join(str(c) for c in cfg.channel_mult), learn_sigma=(cfg.out_channels == 6),
+                     class_cond=cfg.num_classes is not None,
                      attention_resolutions=",".join(str(r) for r in cfg.attention_resolutions), num_heads=4,
                      num_head_channels=cfg.num_head_channels, num_heads_upsample=-1, use_scale_shift_norm=True, dropout=0.0,
                      resblock_updown=True, use_fp16=False, use_new_attention_order=False)
@@ -429,6 +435,73 @@ def runner_fixtures():
     print("runner I/O: ok")
 
 
+def guided_fixtures():
+    """Class-conditional denoiser (imagenet_256_cc.yml: class_cond, unet.py:478-479,651-653) and the classifier-guided branches of
+    ddnm_diffusion / ddnm_plus_diffusion (svd_ddnm.py:48-52, 109-113) executed from the reference, with a toy differentiable
+    classifier standing in for the ImageNet one (oracle/guidance.py)."""
+    from functions.svd_ddnm import ddnm_diffusion, ddnm_plus_diffusion
+    import functions.svd_ddnm as ref_mod
+    from oracle.guidance import make_toy_cond_fn
+    assert ref_mod.class_num == S.CLASS_NUM
+    cfg = UO.OpenAIUNetConfig.tiny_class_cond()
+    create_model_cfg = cfg
+    import guided_diffusion.script_util as su
+    assert su.NUM_CLASSES == cfg.num_classes
+    m = ref_openai(create_model_cfg, 1234)
+    rsd = m.state_dict()
+    sd = UO.init_state_dict(cfg, 1234)
+    assert set(sd) == set(rsd)
+    for k in sd:
+        if not torch.equal(sd[k], rsd[k]):
+            assert rsd[k].abs().sum() == 0, f"{k}: differs from the reference but is not a zero-initialised tensor"
+    m.load_state_dict(sd)
+    out = {}
+    g = torch.Generator().manual_seed(31)
+    B, dim = 2, cfg.image_size
+    x = torch.randn(B, 3, dim, dim, generator=g)
+    t = torch.tensor([417.0, 3.0])
+    labels = torch.tensor([951, 7])
+    with torch.no_grad():
+        r = m(x, t, labels)
+        o = UO.forward(sd, x, t, cfg, y=labels)
+    close(o, r, 0.0, "class-conditional unet")
+    out["unet_x"], out["unet_t"], out["unet_labels"], out["unet_out"] = x.numpy(), t.numpy(), labels.numpy(), r.numpy()
+    cond_fn = make_toy_cond_fn(dim, cfg.num_classes, scale=2.0)
+    gcheck = cond_fn(x, t, labels)
+    out["cond_grad"] = gcheck.numpy()
+    betas = SCH.linear_betas()
+    x_orig = torch.rand(B, 3, dim, dim, generator=g) * 2 - 1
+    x_T = torch.randn(B, 3, dim, dim, generator=g)
+    out["x_T"] = x_T.numpy()
+    orng = torch.Generator().manual_seed(4321)
+    torch.rand(B, 3, dim, dim, generator=orng), torch.randn(B, 3 * dim * dim, generator=orng), torch.randn(B, 3 * dim * dim, generator=orng)
+    opsets = {n: (r_, o_) for n, r_, o_, _ in build_ops(dim, orng)}
+    for name, T, sy in (("sr4", 6, 0.0), ("inpaint", 6, 0.1)):
+        rop, oop = opsets[name]
+        conf = ns(diffusion=ns(num_diffusion_timesteps=1000), time_travel=ns(T_sampling=T, travel_length=1, travel_repeat=1))
+        npairs = len(SCH.time_pairs(1000, T, 1, 1))
+        nrng = torch.Generator().manual_seed(556)
+        tape = [torch.randn(B, 3, dim, dim, generator=nrng) for _ in range(npairs)]
+        y = rop.A(x_orig)
+        if sy > 0:
+            y = y + sy * torch.randn(y.shape, generator=nrng)
+        with torch.no_grad(), cpu_shim(tape):
+            if sy == 0.0:
+                xs, x0s = ddnm_diffusion(x_T, m, betas, 0.85, rop, y, cls_fn=cond_fn, classes=torch.tensor([1, 2]), config=conf)
+            else:
+                xs, x0s = ddnm_plus_diffusion(x_T, m, betas, 0.85, rop, y, sy, cls_fn=cond_fn, classes=torch.tensor([1, 2]), config=conf)
+        with torch.no_grad():
+            ox, ox0 = S.ddnm_sample(x_T, lambda a, b, c: UO.forward(sd, a, b, cfg, y=c), betas, 0.85, oop, y, tape, t_sampling=T,
+                                    travel_length=1, travel_repeat=1, sigma_y=sy, cls_fn=cond_fn)
+        d = close(ox, xs[0], 5e-4, f"guided sampler {name}")
+        close(ox0, x0s[0], 5e-4, f"guided sampler {name} x0")
+        key = f"{name}_T{T}_s{sy}"
+        out[key + "_y"], out[key + "_x0"], out[key + "_x0pred"] = y.numpy(), xs[0].numpy(), x0s[0].numpy()
+        print(f"guided sampler {key}: ok (oracle-ref {d:.2e})")
+    out["noise_seed"] = np.array([556])
+    np.savez_compressed(os.path.join(GOLD, "guided_tiny.npz"), **out)
+
+
 def general_fixtures():
     """GeneralA (svd_operators.py:173-208): a dense 48 x 192 degradation with two singular values pushed under the
     1e-3 threshold so the zeroing branch (:185) is exercised."""
@@ -459,9 +532,11 @@ def general_fixtures():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["unet", "openai", "ops", "sampler", "simplified", "general", "runner"]
+    which = sys.argv[1:] or ["unet", "openai", "ops", "sampler", "simplified", "general", "runner", "guided"]
     if "general" in which:
         general_fixtures()
+    if "guided" in which:
+        guided_fixtures()
     if "runner" in which:
         runner_fixtures()
     if "unet" in which:

@@ -12,11 +12,18 @@ import torch
 from .schedule import alpha_bar_table, time_pairs
 
 
+CLASS_NUM = 951   # svd_ddnm.py:7 — the reference overwrites the caller's ``classes`` with this label (:49, :110)
+
+
 def ddnm_sample(x_T, model, betas, eta, op, y, noise, num_timesteps=1000, t_sampling=100,
-                travel_length=1, travel_repeat=1, sigma_y=0.0, trace=None):
+                travel_length=1, travel_repeat=1, sigma_y=0.0, trace=None, cls_fn=None):
     """Returns (x_0, last x0_pred).  ``model(xt, t)`` -> eps (channels beyond 3 dropped, :54-55).
     sigma_y == 0 -> DDNM (:57-65); sigma_y > 0 (already doubled by the caller, diffusion.py:524) -> DDNM+ (:114-131).
-    ``noise``: callable k -> (B,3,H,W) tensor or an indexable tape."""
+    ``noise``: callable k -> (B,3,H,W) tensor or an indexable tape.
+    ``cls_fn`` (classifier guidance, :48-52 / :109-113): the model is then called as ``model(xt, t, classes)`` with
+    classes = CLASS_NUM for every row, only channels 0..2 of its output are kept, and
+    ``et -= sqrt(1 - at) * cls_fn(x, t, classes)`` where ``x`` is the function's INPUT (the initial noise x_T), not the current
+    iterate — exactly what the reference code does."""
     abar = alpha_bar_table(betas)
     pairs = time_pairs(num_timesteps, t_sampling, travel_length, travel_repeat)
     n = x_T.shape[0]
@@ -29,7 +36,12 @@ def ddnm_sample(x_T, model, betas, eta, op, y, noise, num_timesteps=1000, t_samp
         if j < i:
             t = torch.ones(n) * i
             at = abar[i + 1]
-            et = model(xt, t)
+            if cls_fn is None:
+                et = model(xt, t)
+            else:
+                classes = torch.ones(n, dtype=torch.long) * CLASS_NUM
+                et = model(xt, t, classes)[:, :3]
+                et = et - (1 - at).sqrt() * cls_fn(x_T, t, classes)
             if et.size(1) == 6:
                 et = et[:, :3]
             x0_t = (xt - et * (1 - at).sqrt()) / at.sqrt()

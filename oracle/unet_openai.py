@@ -2,7 +2,7 @@
 by a reference-layout ``state_dict``.
 
 Restates /root/reference/guided_diffusion/unet.py for the variant the shipped configs use (use_scale_shift_norm,
-resblock_updown, legacy attention order, num_head_channels=64, class_cond=False):
+resblock_updown, legacy attention order, num_head_channels=64; class_cond adds the label embedding of :478-479, 651-653):
   TimestepEmbedSequential :66-78, Upsample/Downsample (conv-free inside ResBlocks) :81-140, ResBlock._forward :236-256,
   AttentionBlock._forward :299-305, QKVAttentionLegacy :337-354, UNetModel.__init__ :460-617 and .forward :635-664;
   guided_diffusion/nn.py GroupNorm32 :17-19 (32 groups, eps 1e-5), timestep_embedding :103-121;
@@ -13,7 +13,7 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 """
 import math
 from dataclasses import dataclass
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -30,6 +30,7 @@ class OpenAIUNetConfig:
     num_head_channels: int = 64
     out_channels: int = 6                                      # learn_sigma
     in_channels: int = 3
+    num_classes: Optional[int] = None                          # class_cond (imagenet_256_cc.yml): nn.Embedding(num_classes, 4*ch)
 
     @staticmethod
     def imagenet_256():
@@ -40,6 +41,13 @@ class OpenAIUNetConfig:
         # 32x32, 64..128 channels, attention at 16 and 8, one updown level pair: every layer kind, seconds on CPU
         return OpenAIUNetConfig(image_size=32, model_channels=64, num_res_blocks=1, channel_mult=(1, 2, 2),
                                 attention_resolutions=(16, 8), num_head_channels=64, out_channels=6)
+
+    @staticmethod
+    def tiny_class_cond():
+        # the tiny net with the 1000-class label embedding of imagenet_256_cc.yml (unet.py:478-479)
+        c = OpenAIUNetConfig.tiny()
+        c.num_classes = 1000
+        return c
 
     @property
     def attention_ds(self):
@@ -130,11 +138,15 @@ def block_plan(cfg: OpenAIUNetConfig):
     return inp, mid, out, ch
 
 
-def forward(sd, x, t, cfg: OpenAIUNetConfig, taps=None):
+def forward(sd, x, t, cfg: OpenAIUNetConfig, taps=None, y=None):
     inp, mid, out, _ = block_plan(cfg)
     emb = timestep_embedding(t, cfg.model_channels)
     emb = F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
     emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
+    assert (y is not None) == (cfg.num_classes is not None), "must specify y if and only if the model is class-conditional"   # unet.py:644-646
+    if cfg.num_classes is not None:
+        assert y.shape == (x.shape[0],)
+        emb = emb + sd["label_emb.weight"][y.long()]             # unet.py:651-653
 
     def tap(name, v):
         if taps is not None:
@@ -207,6 +219,8 @@ def init_state_dict(cfg: OpenAIUNetConfig, seed=1234, zero_std=0.02):
     inp, mid, out, ch = block_plan(cfg)
     put("time_embed.0", nn.Linear(cfg.model_channels, tdim))
     put("time_embed.2", nn.Linear(tdim, tdim))
+    if cfg.num_classes is not None:
+        put("label_emb", nn.Embedding(cfg.num_classes, tdim))     # created right after time_embed (unet.py:478-479)
     for i, layers in enumerate(inp):
         build(f"input_blocks.{i}", layers)
     build("middle_block", mid)
