@@ -276,7 +276,7 @@ def main():
                            tensor_pipe_active_pct=tj["tensor_pipe_active_pct"], source="profiles/r01_conv_tc_traffic.json")
         except Exception:
             pass
-        roof = dict(bound="tensor", kernel="conv_tc_kernel<BN> (tcgen05 implicit GEMM, 3x fp16 split)", achieved=ach, peak=pk["tf_sust"],
+        roof = dict(bound="tensor", kernel="conv_tc_kernel<BN, PAIR, DUAL> (tcgen05 implicit GEMM, 3x fp16 split; DUAL form on the 128-channel layers, CTA pairs at BN=256)", achieved=ach, peak=pk["tf_sust"],
                     unit="TFLOP/s", frac=ach / pk["tf_sust"], hw_mma_factor=3, frac_hw=3 * ach / pk["tf_sust"],
                     peak_source=pk["src"] + ", sustained bf16 cuBLAS", traffic=traffic,
                     launches_per_forward=len(tc), avg_launch_ms=tc_ms / max(1, len(tc)), share_of_forward=tc_ms / all_ms,
