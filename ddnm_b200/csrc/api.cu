@@ -289,6 +289,11 @@ int ddnm_tc_debug_dual_mode(int mode) {
   tc_debug_dual_mode(mode);
   DDNM_API_END
 }
+int ddnm_tc_debug_pair_dual(int on) {
+  DDNM_API_BEGIN
+  tc_debug_pair_dual(on);
+  DDNM_API_END
+}
 int ddnm_tc_debug_force_bn(int bn) {
   DDNM_API_BEGIN
   tc_debug_force_bn(bn);

@@ -36,22 +36,32 @@ static constexpr int A_PLANE_BYTES = BM * BK * 2;  // 16 KiB
 // issued instead of 3.
 template <int BN, bool PAIR, bool DUAL = false>
 struct TcCfg {
-  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;       // B rows staged by one CTA
+  static constexpr bool PD = PAIR && DUAL;                // both: see conv_tc_kernel's "PAIR + DUAL" note
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;       // B rows staged by one CTA (plain PAIR)
   static constexpr int B_PLANE_BYTES = B_ROWS * BK * 2;
-  static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
-  static constexpr int STAGES = STAGE_BYTES <= 48 * 1024 ? 4 : (STAGE_BYTES <= 64 * 1024 ? 3 : 2);
+  // B regions of a stage: [X][Y].  plain / DUAL / PAIR: X = B_hi rows, Y = B_lo rows (B_PLANE_BYTES each).
+  // PAIR + DUAL: X = a FULL BN-row plane (B_hi in the leader, B_lo in the peer), Y = this CTA's BN/2-row half of B_hi.
+  static constexpr int BX_BYTES = PD ? BN * BK * 2 : B_PLANE_BYTES;
+  static constexpr int BY_BYTES = PD ? (BN / 2) * BK * 2 : B_PLANE_BYTES;
+  static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + BX_BYTES + BY_BYTES;
+  static constexpr int STAGES = STAGE_BYTES <= 56 * 1024 ? 4 : (STAGE_BYTES <= 64 * 1024 ? 3 : 2);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int ACC_COLS = DUAL ? 2 * BN : BN;    // TMEM columns of one accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
-  static_assert(TMEM_COLS <= 512 && !(PAIR && DUAL), "TMEM capacity / unsupported combination");
+  static_assert(TMEM_COLS <= 512 && SMEM_BYTES <= 227 * 1024, "TMEM / shared memory capacity");
 };
 
 template <int BN, bool PAIR, bool DUAL>
 __global__ void __launch_bounds__(320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant__ CUtensorMap tm_a0l,
                const __grid_constant__ CUtensorMap tm_a1h, const __grid_constant__ CUtensorMap tm_a1l,
-               const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bl, const TcParams p) {
+               const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bl,
+               const __grid_constant__ CUtensorMap tm_b2, const TcParams p) {
+  // PAIR + DUAL (BN = 128: the Cout = 128 layers): A_hi x [B_hi; B_lo] as ONE 256 x 256 cta_group::2 instruction — the leader's
+  // smem supplies the B_hi plane (operand rows 0..127), the peer's the B_lo plane (rows 128..255) — then A_lo x B_hi as a 256 x 128
+  // instruction whose B halves (B_hi rows 0..63 / 64..127) sit in a third region Y of the stage (tm_b2: B_hi with a BN/2-row box).
   using Cfg = TcCfg<BN, PAIR, DUAL>;
+  constexpr bool PD = Cfg::PD;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -168,7 +178,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
             load4(sa, &tm_a1h, fb, c, x0, y0, n0);
             if (lo) load4(sa + A_PLANE_BYTES, &tm_a1l, fb, c, x0, y0, n0);
           }
-          if (PAIR) {
+          if (PD) {
+            tma_load_3d_pair(sa + 2 * A_PLANE_BYTES, rank == 0 ? &tm_bh : &tm_bl, fb, kb * BK, n_idx * BN, bz);   // X: full plane
+            tma_load_3d_pair(sa + 2 * A_PLANE_BYTES + Cfg::BX_BYTES, &tm_b2, fb, kb * BK, n_idx * BN + (int)rank * (BN / 2), bz);
+          } else if (PAIR) {
             tma_load_3d_pair(sa + 2 * A_PLANE_BYTES, &tm_bh, fb, kb * BK, brow, bz);
             if (lo) tma_load_3d_pair(sa + 2 * A_PLANE_BYTES + Cfg::B_PLANE_BYTES, &tm_bl, fb, kb * BK, brow, bz);
           } else if (p.b_batched == 2) {
@@ -216,7 +229,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint32_t adv = 2u * k;  // 16 fp16 = 32 bytes = 2 x 16-byte units inside the swizzle row
-            if (DUAL && p.terms != 1) {
+            if (PD) {
+              // region X of the two CTAs forms [B_hi; B_lo]; region Y holds the B_hi halves of the 256 x 128 product
+              const uint32_t by = (((sa + 2 * A_PLANE_BYTES + Cfg::BX_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+              umma_f16_pair(d_tmem, hi | (ah + adv), hi | (bh + adv), idesc_wide, (uint32_t)((kb | k) != 0));
+              umma_f16_pair(d_tmem, hi | (al + adv), hi | (by + adv), p.idesc, 1u);
+            } else if (DUAL && p.terms != 1) {
               // columns [0,BN) += A_hi*B_hi, [BN,2BN) += A_hi*B_lo in one instruction; then [0,BN) += A_lo*B_hi
               umma_f16(d_tmem, hi | (ah + adv), hi | (bh + adv), idesc_wide, (uint32_t)((kb | k) != 0));
               umma_f16(d_tmem, hi | (al + adv), hi | (bh + adv), p.idesc, 1u);
@@ -457,6 +475,9 @@ void tc_set_terms(int terms) {
 int tc_get_terms() { return g_terms; }
 static int g_pair_mode = -1;   // -1: cost model decides (default), 0: never, 1: CTA pairs wherever legal
 static double g_pair_tkb[2] = {1300.0, 1770.0};   // clocks per k-block of the pair kernel at BN = 128 / 256 (sweep)
+static int g_pair_dual = 1;                         // 1 (default): pairs at BN = 128 use the PAIR + DUAL form
+static double g_pair_dual_tkb = 935.0;              // measured: 3-6 % under DUAL's 1000 on the 256x256 / 128x128 layers
+void tc_debug_pair_dual(int on) { g_pair_dual = on; }
 void tc_debug_pair_mode(int mode) {
   DDNM_CHECK(mode == -1 || mode == 0 || mode == 1, "pair mode must be -1 (cost model), 0 (off) or 1 (wherever legal)");
   g_pair_mode = mode;
@@ -504,7 +525,7 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
     // k-step), 256 the three-instruction form; pairs pay off only at BN = 256 (at BN = 128 they match the single-CTA pace on zeros
     // and lose 14 % on real data under the power cap)
     const Cand cands[] = {{64, false, 1000.0}, {128, false, g_dual_mode ? 1000.0 : 1100.0}, {256, false, 2060.0},
-                          {128, true, g_pair_tkb[0]}, {256, true, g_pair_tkb[1]}};
+                          {128, true, (g_pair_dual && g_terms == 3) ? g_pair_dual_tkb : g_pair_tkb[0]}, {256, true, g_pair_tkb[1]}};
     double best = 1e300;
     L.BN = 64;
     L.pair = false;
@@ -516,6 +537,8 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
       if (!c.pair && g_pair_mode == 1 && w_batches == 1 && m_tiles % 2 == 0 && c.bn >= 128) continue;   // forced pairs
       const long long units = c.pair ? tiles / 2 : tiles;
       const long long slots = c.pair ? num_sms / 2 : num_sms;
+      // PAIR + DUAL was only measured (and only pays) on layers with many tiles; smaller ones keep the single-CTA DUAL form
+      if (c.pair && c.bn == 128 && g_pair_dual && g_pair_mode != 1 && units < 2 * slots) continue;
       const double rounds = (double)((units + slots - 1) / slots);
       const double cost = rounds * (kblocks * c.t_kb + 1500.0);
       if (cost < best) {
@@ -525,7 +548,8 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
       }
     }
   }
-  L.dual = g_dual_mode != 0 && !L.pair && L.BN <= 128;
+  // pairs at BN = 128 run the PAIR + DUAL form when enabled (it needs the 3-term arithmetic), else the plain pair form
+  L.dual = g_dual_mode != 0 && L.BN <= 128 && (!L.pair || (L.BN == 128 && g_pair_dual && g_terms == 3));
   p.n_tiles = Cout / L.BN;
   p.mode0 = mode0;
   p.cb0 = src0.C / BK;
@@ -570,9 +594,15 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   }
   const int Ktot = (p.kb0 + p.kb1) * BK;
   const uint64_t bd[3] = {(uint64_t)Ktot, (uint64_t)Cout, (uint64_t)w_batches};
-  const uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)(L.pair ? L.BN / 2 : L.BN), 1u};
+  const bool pd = L.pair && L.dual;
+  const uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)(L.pair && !pd ? L.BN / 2 : L.BN), 1u};
   L.bh = make_map_f16(w_hi, 3, bd, bbox);
   L.bl = make_map_f16(w_lo, 3, bd, bbox);
+  L.b2 = L.bh;
+  if (pd) {
+    const uint32_t hbox[3] = {(uint32_t)BK, (uint32_t)(L.BN / 2), 1u};
+    L.b2 = make_map_f16(w_hi, 3, bd, hbox);
+  }
   const int total = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
   L.grid = L.pair ? 2 * std::min(total / 2, num_sms / 2) : std::min(total, num_sms);
   L.flops = 2.0 * (double)out.pixels() * Cout * Ktot;
@@ -635,6 +665,7 @@ TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, 
   const uint32_t bbox[4] = {(uint32_t)BK, (uint32_t)L.BN, 1u, 1u};
   L.bh = make_map_f16(B.hi, 4, bd, bbox, bs);
   L.bl = make_map_f16(B.lo, 4, bd, bbox, bs);
+  L.b2 = L.bh;
   L.grid = std::min(m_tiles * p.n_tiles, num_sms);
   L.flops = 2.0 * (double)images * heads * M * (double)N * K;
   return L;
@@ -661,9 +692,9 @@ static void launch_bn(const TcLaunch& L, cudaStream_t stream) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, PAIR, DUAL>, L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.p));
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, PAIR, DUAL>, L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.b2, L.p));
   } else {
-    conv_tc_kernel<BN, PAIR, DUAL><<<L.grid, 320, Cfg::SMEM_BYTES, stream>>>(L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.p);
+    conv_tc_kernel<BN, PAIR, DUAL><<<L.grid, 320, Cfg::SMEM_BYTES, stream>>>(L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.b2, L.p);
   }
   CUDA_CHECK(cudaGetLastError());
 }
@@ -675,7 +706,8 @@ void tc_run(const TcLaunch& L, cudaStream_t stream) {
       else launch_bn<256, false, false>(L, stream);
       break;
     case 128:
-      if (L.pair) launch_bn<128, true, false>(L, stream);
+      if (L.pair && L.dual) launch_bn<128, true, true>(L, stream);
+      else if (L.pair) launch_bn<128, true, false>(L, stream);
       else if (L.dual) launch_bn<128, false, true>(L, stream);
       else launch_bn<128, false, false>(L, stream);
       break;

@@ -41,7 +41,7 @@ struct TcParams {
 };
 
 struct TcLaunch {
-  CUtensorMap a0h, a0l, a1h, a1l, bh, bl;
+  CUtensorMap a0h, a0l, a1h, a1l, bh, bl, b2;   // b2: B_hi with a BN/2-row box (PAIR + DUAL form), else = bh
   TcParams p;
   int BN = 128;
   bool pair = false;           // CTA-pair kernel (cta_group::2, 256-row MMAs, cluster of 2)
@@ -76,6 +76,7 @@ TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, 
 // debug knobs (tests only): override descriptor words for the NEXT launches built
 void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor);
 void tc_debug_force_bn(int bn);
+void tc_debug_pair_dual(int on);     // 1 (default): CTA pairs at BN = 128 use the PAIR + DUAL form
 void tc_debug_dual_mode(int mode);   // 1: DUAL kernel for single-CTA BN <= 128 launches (default), 0: never
 void tc_debug_pair_mode(int mode);   // -1: cost model decides (default), 0: never, 1: CTA pairs wherever legal
 // number of fp16 product terms used by launches built from now on (3 = parity mode, 1 = fast mode)

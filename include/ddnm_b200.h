@@ -190,6 +190,8 @@ int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const
 int ddnm_tc_debug_override(unsigned desc_hi, unsigned idesc_xor);
 /* tuning experiments: force the N-tile width of conv launches built afterwards (0 = heuristic) */
 int ddnm_tc_debug_force_bn(int bn);
+/* 1 (default): CTA pairs at BN = 128 (Cout = 128 layers) use the PAIR + DUAL instruction form; 0: the plain pair form */
+int ddnm_tc_debug_pair_dual(int on);
 /* 1 (default): single-CTA launches with BN <= 128 issue hi*hi and hi*lo as one N = 2*BN instruction (two partial accumulators); 0: never */
 int ddnm_tc_debug_dual_mode(int mode);
 /* CTA-pair kernel (tcgen05 cta_group::2) for conv launches built afterwards: -1 (default) the cost model decides,

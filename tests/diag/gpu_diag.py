@@ -164,6 +164,24 @@ def group_bn_sweep():
     _lib.check(L.ddnm_tc_debug_dual_mode(1))
 
 
+def group_pd_bench():
+    """PAIR + DUAL form vs DUAL on the Cout = 128 layer shapes, zero and random operands."""
+    ms, fl = C.c_float(), C.c_double()
+    for (N, H, W, Cin, Cout, mode) in [(16, 256, 256, 256, 128, 0), (16, 256, 256, 128, 128, 0), (16, 128, 128, 256, 128, 0), (16, 128, 128, 128, 128, 0)]:
+        for label, iters in (("zeros ", 20), ("random", -20)):
+            row = []
+            for pair, pd in ((0, 0), (1, 1), (1, 0)):
+                _lib.check(L.ddnm_tc_debug_force_bn(128))
+                _lib.check(L.ddnm_tc_debug_pair_mode(pair))
+                _lib.check(L.ddnm_tc_debug_pair_dual(pd))
+                _lib.check(L.ddnm_conv_tc_bench(N, H, W, Cin, Cout, mode, iters, C.byref(ms), C.byref(fl)))
+                row.append(f"{ms.value * 1e3:7.1f}")
+            print(f"[pd_bench] {label} N{N} {H}x{W} {Cin}->{Cout}: dual {row[0]} | pair+dual {row[1]} | pair {row[2]} us", flush=True)
+    _lib.check(L.ddnm_tc_debug_force_bn(0))
+    _lib.check(L.ddnm_tc_debug_pair_mode(-1))
+    _lib.check(L.ddnm_tc_debug_pair_dual(1))
+
+
 def _cfg_ns(cfg):
     import types
     ns = types.SimpleNamespace
@@ -301,10 +319,11 @@ def group_cpu_threads():
             print(f"   threads {nt}: {time.time() - t0:.2f} s / image-forward", flush=True)
 
 
-def group_unet_bench(which="celeba", B=16, iters=5, prec="fp32"):
+def group_unet_bench(which="celeba", B=16, iters=5, prec="fp32", pair_dual=1):
     from oracle import unet_simple as U
     from ddnm_b200.model import Model
     B, iters = int(B), int(iters)
+    _lib.check(L.ddnm_tc_debug_pair_dual(int(pair_dual)))
     cfg = U.SimpleUNetConfig.tiny() if which == "tiny" else U.SimpleUNetConfig.celeba_hq()
     sd = U.init_state_dict(cfg, 1234)
     m = Model(_cfg_ns(cfg))

@@ -103,9 +103,11 @@ def test_tc_conv_cta_pair_vs_fp64_and_single_cta(lib, shape):
         lib.check(L.ddnm_tc_debug_pair_mode(0))
         single = _conv_tc(lib, x, w, b, mode=mode).clone()
         lib.check(L.ddnm_tc_debug_pair_mode(1))
+        lib.check(L.ddnm_tc_debug_pair_dual(0))          # the plain pair form; PAIR + DUAL has its own test
         pair = _conv_tc(lib, x, w, b, mode=mode)
     finally:
         L.ddnm_tc_debug_pair_mode(-1)
+        L.ddnm_tc_debug_pair_dual(1)
     torch.cuda.synchronize()
     assert_close(pair, single, 2e-5, 1e-5, f"pair vs single-CTA {shape}")   # same products, sums re-associated
     assert_close(pair, _conv_ref(x, w, b, mode=mode), rtol=1e-4, atol=5e-5, what=f"pair conv {shape}")
@@ -134,6 +136,34 @@ def test_tc_conv_dual_accumulator_vs_three_instruction_form(lib, shape):
     torch.cuda.synchronize()
     assert_close(dual, plain, 2e-5, 1e-5, f"dual vs plain {shape}")
     assert_close(dual, _conv_ref(x, w, b, mode=mode), rtol=1e-4, atol=5e-5, what=f"dual conv {shape}")
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 256, 64, 128, 0), (4, 128, 128, 128, 128, 0), (4, 128, 128, 64, 128, 1), (8, 128, 128, 64, 128, 2),
+                                   (2, 128, 128, 64, 384, 0)], ids=str)
+def test_tc_conv_pair_dual_form(lib, shape):
+    """PAIR + DUAL (Cout % 128 == 0 layers at BN = 128): A_hi x [B_hi; B_lo] as one 256 x 256 cta_group::2 instruction, the leader's
+    smem holding the B_hi plane and the peer's the B_lo plane, plus A_lo x B_hi from a third B region."""
+    N, H, W, Cin, Cout, mode = shape
+    torch.manual_seed(8)
+    k = 1 if mode == 1 else 3
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, k, k, device=dev) / (k * k * Cin) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    L = lib.lib()
+    try:
+        lib.check(L.ddnm_tc_debug_pair_mode(0))
+        single = _conv_tc(lib, x, w, b, mode=mode).clone()
+        lib.check(L.ddnm_tc_debug_pair_mode(1))
+        lib.check(L.ddnm_tc_debug_pair_dual(1))
+        lib.check(L.ddnm_tc_debug_force_bn(128))
+        pd = _conv_tc(lib, x, w, b, mode=mode)
+    finally:
+        L.ddnm_tc_debug_pair_mode(-1)
+        L.ddnm_tc_debug_pair_dual(1)
+        L.ddnm_tc_debug_force_bn(0)
+    torch.cuda.synchronize()
+    assert_close(pd, single, 2e-5, 1e-5, f"pair+dual vs single-CTA {shape}")
+    assert_close(pd, _conv_ref(x, w, b, mode=mode), rtol=1e-4, atol=5e-5, what=f"pair+dual conv {shape}")
 
 
 def test_tc_conv_cta_pair_fusions(lib):
