@@ -17,7 +17,8 @@
 // Three instantiations (picked per layer by the cost model in tc_make_launch, constants from profiles/r01_bn_sweep.md):
 //   <BN, false, false>  three instructions per k-step (hi*hi, hi*lo, lo*hi) into one accumulator;
 //   <BN, false, true>   DUAL: A_hi x [B_hi; B_lo] as one N = 2*BN instruction + A_lo x B_hi, two partial accumulators;
-//   <BN, true,  false>  PAIR: cluster of two CTAs, 256-row tcgen05.mma.cta_group::2, each CTA stages half of the B tile.
+//   <BN, true,  false>  PAIR: cluster of two CTAs, 256-row tcgen05.mma.cta_group::2, each CTA stages half of the B tile;
+//   <128, true, true>   PAIR + DUAL: 256 x 256 A_hi x [B_hi; B_lo] with the two planes held by the two CTAs + 256 x 128 A_lo x B_hi.
 #include "tc_gemm.cuh"
 
 namespace ddnm {
