@@ -128,7 +128,7 @@ def _save_all(folder, pattern, u8_cuda, idx0):
 
 
 def restore_batch(config, model, A_funcs, deg, x_orig, betas, eta, sigma_y=0.0, add_noise=False, image_folder=None, idx_so_far=0,
-                  x_T=None, noise=None):
+                  x_T=None, noise=None, cls_fn=None):
     """Body of the reference's evaluation loop for one batch (guided_diffusion/diffusion.py:533-603).
 
     x_orig: (B,C,H,W) in [0,1] (what the DataLoader yields), host or CUDA.  ``sigma_y`` is the level the reference passes on,
@@ -156,7 +156,8 @@ def restore_batch(config, model, A_funcs, deg, x_orig, betas, eta, sigma_y=0.0, 
         if x_T is None:
             x_T = torch.randn(b, C_, R, R, device=dev)                                    # :578-584
         plus = sigma_y != 0.0                                                             # :587-590
-        x0, _ = sample_device(x_T, model, betas, eta, A_funcs, y, sigma_y if plus else 0.0, plus, config, noise=noise)
+        x0, _ = sample_device(x_T, model, betas, eta, A_funcs, y, sigma_y if plus else 0.0, plus, config, noise=noise,
+                              cls_fn=cls_fn)                                              # cls_fn: diffusion.py:181-189 (class-conditional configs)
         img_u8, psnr, _ = finish_images(config, x0, x_orig)                               # :592-601
         out = dict(psnr=psnr.cpu(), y=y)
         if image_folder is not None:

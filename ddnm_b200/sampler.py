@@ -18,9 +18,9 @@ from .schedule import alpha_bar_table, time_pairs
 class_num = 951
 
 
-def sample_device(x, model, b, eta, A_funcs, y, sigma_y, plus, config, noise=None):
+def sample_device(x, model, b, eta, A_funcs, y, sigma_y, plus, config, noise=None, cls_fn=None):
     """The loop with device-resident inputs and outputs (no host copies): returns (x_0, x0_pred) CUDA tensors."""
-    return _run(x, model, b, eta, A_funcs, y, sigma_y, plus, None, None, config, noise, to_host=False)
+    return _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, None, config, noise, to_host=False)
 
 
 def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, noise=None, to_host=True):
