@@ -31,7 +31,32 @@ struct Error : std::runtime_error {
   } while (0)
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// One-time per-DEVICE actions (cudaFuncSetAttribute is a per-device setting): true the first time `flags` sees the current device.
+inline bool first_use_on_device(bool (&flags)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
 inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
+
+// Stream-ordered scratch that is returned to the pool on every exit path (a DDNM_CHECK throw inside a sampling loop must not
+// leak the loop's buffers).
+struct StreamBuf {
+  float* p = nullptr;
+  cudaStream_t st = nullptr;
+  StreamBuf(size_t elems, cudaStream_t s) : st(s) {
+    cudaError_t e = cudaMallocAsync((void**)&p, elems * sizeof(float), s);
+    if (e != cudaSuccess) throw Error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in cudaMallocAsync (sampler scratch)");
+  }
+  ~StreamBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+  StreamBuf(const StreamBuf&) = delete;
+  StreamBuf& operator=(const StreamBuf&) = delete;
+};
 
 // A strided NHWC fp32 activation view: element (n, y, x, c) at p[((n*H + y)*W + x)*ld + c].
 // ld >= C lets a tensor live inside a channel slice of a wider (concat) buffer.

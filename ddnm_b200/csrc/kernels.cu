@@ -405,12 +405,9 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ i
 void linear(const float* in, int N, int K, const float* W, const float* bias, int O, float* out, int ldo, int act_in,
             int act_out, cudaStream_t st) {
   DDNM_CHECK(K % 4 == 0, "linear: K must be a multiple of 4");
-  static bool attr = false;
+  static bool attr[64] = {};
   constexpr int kMaxSmem = 160 * 1024;
-  if (!attr) {
-    CUDA_CHECK(cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr = true;
-  }
+  if (first_use_on_device(attr)) CUDA_CHECK(cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   const int rows_max = std::max(1, kMaxSmem / (K * 4));
   for (int n0 = 0; n0 < N; n0 += rows_max) {     // batches whose activations exceed the staging buffer go in row chunks
     const int n = std::min(rows_max, N - n0);

@@ -700,11 +700,9 @@ void Operator::fwht(float* buf, int B, cudaStream_t s) {
   fwht_rows_kernel<<<(int)cdivll(rows, rpb), threads, (size_t)rpb * D_ * 4, s>>>(buf, D_, rows);
   CUDA_CHECK(cudaGetLastError());
   const size_t smem = (size_t)D_ * 33 * 4;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(fwht_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  // the attribute is per device: set it whenever more than the default 48 KiB is needed (a cached process-wide flag would leave
+  // a second GPU of the same process without it)
+  if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(fwht_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(D_ / 32, B * C_);
   fwht_cols_kernel<<<grid, 256, smem, s>>>(buf, D_, (float)D_);
   CUDA_CHECK(cudaGetLastError());

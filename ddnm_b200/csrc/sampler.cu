@@ -2,6 +2,7 @@
 // no host synchronisation: per denoising pair one UNet graph launch + one fused update; travel-back pairs are one
 // elementwise kernel.  The reference instead bounces xt / x0_t through host memory every step (:67-68, :45).
 #include <cmath>
+#include <memory>
 #include <vector>
 
 #include "../../include/ddnm_b200.h"
@@ -32,14 +33,18 @@ __global__ void guide_kernel(float* __restrict__ et, long long et_stride, const 
   *e = __fsub_rn(*e, __fmul_rn(s1, grad[i]));
 }
 
-static void sample(UNetEngine* unet, Operator* op, const ddnm_schedule* sc, const float* x_T, const float* y, const float* noise,
-                   int B, float* out_x0, float* out_x0_pred, cudaStream_t st, const int* labels = nullptr,
-                   const float* grad_buf = nullptr, ddnm_guidance_fn guide = nullptr, void* user = nullptr) {
-  DDNM_CHECK(unet && op && sc && x_T && y && noise && out_x0, "null argument");
+// Pairs [k0, k1) of the schedule.  State lives in the caller's buffers so that a long schedule can be run as several calls
+// with a bounded noise buffer each: xt_state = current iterate (in/out), x0t = last un-projected x0_t (in/out, read by
+// travel-back pairs), *have_x0 = whether x0t holds one.  noise = the draws of exactly these pairs.
+static void sample_range(UNetEngine* unet, Operator* op, const ddnm_schedule* sc, int k0, int k1, float* xt_state, float* x0t,
+                         int* have_x0, const float* y, const float* noise, int B, cudaStream_t st, const int* labels = nullptr,
+                         const float* grad_buf = nullptr, ddnm_guidance_fn guide = nullptr, void* user = nullptr) {
+  DDNM_CHECK(unet && op && sc && xt_state && x0t && have_x0 && y && noise, "null argument");
+  DDNM_CHECK(unet->batch() == B, "engine was built for a different batch size");   // before anything reads B elements
+  DDNM_CHECK(0 <= k0 && k0 <= k1 && k1 <= sc->n_pairs, "pair range outside the schedule");
   DDNM_CHECK((labels != nullptr) == unet->class_conditional(), "class labels go with a class-conditional denoiser, and only with one");
   DDNM_CHECK((guide != nullptr) == (grad_buf != nullptr), "guidance callback and gradient buffer go together");
   if (labels) unet->set_labels(labels, st);
-  DDNM_CHECK(unet->batch() == B, "engine was built for a different batch size");
   const int R = unet->resolution();
   DDNM_CHECK(op->x_dim() == (long long)unet->in_channels() * R * R, "operator / denoiser image size mismatch");
   DDNM_CHECK(unet->out_ch() == 3 || unet->out_ch() == 6, "denoiser must predict 3 (eps) or 6 (eps, sigma) channels");
@@ -48,18 +53,15 @@ static void sample(UNetEngine* unet, Operator* op, const ddnm_schedule* sc, cons
   const long long et_stride = (long long)unet->out_ch() * R * R;  // 6-channel nets: keep channels 0..2 (:54-55)
   float* xt = unet->x_in();      // the denoiser reads its input here
   float* et = unet->out_buf();   // and leaves eps here
-  float *x0t = nullptr, *xn = nullptr;
-  CUDA_CHECK(cudaMallocAsync((void**)&x0t, n * sizeof(float), st));
-  CUDA_CHECK(cudaMallocAsync((void**)&xn, n * sizeof(float), st));
-  CUDA_CHECK(cudaMemcpyAsync(xt, x_T, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  StreamBuf xn((size_t)n, st);
+  CUDA_CHECK(cudaMemcpyAsync(xt, xt_state, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   const float eta = sc->eta;
   const float c_eta = (float)std::sqrt(1.0 - (double)eta * (double)eta);  // (1 - eta ** 2) ** 0.5 as the fp32 scalar torch sees
-  bool have_x0 = false;
-  for (int k = 0; k < sc->n_pairs; ++k) {
+  for (int k = k0; k < k1; ++k) {
     const int i = sc->t_i[k], j = sc->t_j[k];
     DDNM_CHECK(i >= 0 && i < sc->num_timesteps && j >= -1 && j < sc->num_timesteps, "time index out of range");
     const float at_next = sc->abar[j + 1];
-    const float* z = noise + (long long)k * n;
+    const float* z = noise + (long long)(k - k0) * n;
     if (j < i) {
       const float at = sc->abar[i + 1];
       fill_kernel<<<cdiv(B, 128), 128, 0, st>>>(unet->t_in(), B, (float)i);
@@ -80,19 +82,34 @@ static void sample(UNetEngine* unet, Operator* op, const ddnm_schedule* sc, cons
       s.c2 = s1n * c_eta;
       s.use_plus = sc->plus ? 1 : 0;
       if (s.use_plus) s.plus = Operator::make_plus(s.sqrt_atn, sc->sigma_y, s1n, eta);
-      op->step(xt, et, et_stride, z, y, B, s, x0t, xn, st);
-      have_x0 = true;
+      op->step(xt, et, et_stride, z, y, B, s, x0t, xn.p, st);
+      *have_x0 = 1;
     } else {
-      DDNM_CHECK(have_x0, "schedule starts with a travel-back step");
-      travel_back_kernel<<<(int)cdivll(n, 256), 256, 0, st>>>(x0t, z, std::sqrt(at_next), std::sqrt(1.0f - at_next), xn, n);
+      DDNM_CHECK(*have_x0, "schedule starts with a travel-back step");
+      travel_back_kernel<<<(int)cdivll(n, 256), 256, 0, st>>>(x0t, z, std::sqrt(at_next), std::sqrt(1.0f - at_next), xn.p, n);
       CUDA_CHECK(cudaGetLastError());
     }
-    CUDA_CHECK(cudaMemcpyAsync(xt, xn, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(xt, xn.p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
-  CUDA_CHECK(cudaMemcpyAsync(out_x0, xt, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (out_x0_pred) CUDA_CHECK(cudaMemcpyAsync(out_x0_pred, x0t, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  CUDA_CHECK(cudaFreeAsync(x0t, st));
-  CUDA_CHECK(cudaFreeAsync(xn, st));
+  CUDA_CHECK(cudaMemcpyAsync(xt_state, xt, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+}
+
+// the whole schedule from one full-length noise tape
+static void sample(UNetEngine* unet, Operator* op, const ddnm_schedule* sc, const float* x_T, const float* y, const float* noise,
+                   int B, float* out_x0, float* out_x0_pred, cudaStream_t st, const int* labels = nullptr,
+                   const float* grad_buf = nullptr, ddnm_guidance_fn guide = nullptr, void* user = nullptr) {
+  DDNM_CHECK(unet && op && sc && x_T && y && noise && out_x0, "null argument");
+  DDNM_CHECK(unet->batch() == B, "engine was built for a different batch size");
+  const long long n = (long long)B * op->x_dim();
+  std::unique_ptr<StreamBuf> own;
+  float* x0t = out_x0_pred;
+  if (!x0t) {
+    own.reset(new StreamBuf((size_t)n, st));
+    x0t = own->p;
+  }
+  if (out_x0 != x_T) CUDA_CHECK(cudaMemcpyAsync(out_x0, x_T, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  int have_x0 = 0;
+  sample_range(unet, op, sc, 0, sc->n_pairs, out_x0, x0t, &have_x0, y, noise, B, st, labels, grad_buf, guide, user);
 }
 
 }  // namespace ddnm
@@ -111,5 +128,13 @@ extern "C" int ddnm_sample_guided(void* unet, void* op, const ddnm_schedule* sch
   DDNM_API_BEGIN
   sample(static_cast<UNetEngine*>(unet), static_cast<Operator*>(op), sched, x_T, y, noise, B, out_x0, out_x0_pred,
          (cudaStream_t)stream, labels, grad_buf, fn, user);
+  DDNM_API_END
+}
+extern "C" int ddnm_sample_range(void* unet, void* op, const ddnm_schedule* sched, int k_begin, int k_end, float* xt, float* x0_pred,
+                                 int* have_x0, const float* y, const float* noise, int B, const int* labels, const float* grad_buf,
+                                 ddnm_guidance_fn fn, void* user, void* stream) {
+  DDNM_API_BEGIN
+  sample_range(static_cast<UNetEngine*>(unet), static_cast<Operator*>(op), sched, k_begin, k_end, xt, x0_pred, have_x0, y, noise, B,
+               (cudaStream_t)stream, labels, grad_buf, fn, user);
   DDNM_API_END
 }

@@ -2,6 +2,7 @@
 // image-space operators built from mask / colour-to-gray / average-pool (diffusion.py:244-290, helpers :27-42) and a scalar
 // lambda_t / gamma_t update (:355-376).  One fused kernel per step; thread = one scale x scale patch across the 3 channels.
 #include <cmath>
+#include <memory>
 
 #include "../../include/ddnm_b200.h"
 #include "api_util.cuh"
@@ -141,10 +142,12 @@ __global__ void simp_travel_kernel(const float* __restrict__ x0, const float* __
   if (i < n) xn[i] = __fadd_rn(__fmul_rn(sa, x0[i]), __fmul_rn(z[i], s1));
 }
 
-static void sample_simplified(UNetEngine* unet, const ddnm_simple_deg* d, const ddnm_schedule* sc, const float* x_T, const float* y,
-                              const float* noise, int B, float* out_x0, float* out_x0_pred, cudaStream_t st) {
-  DDNM_CHECK(unet && sc && x_T && y && noise && out_x0, "null argument");
+// pairs [k0, k1) with the state in the caller's buffers (same contract as sample_range in sampler.cu)
+static void sample_simplified_range(UNetEngine* unet, const ddnm_simple_deg* d, const ddnm_schedule* sc, int k0, int k1, float* xt_state,
+                                    float* x0t, int* have_x0, const float* y, const float* noise, int B, cudaStream_t st) {
+  DDNM_CHECK(unet && sc && xt_state && x0t && have_x0 && y && noise, "null argument");
   DDNM_CHECK(unet->batch() == B, "engine was built for a different batch size");
+  DDNM_CHECK(0 <= k0 && k0 <= k1 && k1 <= sc->n_pairs, "pair range outside the schedule");
   SimpDeg dg = make_deg(d);
   const int R = unet->resolution();
   DDNM_CHECK(dg.D == R && unet->in_channels() == 3, "degradation / denoiser image size mismatch");
@@ -152,18 +155,16 @@ static void sample_simplified(UNetEngine* unet, const ddnm_simple_deg* d, const 
   const long long et_stride = (long long)unet->out_ch() * R * R;
   float* xt = unet->x_in();
   float* et = unet->out_buf();
-  float *x0t = nullptr, *xn = nullptr;
-  CUDA_CHECK(cudaMallocAsync((void**)&x0t, n * sizeof(float), st));
-  CUDA_CHECK(cudaMallocAsync((void**)&xn, n * sizeof(float), st));
-  CUDA_CHECK(cudaMemcpyAsync(xt, x_T, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  StreamBuf xnb((size_t)n, st);
+  float* xn = xnb.p;
+  CUDA_CHECK(cudaMemcpyAsync(xt, xt_state, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   const float eta = sc->eta, sigma_y = sc->sigma_y;
   const float c_eta = (float)std::sqrt(1.0 - (double)eta * (double)eta);
-  bool have_x0 = false;
-  for (int k = 0; k < sc->n_pairs; ++k) {
+  for (int k = k0; k < k1; ++k) {
     const int i = sc->t_i[k], j = sc->t_j[k];
     DDNM_CHECK(i >= 0 && i < sc->num_timesteps && j >= -1 && j < sc->num_timesteps, "time index out of range");
     const float at_next = sc->abar[j + 1];
-    const float* z = noise + (long long)k * n;
+    const float* z = noise + (long long)(k - k0) * n;
     if (j < i) {
       const float at = sc->abar[i + 1];
       simp_fill_kernel<<<cdiv(B, 128), 128, 0, st>>>(unet->t_in(), B, (float)i);
@@ -186,18 +187,31 @@ static void sample_simplified(UNetEngine* unet, const ddnm_simple_deg* d, const 
         s.gamma_t = 0.0f;
       }
       simp_launch<SF_STEP>(dg, xt, et, et_stride, z, y, s, x0t, xn, B, st);
-      have_x0 = true;
+      *have_x0 = 1;
     } else {
-      DDNM_CHECK(have_x0, "schedule starts with a travel-back step");
+      DDNM_CHECK(*have_x0, "schedule starts with a travel-back step");
       simp_travel_kernel<<<(int)cdivll(n, 256), 256, 0, st>>>(x0t, z, std::sqrt(at_next), std::sqrt(1.0f - at_next), xn, n);
       CUDA_CHECK(cudaGetLastError());
     }
     CUDA_CHECK(cudaMemcpyAsync(xt, xn, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
-  CUDA_CHECK(cudaMemcpyAsync(out_x0, xt, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (out_x0_pred) CUDA_CHECK(cudaMemcpyAsync(out_x0_pred, x0t, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  CUDA_CHECK(cudaFreeAsync(x0t, st));
-  CUDA_CHECK(cudaFreeAsync(xn, st));
+  CUDA_CHECK(cudaMemcpyAsync(xt_state, xt, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+}
+
+static void sample_simplified(UNetEngine* unet, const ddnm_simple_deg* d, const ddnm_schedule* sc, const float* x_T, const float* y,
+                              const float* noise, int B, float* out_x0, float* out_x0_pred, cudaStream_t st) {
+  DDNM_CHECK(unet && sc && x_T && y && noise && out_x0, "null argument");
+  DDNM_CHECK(unet->batch() == B, "engine was built for a different batch size");
+  const long long n = (long long)B * 3 * unet->resolution() * unet->resolution();
+  std::unique_ptr<StreamBuf> own;
+  float* x0t = out_x0_pred;
+  if (!x0t) {
+    own.reset(new StreamBuf((size_t)n, st));
+    x0t = own->p;
+  }
+  if (out_x0 != x_T) CUDA_CHECK(cudaMemcpyAsync(out_x0, x_T, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  int have_x0 = 0;
+  sample_simplified_range(unet, d, sc, 0, sc->n_pairs, out_x0, x0t, &have_x0, y, noise, B, st);
 }
 
 }  // namespace ddnm
@@ -214,6 +228,13 @@ int ddnm_simplified_Ap(const ddnm_simple_deg* d, const float* y, int B, float* x
   DDNM_API_BEGIN
   SimpScalars s{};
   simp_launch<SF_AP>(make_deg(d), nullptr, nullptr, 0, nullptr, y, s, x, nullptr, B, (cudaStream_t)stream);
+  DDNM_API_END
+}
+int ddnm_sample_simplified_range(void* unet, const ddnm_simple_deg* d, const ddnm_schedule* sched, int k_begin, int k_end, float* xt,
+                                 float* x0_pred, int* have_x0, const float* y, const float* noise, int B, void* stream) {
+  DDNM_API_BEGIN
+  sample_simplified_range(static_cast<UNetEngine*>(unet), d, sched, k_begin, k_end, xt, x0_pred, have_x0, y, noise, B,
+                          (cudaStream_t)stream);
   DDNM_API_END
 }
 int ddnm_sample_simplified(void* unet, const ddnm_simple_deg* d, const ddnm_schedule* sched, const float* x_T, const float* y,

@@ -675,11 +675,9 @@ TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, 
 template <int BN, bool PAIR, bool DUAL>
 static void launch_bn(const TcLaunch& L, cudaStream_t stream) {
   using Cfg = TcCfg<BN, PAIR, DUAL>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set))
     CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, PAIR, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
   if (PAIR) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(L.grid);

@@ -181,6 +181,10 @@ class UNetModel(_EngineModel):
         self.out_channels = self.out_ch
         self.num_res_blocks = int(num_res_blocks)
         self.attention_resolutions = tuple(int(v) for v in attention_resolutions)   # downsample rates, as in the reference
+        # the reference computes int(mult * model_channels) (unet.py:484); the engine's config carries integer multipliers, so a
+        # fractional one (create_model's image_size=512 default starts with 0.5) is refused instead of being truncated to 0
+        if any(float(v) != int(v) for v in channel_mult):
+            raise NotImplementedError(f"ddnm_b200 UNetModel: non-integer channel multipliers {tuple(channel_mult)} are not built")
         self.channel_mult = tuple(int(v) for v in channel_mult)
         self.num_head_channels = int(num_head_channels)
         self.use_fp16 = bool(use_fp16)

@@ -2,8 +2,9 @@
 reference's signatures and return convention (``([x_0.cpu()], [x0_pred.cpu()])``).
 
 The whole loop runs inside libddnm_b200.so on the current CUDA stream without host round trips.  The Gaussian draws
-are taken from torch's generator in the reference's order (one ``randn_like`` per time pair, :65/:74) into a tape
-before the loop starts, so a run is seed-for-seed comparable with the reference on the same device.
+are taken from torch's generator in the reference's order (one ``randn_like`` per time pair, :65/:74), a bounded chunk of
+pairs at a time on a side stream while the previous chunk is being denoised (``NOISE_CHUNK_BYTES``), so a run is
+seed-for-seed comparable with the reference on the same device and its noise memory does not grow with the schedule.
 """
 import ctypes as C
 
@@ -16,6 +17,47 @@ from .operators import CS, Deblurring2D, GeneralA, SRConv, _Operator
 from .schedule import alpha_bar_table, time_pairs
 
 class_num = 951
+
+# Upper bound for ONE of the two noise buffers of the chunked loop (the other is being refilled on a side stream): the reference
+# draws one randn_like per pair and keeps none, so its noise memory is O(1); here it is 2 x NOISE_CHUNK_BYTES at most, whatever
+# T_sampling / travel_repeat are.
+NOISE_CHUNK_BYTES = 256 << 20
+
+
+def _chunked(n_pairs, x, run_range):
+    """Drive ``run_range(k0, k1, noise_chunk)`` over the schedule with the Gaussian draws produced chunk by chunk on a side stream
+    (double-buffered), in the reference's generator order: pair k gets the k-th ``randn_like(x)`` after the caller's last draw."""
+    per_pair = x.numel() * 4
+    K = max(1, min(n_pairs, NOISE_CHUNK_BYTES // per_pair))
+    main = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+    bufs = [torch.empty((K,) + tuple(x.shape), device=x.device, dtype=torch.float32) for _ in range(2 if n_pairs > K else 1)]
+    consumed = [None, None]
+    side.wait_stream(main)                                  # the buffers' allocation / earlier use of their memory
+    chunks = [(k0, min(n_pairs, k0 + K)) for k0 in range(0, n_pairs, K)]
+
+    def fill(c):
+        k0, k1 = chunks[c]
+        b = bufs[c % len(bufs)]
+        with torch.cuda.stream(side):
+            if consumed[c % 2] is not None:
+                side.wait_event(consumed[c % 2])
+            for k in range(k1 - k0):
+                b[k].normal_()                              # == torch.randn_like(x): same generator consumption, no extra copy
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return ev
+    ready = fill(0)
+    for c, (k0, k1) in enumerate(chunks):
+        nxt = fill(c + 1) if c + 1 < len(chunks) else None  # next chunk's draws overlap this chunk's denoising steps
+        main.wait_event(ready)
+        run_range(k0, k1, bufs[c % len(bufs)])
+        ev = torch.cuda.Event()
+        ev.record(main)
+        consumed[c % 2] = ev
+        ready = nxt
+    for b in bufs:
+        b.record_stream(side)                               # allocated on the caller's stream, written on the side stream
 
 
 def sample_device(x, model, b, eta, A_funcs, y, sigma_y, plus, config, noise=None, cls_fn=None):
@@ -42,11 +84,7 @@ def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, n
         ti = np.ascontiguousarray(np.array([p[0] for p in pairs], dtype=np.int32))
         tj = np.ascontiguousarray(np.array([p[1] for p in pairs], dtype=np.int32))
         x = x.float().contiguous()
-        if noise is None:
-            noise = torch.empty((len(pairs),) + tuple(x.shape), device=x.device, dtype=torch.float32)
-            for k in range(len(pairs)):
-                noise[k] = torch.randn_like(x)              # same generator consumption as the reference loop
-        else:
+        if noise is not None:                               # a caller-supplied tape (tests, seed-for-seed comparisons)
             assert noise.shape == (len(pairs),) + tuple(x.shape)
             noise = noise.to(x.device).float().contiguous()
         yv = y.reshape(n, -1).to(x.device, non_blocking=True).float().contiguous()
@@ -55,13 +93,27 @@ def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, n
         s.n_pairs, s.t_i, s.t_j, s.abar = len(pairs), ti.ctypes.data, tj.ctypes.data, abar.ctypes.data
         s.num_timesteps, s.eta, s.sigma_y = int(config.diffusion.num_diffusion_timesteps), float(eta), float(sigma_y)
         s.plus = 1 if plus else 0
-        out = torch.empty_like(x)
+        out = x.clone()                                     # the iterate, updated in place range by range
         x0p = torch.empty_like(x)
+        eng = model.engine(n)
+        have_x0 = C.c_int(0)
         if cls_fn is None:
-            _lib.check(_lib.lib().ddnm_sample(model.engine(n), A_funcs._h, C.byref(s), _lib.ptr(x), _lib.ptr(yv), _lib.ptr(noise), n,
-                                             _lib.ptr(out), _lib.ptr(x0p), _lib.cur_stream()))
+            labels = grad = fn = None
+            failure = []
         else:
-            _guided(x, model, A_funcs, s, yv, noise, n, cls_fn, out, x0p)
+            labels, grad, fn, failure = _guidance(x, model, n, cls_fn)
+
+        def run_range(k0, k1, chunk):
+            rc = _lib.lib().ddnm_sample_range(eng, A_funcs._h, C.byref(s), k0, k1, _lib.ptr(out), _lib.ptr(x0p), C.byref(have_x0),
+                                             _lib.ptr(yv), _lib.ptr(chunk), n, _lib.ptr(labels), _lib.ptr(grad), fn, None,
+                                             _lib.cur_stream())
+            if failure:
+                raise failure[0]
+            _lib.check(rc)
+        if noise is not None:
+            run_range(0, len(pairs), noise)
+        else:
+            _chunked(len(pairs), x, run_range)
         if not to_host:
             return out, x0p
         return [out.to("cpu")], [x0p.to("cpu")]
@@ -70,11 +122,12 @@ def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, n
 CLASS_NUM = 951   # functions/svd_ddnm.py:7
 
 
-def _guided(x, model, A_funcs, sched, yv, noise, n, cls_fn, out, x0p):
-    """Classifier-guided loop (svd_ddnm.py:48-52, :109-113).  As in the reference, the caller's ``classes`` are replaced by
+def _guidance(x, model, n, cls_fn):
+    """Classifier guidance (svd_ddnm.py:48-52, :109-113).  As in the reference, the caller's ``classes`` are replaced by
     ``class_num`` for every row, the denoiser is called as ``model(xt, t, classes)``, only channels 0..2 of its output are
     kept, and ``cls_fn`` is evaluated at ``x`` — the function's INPUT, not the current iterate.  ``cls_fn`` (the classifier's
-    autograd gradient, diffusion.py:181-189) is the caller's PyTorch callable; everything else runs in libddnm_b200.so."""
+    autograd gradient, diffusion.py:181-189) is the caller's PyTorch callable; everything else runs in libddnm_b200.so.
+    Returns (labels, grad buffer, C callback, list that collects an exception raised inside the callback)."""
     assert model.num_classes is not None, "must specify y if and only if the model is class-conditional"   # unet.py:644-646
     classes = torch.ones(n, dtype=torch.long, device=x.device) * CLASS_NUM
     labels = classes.to(torch.int32)
@@ -91,12 +144,7 @@ def _guided(x, model, A_funcs, sched, yv, noise, n, cls_fn, out, x0p):
         except BaseException as e:   # noqa: BLE001 — re-raised after the C call returns
             failure.append(e)
             return 1
-    fn = _lib.GuidanceFn(cb)
-    rc = _lib.lib().ddnm_sample_guided(model.engine(n), A_funcs._h, C.byref(sched), _lib.ptr(x), _lib.ptr(yv), _lib.ptr(noise), n,
-                                       _lib.ptr(labels), _lib.ptr(grad), fn, None, _lib.ptr(out), _lib.ptr(x0p), _lib.cur_stream())
-    if failure:
-        raise failure[0]
-    _lib.check(rc)
+    return labels, grad, _lib.GuidanceFn(cb), failure
 
 
 def ddnm_diffusion(x, model, b, eta, A_funcs, y, cls_fn=None, classes=None, config=None, noise=None):
@@ -163,17 +211,22 @@ def simplified_ddnm_plus(x, model, b, eta, degradation, y, sigma_y, config=None,
         ti = np.ascontiguousarray(np.array([p[0] for p in pairs], dtype=np.int32))
         tj = np.ascontiguousarray(np.array([p[1] for p in pairs], dtype=np.int32))
         x = x.float().contiguous()
-        if noise is None:
-            noise = torch.empty((len(pairs),) + tuple(x.shape), device=x.device, dtype=torch.float32)
-            for k in range(len(pairs)):
-                noise[k] = torch.randn_like(x)
-        else:
+        if noise is not None:
             noise = noise.to(x.device).float().contiguous()
         yv = y.to(x.device, non_blocking=True).float().contiguous()
         s = _lib.Schedule()
         s.n_pairs, s.t_i, s.t_j, s.abar = len(pairs), ti.ctypes.data, tj.ctypes.data, abar.ctypes.data
         s.num_timesteps, s.eta, s.sigma_y, s.plus = int(config.diffusion.num_diffusion_timesteps), float(eta), float(sigma_y), 1
-        out, x0p = torch.empty_like(x), torch.empty_like(x)
-        _lib.check(_lib.lib().ddnm_sample_simplified(model.engine(n), C.byref(degradation._d), C.byref(s), _lib.ptr(x), _lib.ptr(yv),
-                                                    _lib.ptr(noise), n, _lib.ptr(out), _lib.ptr(x0p), _lib.cur_stream()))
+        out, x0p = x.clone(), torch.empty_like(x)
+        eng = model.engine(n)
+        have_x0 = C.c_int(0)
+
+        def run_range(k0, k1, chunk):
+            _lib.check(_lib.lib().ddnm_sample_simplified_range(eng, C.byref(degradation._d), C.byref(s), k0, k1, _lib.ptr(out),
+                                                              _lib.ptr(x0p), C.byref(have_x0), _lib.ptr(yv), _lib.ptr(chunk), n,
+                                                              _lib.cur_stream()))
+        if noise is not None:
+            run_range(0, len(pairs), noise)
+        else:
+            _chunked(len(pairs), x, run_range)
         return [out.to("cpu")], [x0p.to("cpu")]

@@ -139,6 +139,18 @@ int ddnm_sample_guided(void* unet, void* op, const ddnm_schedule* sched, const f
                        const int* labels, const float* grad_buf, ddnm_guidance_fn fn, void* user, float* out_x0, float* out_x0_pred,
                        void* stream);
 
+/* Bounded-memory form of the same loop: pairs [k_begin, k_end) of the schedule, state in the caller's buffers, so a long
+ * schedule (T_sampling = 1000, time-travel) runs as several calls that each see only their own slice of the noise draws
+ * (the reference needs O(1) noise memory: one torch.randn_like per pair, svd_ddnm.py:65,74).
+ *   xt       [B,3,R,R] in/out: the iterate (x_T before the first range, xs[-1] after the last)
+ *   x0_pred  [B,3,R,R] in/out: the last UN-projected x0_t (travel-back pairs read it); *have_x0 (host int, in/out) says whether
+ *            it holds one yet (0 before the first range)
+ *   noise    [(k_end - k_begin),B,3,R,R]: the draws of exactly these pairs
+ * labels / grad_buf / fn / user as in ddnm_sample_guided (all NULL for the unguided loop). */
+int ddnm_sample_range(void* unet, void* op, const ddnm_schedule* sched, int k_begin, int k_end, float* xt, float* x0_pred,
+                      int* have_x0, const float* y, const float* noise, int B, const int* labels, const float* grad_buf,
+                      ddnm_guidance_fn fn, void* user, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * "Simplified" DDNM+ (guided_diffusion/diffusion.py:211-415, the README quick-start path): image-space operators composed
  * of mask (A1 = z*mask, :256), colour->gray (color2gray/gray2color, :33-42) and average pooling (AdaptiveAvgPool2d /
@@ -155,6 +167,10 @@ int ddnm_simplified_Ap(const ddnm_simple_deg* deg, const float* y, int B, float*
 /* schedule->sigma_y is the doubled level (diffusion.py:292); schedule->plus is ignored */
 int ddnm_sample_simplified(void* unet, const ddnm_simple_deg* deg, const ddnm_schedule* sched, const float* x_T, const float* y,
                            const float* noise, int B, float* out_x0, float* out_x0_pred, void* stream);
+
+/* pairs [k_begin, k_end) with caller-held state: same contract as ddnm_sample_range */
+int ddnm_sample_simplified_range(void* unet, const ddnm_simple_deg* deg, const ddnm_schedule* sched, int k_begin, int k_end, float* xt,
+                                 float* x0_pred, int* have_x0, const float* y, const float* noise, int B, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * The runner's I/O step either side of the loop (guided_diffusion/diffusion.py:533-603), device pointers throughout.

@@ -14,6 +14,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Without a CUDA device (the build container) the gpu-marked tests are skipped, so a bare `pytest tests` is green there."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def built_library():
     """The tests exercise the in-tree libddnm_b200.so; compile it first if this checkout has not been built yet
