@@ -268,8 +268,8 @@ int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const
   DDNM_API_BEGIN
   cudaStream_t s = (cudaStream_t)stream;
   Tmp tmp;
-  double* st = tmp.get<double>((size_t)N * C * 2);
-  CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)N * C * 2 * sizeof(double), s));
+  StatAcc* st = tmp.get<StatAcc>((size_t)N * C * 2);
+  CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)N * C * 2 * sizeof(StatAcc), s));
   View xv = mkview(const_cast<float*>(x), N, H, W, C);
   xv.st = st;
   xv.st_ld = C;

@@ -58,6 +58,15 @@ struct StreamBuf {
   StreamBuf& operator=(const StreamBuf&) = delete;
 };
 
+// One GroupNorm running sum: a 128-bit two's-complement fixed-point accumulator with 64 fractional bits.  Partial sums from many
+// CTAs are added with integer atomics, so the total does not depend on the order in which they arrive: a forward pass is
+// bit-reproducible run to run (floating-point atomics are not).  Range +-2^63, resolution 2^-64 (anything a float partial sum
+// below 2^-40 would lose is far under the fp32 noise of the statistics themselves).
+struct StatAcc {
+  unsigned long long lo;
+  long long hi;
+};
+
 // A strided NHWC fp32 activation view: element (n, y, x, c) at p[((n*H + y)*W + x)*ld + c].
 // ld >= C lets a tensor live inside a channel slice of a wider (concat) buffer.
 // st (optional): per-(image, channel) running sums for GroupNorm, st[(n*st_ld + c)*2 + {0,1}] = {sum, sum of squares}
@@ -66,7 +75,7 @@ struct StreamBuf {
 struct View {
   float* p = nullptr;
   int N = 0, H = 0, W = 0, C = 0, ld = 0;
-  double* st = nullptr;
+  StatAcc* st = nullptr;
   int st_ld = 0;
   long long pixels() const { return (long long)N * H * W; }
   View slice(int c0, int c) const {
@@ -239,6 +248,31 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
   const uint16_t mask = 3;
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
+}
+
+// acc += p, exactly (p is converted to the 128-bit fixed point without rounding unless it has bits below 2^-64) and independent
+// of the order of concurrent adds: the low word's carry is detected by the one thread whose add wrapped it.
+__device__ __forceinline__ void stat_add(StatAcc* acc, float p) {
+  const int bits = __float_as_int(p);
+  int ex = (bits >> 23) & 0xff;
+  unsigned long long m = (unsigned long long)(bits & 0x7fffff);
+  if (ex) m |= 0x800000ull; else ex = 1;          // |p| = m * 2^(ex - 150)
+  const int sh = ex - 150 + 64;                   // fixed = m * 2^sh
+  unsigned long long lo = 0, hi = 0;
+  if (sh >= 64) hi = m << min(sh - 64, 39);        // |p| >= 2^63 cannot occur for activation sums; clamp the shift
+  else if (sh > 0) { lo = m << sh; hi = m >> (64 - sh); }
+  else if (sh > -24) lo = m >> (-sh);
+  if (bits < 0) {                                 // two's-complement negate
+    lo = ~lo + 1ull;
+    hi = ~hi + (lo == 0ull ? 1ull : 0ull);
+  }
+  if ((lo | hi) == 0ull) return;
+  const unsigned long long old = atomicAdd(&acc->lo, lo);
+  const unsigned long long carry = (old + lo < old) ? 1ull : 0ull;
+  if ((hi | carry) != 0ull) atomicAdd(reinterpret_cast<unsigned long long*>(&acc->hi), hi + carry);
+}
+__device__ __forceinline__ double stat_value(const StatAcc& a) {
+  return ((double)a.hi * 18446744073709551616.0 + (double)a.lo) * (1.0 / 18446744073709551616.0);
 }
 
 // fp32 -> (hi, lo) fp16 pair: hi = rn(x) saturated to the finite fp16 range, lo = rn(x - hi).

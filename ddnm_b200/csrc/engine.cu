@@ -73,17 +73,17 @@ View UNetEngine::new_view(int H, int W, int C) {
 }
 
 // a [B][C][2] block of per-channel GroupNorm sums from the pool that one memset clears at the start of every forward
-double* UNetEngine::new_stats(int C) {
+StatAcc* UNetEngine::new_stats(int C) {
   const size_t need = (size_t)B_ * C * 2;
   if (stats_chunks_.empty() || stats_chunks_.back().used + need > stats_chunks_.back().cap) {
     StatsChunk c;
-    c.cap = std::max<size_t>(need, (size_t)1 << 20);   // doubles
+    c.cap = std::max<size_t>(need, (size_t)1 << 20);   // accumulators
     c.used = 0;
-    c.p = (double*)arena_.alloc(c.cap * sizeof(double));
+    c.p = (StatAcc*)arena_.alloc(c.cap * sizeof(StatAcc));
     stats_chunks_.push_back(c);
   }
   StatsChunk& c = stats_chunks_.back();
-  double* p = c.p + c.used;
+  StatAcc* p = c.p + c.used;
   c.used += need;
   return p;
 }
@@ -299,11 +299,11 @@ void UNetEngine::finalize() {
     throw;
   }
   tc_set_terms(prev);
-  // every GroupNorm sum is accumulated with atomics during the forward: clear the pool first
+  // every GroupNorm sum is accumulated with (integer, order-independent) atomics during the forward: clear the pool first
   std::vector<OpRecord> zero;
   for (const StatsChunk& c : stats_chunks_) {
-    double* sb = c.p;
-    const size_t sbytes = c.used * sizeof(double);
+    StatAcc* sb = c.p;
+    const size_t sbytes = c.used * sizeof(StatAcc);
     zero.push_back(OpRecord{"stats.zero", "memset", 0, (double)sbytes,
                             [=](cudaStream_t s) { CUDA_CHECK(cudaMemsetAsync(sb, 0, sbytes, s)); }});
   }

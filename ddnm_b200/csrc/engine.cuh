@@ -88,7 +88,7 @@ class UNetEngine {
   struct Param { float* p; long long n; };
   const float* P(const std::string& name, long long expect = -1) const;
   View new_view(int H, int W, int C);
-  double* new_stats(int C);
+  StatAcc* new_stats(int C);
   struct TcWeights { __half *hi, *lo; int ktot; };
   // main / side: full parameter names of the OIHW weight tensors ("" = absent)
   TcWeights prep_weights(const std::string& main, int Cout, int Cin, int taps, const std::string& side, int CinSide);
@@ -140,7 +140,7 @@ class UNetEngine {
   size_t hbuf_elems_ = 0;
   float *qkv_ = nullptr, *attS_ = nullptr, *attO_ = nullptr;
   __half *qkvh_ = nullptr, *qkvl_ = nullptr, *ph_ = nullptr, *pl_ = nullptr, *vth_ = nullptr, *vtl_ = nullptr;
-  struct StatsChunk { double* p; size_t cap, used; };
+  struct StatsChunk { StatAcc* p; size_t cap, used; };
   std::vector<StatsChunk> stats_chunks_;
   float *emb_ = nullptr, *temb0_ = nullptr, *temb_ = nullptr, *ca_all_ = nullptr, *freq_ = nullptr;
   int ca_total_ = 0;

@@ -11,22 +11,16 @@ __device__ __forceinline__ float swishf(float x) { return x / (1.0f + expf(-x));
 // ---------------------------------------------------------------------------------------------------------------
 // Per-channel sums for GroupNorm (torch.nn.GroupNorm(32, C): models.py:32-33 / nn.py:17-19) of a tensor that was NOT
 // produced by the tensor-core kernel (whose epilogue accumulates them itself).  One CTA = one image x one pixel chunk;
-// every thread owns 4 fixed channels (float4 loads along the contiguous NHWC channel axis), partial sums meet in
-// shared memory per channel, then one double atomicAdd pair per (CTA, channel).
+// every thread owns 4 fixed channels (float4 loads along the contiguous NHWC channel axis) and adds its partial sums to the
+// per-(image, channel) 128-bit fixed-point accumulators (StatAcc).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int ld, int pix_per_cta,
-                                double* __restrict__ stats, int st_ld) {
-  __shared__ float csum[MAX_C], csq[MAX_C];
+                                StatAcc* __restrict__ stats, int st_ld) {
   const int n = blockIdx.y;
   const int C4 = C >> 2;
   const int rows = blockDim.x / C4;
   const int c4 = threadIdx.x % C4;
   const int prow = threadIdx.x / C4;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    csum[i] = 0.f;
-    csq[i] = 0.f;
-  }
-  __syncthreads();
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
@@ -53,16 +47,14 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int 
       s[2] += v.z; q[2] += v.z * v.z;
       s[3] += v.w; q[3] += v.w * v.w;
     }
+    // every thread's partial sums (a fixed set of pixels, summed in a fixed order) go straight into the order-independent
+    // fixed-point accumulators: no floating-point atomics anywhere, so the statistics are bit-reproducible
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(&csum[c4 * 4 + j], s[j]);
-      atomicAdd(&csq[c4 * 4 + j], q[j]);
+      StatAcc* d = stats + ((size_t)n * st_ld + c4 * 4 + j) * 2;
+      stat_add(d, s[j]);
+      stat_add(d + 1, q[j]);
     }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomicAdd(&stats[((size_t)n * st_ld + c) * 2 + 0], (double)csum[c]);
-    atomicAdd(&stats[((size_t)n * st_ld + c) * 2 + 1], (double)csq[c]);
   }
 }
 
@@ -88,7 +80,7 @@ void gn_stats(const View& x, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------
 template <bool F32OUT>
 __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C, int ld, int N, int groups,
-                                const double* __restrict__ stats, int st_ld, const float* __restrict__ gamma,
+                                const StatAcc* __restrict__ stats, int st_ld, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu, int mode, int pix_per_cta,
                                 __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ out32,
                                 const float* __restrict__ ss, int ss_ld, __half* __restrict__ raw_hi,
@@ -105,12 +97,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
   if (stats) {
     const int cpg = C / groups;
     const double cnt = (double)HW * cpg;
-    const double2* gsrc = reinterpret_cast<const double2*>(stats + (size_t)n * st_ld * 2);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const double2 v = gsrc[c];
-      sd[2 * c] = v.x;
-      sd[2 * c + 1] = v.y;
-    }
+    const StatAcc* gsrc = stats + (size_t)n * st_ld * 2;
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sd[c] = stat_value(gsrc[c]);
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const int g0 = (c / cpg) * cpg;   // the group's channels are adjacent
@@ -243,7 +231,7 @@ static void gn_apply_launch(const View& x, int groups, bool normalise, const flo
   if (raw_hi) DDNM_CHECK(mode == SPLIT_SAME && raw_lo && !out32, "raw side output only with the plain split");
   DDNM_CHECK(x.C % 8 == 0 && x.C <= MAX_C && x.ld % 4 == 0, "gn_apply: unsupported channel count");
   if (mode == SPLIT_S2D || mode == SPLIT_AVG2) DDNM_CHECK(x.H % 2 == 0 && x.W % 2 == 0, "space-to-depth / avg-pool need even dims");
-  const double* stats = normalise ? x.st : nullptr;
+  const StatAcc* stats = normalise ? x.st : nullptr;
   if (normalise) DDNM_CHECK(x.st != nullptr && x.C % groups == 0, "normalisation needs the tensor's per-channel sums (View::st)");
   if (ss) DDNM_CHECK(normalise, "scale-shift needs a normalisation");
   const int HW = mode == SPLIT_AVG2 ? x.H * x.W / 4 : x.H * x.W;   // pixels the grid iterates over

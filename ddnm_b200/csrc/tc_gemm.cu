@@ -385,7 +385,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
       }
       if (p.stats) {
         // the warp's 32 rows lie in one image (>= 32 pixels per image): keep running sums while consecutive tiles stay in
-        // the same image / channel block, flush with one atomic pair per column otherwise
+        // the same image / channel block (the tile -> CTA map is static, so these fp32 partial sums are the same every run),
+        // flush with one order-independent fixed-point add pair per column otherwise
         const int img_w = n0 + (ew * 32) / (p.bw * p.bh);
         int next_img = -1, next_nidx = -1;
         if (u + unit_step < unit_end) {
@@ -397,9 +398,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
           if (img_w < p.N) {
 #pragma unroll
             for (int ch = 0; ch < CW / 32; ++ch) {
-              double* d = p.stats + ((size_t)img_w * p.st_ld + n_idx * BN + chalf * CW + ch * 32 + lane) * 2;
-              atomicAdd(d, (double)run_s[ch]);
-              atomicAdd(d + 1, (double)run_q[ch]);
+              StatAcc* d = p.stats + ((size_t)img_w * p.st_ld + n_idx * BN + chalf * CW + ch * 32 + lane) * 2;
+              stat_add(d, run_s[ch]);        // integer accumulation: the total is independent of the arrival order
+              stat_add(d + 1, run_q[ch]);
             }
           }
 #pragma unroll

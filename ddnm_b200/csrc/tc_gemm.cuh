@@ -33,7 +33,7 @@ struct TcParams {
   int ldr;
   int res_mode;                // 0: same pixel; 1: nearest-upsampled source (H/2 x W/2); 2: 2x2 average of a (2H x 2W) source
   float alpha;                 // out = alpha*acc + chanadd + residual
-  double* stats;               // optional GroupNorm sums of the OUTPUT: stats[(image*st_ld + co)*2 + {0,1}] += {sum, sumsq}
+  StatAcc* stats;              // optional GroupNorm sums of the OUTPUT: stats[(image*st_ld + co)*2 + {0,1}] += {sum, sumsq}
   int st_ld;
   int terms;                   // 3: hi*hi + hi*lo + lo*hi (fp32-grade, default); 1: hi*hi only (plain fp16 inputs, fast mode)
   uint32_t desc_hi;            // UMMA smem descriptor high word (SW128 K-major), see tc_gemm.cu

@@ -43,37 +43,7 @@ def ref_model(cfg, seed):
     return Model(c).eval()
 
 
-class cpu_shim:
-    """Redirect the reference's hard-coded device moves (svd_ddnm.py:45,72) and feed randn_like from a tape."""
-
-    def __init__(self, tape):
-        self.tape = list(tape)
-
-    def __enter__(self):
-        self._to, self._rl, self._ones = torch.Tensor.to, torch.randn_like, torch.ones
-        orig_to, orig_ones = self._to, self._ones
-
-        def ones(*a, **k):          # svd_ddnm.py:49,110 build the label vector with device=torch.device("cuda")
-            k.pop("device", None)
-            return orig_ones(*a, **k)
-        torch.ones = ones
-
-        def to(t, *a, **k):
-            if a and isinstance(a[0], str) and a[0].startswith("cuda"):
-                return t
-            return orig_to(t, *a, **k)
-        tape = self.tape
-
-        def randn_like(x, *a, **k):
-            z = tape.pop(0)
-            assert z.shape == x.shape
-            return z
-        torch.Tensor.to = to
-        torch.randn_like = randn_like
-        return self
-
-    def __exit__(self, *exc):
-        torch.Tensor.to, torch.randn_like, torch.ones = self._to, self._rl, self._ones
+from oracle.ref_shim import cpu_shim      # noqa: E402,F401  (the .to('cuda') / randn_like redirection)
 
 
 def close(a, b, tol, what):
@@ -502,6 +472,125 @@ def guided_fixtures():
     np.savez_compressed(os.path.join(GOLD, "guided_tiny.npz"), **out)
 
 
+# --------------------------------------------------------------------------------------------------
+from oracle.fullsize import FULLSIZE_CASES, fullsize_inputs, uni_kernel      # noqa: E402
+
+
+def fullsize_ops(wh_perm=None):
+    """Reference + oracle operators at 256x256 the way the runner builds them (diffusion.py:452-523)."""
+    from functions import svd_operators as R
+    ops = {}
+    r = R.SuperResolution(3, 256, 4, "cpu")
+    ops["sr4"] = (r, O.SuperResolution(3, 256, 4, r.U_small, r.singulars_small, r.V_small))
+    r = R.Colorization(256, "cpu")
+    ops["color"] = (r, O.Colorization(256, r.U_small, r.singulars_small, r.V_small))
+    mask = np.load(os.path.join(REF, "exp/inp_masks/mask.npy"))
+    r = _ref_inpainting(R, 3, 256, torch.from_numpy(mask).reshape(-1))
+    ops["inpaint"] = (r, O.Inpainting(3, 256, mask))
+    perm = torch.randperm(256 ** 2, generator=torch.Generator().manual_seed(4242)) if wh_perm is None else wh_perm
+    r = R.WalshHadamardCS(3, 256, 4, perm, "cpu")
+    ops["wh"] = (r, O.WalshHadamardCS(3, 256, 4, perm))
+    for name, k in (("deblur", gauss_kernel()), ("deblur_uni", uni_kernel())):
+        r = R.Deblurring(k, 3, 256, "cpu")
+        ops[name] = (r, O.Deblurring(3, 256, r.U_small, r.V_small, r._singulars, r._singulars_orig, r._perm))
+    return ops, mask, perm
+
+
+def fullsize_fixtures():
+    """BASELINE configs at their real size (256x256, the real celeba / imagenet networks with seeded random weights, the real
+    exp/inp_masks/mask.npy) through the UNMODIFIED reference samplers, plus the deblur_uni operator (diffusion.py:500-503) that
+    operators.npz lacks.  Stored: strided samples + sums of the reference results, the WH permutation, the mask bits and, for the
+    two Deblurring operators, the LAPACK-dependent artefacts (U_small, V_small, singulars, perm) so that another machine's
+    torch.svd cannot change the operator under test."""
+    from functions.svd_ddnm import ddnm_diffusion, ddnm_plus_diffusion
+    from functions import svd_operators as R
+    out = {}
+    ops, mask, perm = fullsize_ops()
+    out["mask_bits"] = np.packbits(mask.astype(np.uint8).reshape(-1))
+    out["wh_perm"] = perm.numpy().astype(np.int32)
+    for name in ("deblur", "deblur_uni"):
+        r = ops[name][0]
+        for k, v in dict(U_small=r.U_small, V_small=r.V_small, singulars=r._singulars, singulars_orig=r._singulars_orig,
+                         perm=r._perm).items():
+            out[f"{name}_art_{k}"] = v.numpy() if k != "perm" else v.numpy().astype(np.int32)
+    # ---- deblur_uni operator fixtures, dim 32 (full vectors + artefacts) and 256 (strided), as operator_fixtures does
+    for dim, B in ((32, 2), (256, 1)):
+        rng = torch.Generator().manual_seed(4321)
+        x = torch.rand(B, 3, dim, dim, generator=rng) * 2 - 1
+        v = torch.randn(B, 3 * dim * dim, generator=rng)
+        e = torch.randn(B, 3 * dim * dim, generator=rng)
+        tag = f"d{dim}_deblur_uni"
+        if dim == 32:
+            r = R.Deblurring(uni_kernel(), 3, dim, "cpu")
+            o = O.Deblurring(3, dim, r.U_small, r.V_small, r._singulars, r._singulars_orig, r._perm)
+            for k, a in dict(U_small=r.U_small, V_small=r.V_small, singulars=r._singulars, singulars_orig=r._singulars_orig,
+                             perm=r._perm).items():
+                out[f"{tag}_art_{k}"] = a.numpy()
+        else:
+            r, o = ops["deblur_uni"]
+        sub = (lambda z: z) if dim == 32 else (lambda z: z.reshape(B, -1)[:, ::61].contiguous())
+        y = r.A(x)
+        close(o.A(x.reshape(B, -1)), y, 2e-6, "deblur_uni A")
+        yq = y * 0.9 + 0.05
+        pin = r.A_pinv(yq.clone())
+        close(o.A_pinv(yq.clone()), pin, 2e-6, "deblur_uni A_pinv")
+        proj = x - r.A_pinv(r.A(x.reshape(B, -1)) - yq.reshape(B, -1)).reshape(x.shape)
+        close(o.project(x, yq), proj, 4e-6, "deblur_uni project")
+        out[f"{tag}_A"], out[f"{tag}_Apinv"], out[f"{tag}_proj"] = sub(y).numpy(), sub(pin).numpy(), sub(proj).numpy()
+        for ci, (a, sy, st) in enumerate(LAMBDA_CASES):
+            at, stt = torch.tensor(a), torch.tensor(st)
+            L = r.Lambda(v.clone(), at, sy, stt, 0.85)
+            Ln = r.Lambda_noise(v.clone(), at, sy, stt, 0.85, e.clone())
+            close(o.Lambda(v.clone(), at, sy, stt, 0.85), L, 4e-6, f"deblur_uni Lambda{ci}")
+            close(o.Lambda_noise(v.clone(), at, sy, stt, 0.85, e.clone()), Ln, 4e-6, f"deblur_uni Lnoise{ci}")
+            out[f"{tag}_L{ci}"], out[f"{tag}_Ln{ci}"] = sub(L).numpy(), sub(Ln).numpy()
+        print(f"operator deblur_uni@{dim}: ok")
+    # ---- real-size sampler runs through the reference
+    betas = SCH.linear_betas()
+    nets = {}
+
+    def net(kind):
+        if kind not in nets:
+            if kind == "celeba":
+                cfg = U.SimpleUNetConfig.celeba_hq()
+                m, sd = ref_model(cfg, 1234), U.init_state_dict(cfg, 1234)
+                fwd = lambda a, b: U.forward(sd, a, b, cfg)          # noqa: E731
+            else:
+                cfg = UO.OpenAIUNetConfig.imagenet_256()
+                m, sd = ref_openai(cfg, 1234), UO.init_state_dict(cfg, 1234)
+                m.load_state_dict(sd)
+                fwd = lambda a, b: UO.forward(sd, a, b, cfg)         # noqa: E731
+            nets[kind] = (m, fwd)
+        return nets[kind]
+    for key, kind, opname, T, tl, tr, sy in FULLSIZE_CASES:
+        m, fwd = net(kind)
+        rop, oop = ops[opname]
+        conf = ns(diffusion=ns(num_diffusion_timesteps=1000), time_travel=ns(T_sampling=T, travel_length=tl, travel_repeat=tr))
+        npairs = len(SCH.time_pairs(1000, T, tl, tr))
+        x_orig, x_T, tape, ynoise = fullsize_inputs(key, npairs)
+        y = rop.A(x_orig)
+        if sy > 0:
+            y = y + sy * ynoise[:, : y.shape[1]]
+        with torch.no_grad(), cpu_shim(tape):
+            if sy == 0.0:
+                xs, x0s = ddnm_diffusion(x_T, m, betas, 0.85, rop, y, config=conf)
+            else:
+                xs, x0s = ddnm_plus_diffusion(x_T, m, betas, 0.85, rop, y, sy, config=conf)
+        with torch.no_grad():
+            ox, ox0 = S.ddnm_sample(x_T, fwd, betas, 0.85, oop, y, tape, t_sampling=T, travel_length=tl, travel_repeat=tr, sigma_y=sy)
+        d = close(ox, xs[0], 2e-3, f"fullsize {key}")
+        close(ox0, x0s[0], 2e-3 * max(1.0, x0s[0].abs().max().item()), f"fullsize {key} x0")
+        r0, r1 = xs[0], x0s[0]
+        out[key + "_x0_s4"] = r0[:, :, ::4, ::4].contiguous().numpy()
+        out[key + "_x0pred_s4"] = r1[:, :, ::4, ::4].contiguous().numpy()
+        out[key + "_sums"] = np.array([r0.double().sum().item(), r0.double().abs().sum().item(), r1.double().sum().item(),
+                                       r1.double().abs().sum().item()])
+        out[key + "_resid"] = np.array([(rop.A(r0).reshape(1, -1) - y.reshape(1, -1)).abs().max().item()])
+        print(f"fullsize {key}: ok (oracle-ref {d:.2e}), npairs {npairs}, |A x0 - y| {out[key + '_resid'][0]:.2e}")
+    np.savez_compressed(os.path.join(GOLD, "fullsize.npz"), **out)
+
+
+
 def general_fixtures():
     """GeneralA (svd_operators.py:173-208): a dense 48 x 192 degradation with two singular values pushed under the
     1e-3 threshold so the zeroing branch (:185) is exercised."""
@@ -532,7 +621,7 @@ def general_fixtures():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["unet", "openai", "ops", "sampler", "simplified", "general", "runner", "guided"]
+    which = sys.argv[1:] or ["unet", "openai", "ops", "sampler", "simplified", "general", "runner", "guided", "fullsize"]
     if "general" in which:
         general_fixtures()
     if "guided" in which:
@@ -549,4 +638,6 @@ if __name__ == "__main__":
         sampler_fixtures()
     if "simplified" in which:
         simplified_fixtures()
+    if "fullsize" in which:
+        fullsize_fixtures()
     print("golden fixtures written to", GOLD)

@@ -258,6 +258,27 @@ def test_unet_fast_fp16_mode_is_close_but_flagged_non_parity(gold):
     assert err > 1e-5, "fast mode unexpectedly as accurate as the 3-term mode: is the flag wired?"
 
 
+def test_unet_forward_is_bit_reproducible():
+    """GroupNorm sums are accumulated by many CTAs with atomics; they are 128-bit fixed-point integer accumulators (StatAcc), so
+    the arrival order cannot change the result: every replay of a forward is bit-identical (eager and CUDA-graph alike)."""
+    cfg = U.SimpleUNetConfig.celeba_hq()
+    torch.manual_seed(17)
+    x = torch.randn(2, 3, 256, 256, device=dev)
+    t = torch.tensor([700.0, 31.0], device=dev)
+    for graph in (True, False):
+        m = _engine_model(cfg, graph)
+        first = m(x, t).clone()
+        for _ in range(3):
+            assert torch.equal(m(x, t), first), f"forward not reproducible (graph={graph})"
+    cfg = U.SimpleUNetConfig.tiny()
+    m = _engine_model(cfg)
+    x = torch.randn(4, 3, 32, 32, device=dev)
+    t = torch.tensor([10.0, 500.0, 999.0, 0.0], device=dev)
+    first = m(x, t).clone()
+    for _ in range(5):
+        assert torch.equal(m(x, t), first)
+
+
 def test_unet_batch_rows_independent():
     """Rows of a batch are independent trajectories (the property multi-GPU sharding relies on)."""
     cfg = U.SimpleUNetConfig.tiny()
