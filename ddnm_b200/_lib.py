@@ -71,7 +71,7 @@ _SIGS = {
     "ddnm_operator_destroy": (C.c_int, [_P]),
     "ddnm_sample": (C.c_int, [_P, _P, C.POINTER(Schedule), _P, _P, _P, _I, _P, _P, _P]),
     "ddnm_sample_guided": (C.c_int, [_P, _P, C.POINTER(Schedule), _P, _P, _P, _I, _P, _P, GuidanceFn, _P, _P, _P, _P]),
-    "ddnm_sample_range": (C.c_int, [_P, _P, C.POINTER(Schedule), _I, _I, _P, _P, C.POINTER(C.c_int), _P, _P, _I, _P, _P, GuidanceFn, _P, _P]),
+    "ddnm_sample_range": (C.c_int, [_P, _P, C.POINTER(Schedule), _I, _I, _P, _P, C.POINTER(C.c_int), _P, _P, _I, _P, _P, _P, _P, _P]),
     "ddnm_sample_simplified_range": (C.c_int, [_P, C.POINTER(SimpleDeg), C.POINTER(Schedule), _I, _I, _P, _P, C.POINTER(C.c_int), _P, _P,
                                                _I, _P]),
     "ddnm_simplified_A": (C.c_int, [C.POINTER(SimpleDeg), _P, _I, _P, _P]),
@@ -84,6 +84,9 @@ _SIGS = {
     "ddnm_conv_direct": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
     "ddnm_conv_tc_bench": (C.c_int, [_I, _I, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_D)]),
     "ddnm_groupnorm": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P]),
+    "ddnm_conv_gn_tc": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _I, _P, _I, _P, _P, _P, _I, C.POINTER(_F), _P]),
+    "ddnm_tc_debug_gn_desc_mode": (C.c_int, [_I]),
+    "ddnm_tc_debug_gn_fused": (C.c_int, [_I]),
     "ddnm_tc_debug_override": (C.c_int, [C.c_uint, C.c_uint]),
     "ddnm_tc_debug_force_bn": (C.c_int, [_I]),
     "ddnm_tc_debug_pair_dual": (C.c_int, [_I]),

@@ -160,6 +160,27 @@ void UNetEngine::emit_tc(const std::string& name, const SplitView& a, int mode, 
   add_op(name, "tc", L.flops, bytes, [L](cudaStream_t s) { tc_run(L, s); });
 }
 
+bool UNetEngine::fused_ok(const View& x, const View* side, int Cout, const View& out) const {
+  return terms_ == 3 && x.st != nullptr && tc_gn_eligible(x, side, Cout, out);
+}
+
+void UNetEngine::emit_tcgn(const std::string& name, const View& x, const std::string& norm, const float* ss, int ss_ld, const View* side,
+                           const TcWeights& w, int Cout, const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr) {
+  GnAffine gn;
+  gn.gamma = P(norm + ".weight", x.C);
+  gn.beta = P(norm + ".bias", x.C);
+  gn.eps = eps_;
+  gn.groups = groups_;
+  gn.silu = true;
+  gn.ss = ss;
+  gn.ss_ld = ss_ld;
+  TcGnLaunch L = tc_make_gn_launch(x, gn, side, w.hi, w.lo, Cout, out, chanadd, ca_ld, residual, ldr, num_sms_);
+  // algorithmic HBM bytes: the fp32 activation(s) in, the weights, the fp32 output (+ residual) — no fp16 planes
+  const double bytes = (double)x.pixels() * x.C * 4 + (side ? (double)side->pixels() * side->C * 4 : 0) + (double)Cout * w.ktot * 4 +
+                       (double)out.pixels() * Cout * 4 * (residual ? 2 : 1);
+  add_op(name, "tcgn", L.flops, bytes, [L](cudaStream_t s) { tc_gn_run(L, s); });
+}
+
 // scratch every program needs; split planes are shared by all convolutions of a forward (stream order serialises them)
 void UNetEngine::alloc_common(size_t split_elems, size_t hbuf_elems) {
   split_elems_ = split_elems;

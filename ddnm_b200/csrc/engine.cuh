@@ -104,6 +104,11 @@ class UNetEngine {
                      const float* ss = nullptr, int ss_ld = 0, SplitView* raw = nullptr);
   void emit_tc(const std::string& name, const SplitView& a, int mode, const SplitView* side, const TcWeights& w, int Cout,
                const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr, int res_mode = 0);
+  // fused form of emit_gn_split + emit_tc for 3x3 convolutions on rows >= 128 pixels wide (tc_gn_conv.cu): x is normalised (norm =
+  // parameter prefix), activated, split and convolved in one kernel; side = raw fp32 input of a 1x1 shortcut (extra K blocks)
+  bool fused_ok(const View& x, const View* side, int Cout, const View& out) const;
+  void emit_tcgn(const std::string& name, const View& x, const std::string& norm, const float* ss, int ss_ld, const View* side,
+                 const TcWeights& w, int Cout, const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr);
   // softmax(alpha * Q K^T) V for `heads` heads of width ch over T tokens; q/k/v live in the fp32 qkv_ buffer
   // ([token][qkv_ld], head h at column h*head_stride + {q_off, k_off, v_off}); result -> attO_ [token][heads*ch].
   // T % 128 == 0 runs both contractions on the tensor cores, otherwise (8x8 maps) on CUDA cores.

@@ -468,6 +468,13 @@ static CUtensorMap make_map_f16(const void* base, int rank, const uint64_t* dims
   return m;
 }
 
+// 3D map over a K-major [Cout][Ktot] fp16 weight matrix with a (64, box_rows, 1) box (used by the fused GroupNorm convolution)
+CUtensorMap tc_make_weight_map(const __half* w, int Ktot, int Cout, int box_rows) {
+  const uint64_t bd[3] = {(uint64_t)Ktot, (uint64_t)Cout, 1u};
+  const uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)box_rows, 1u};
+  return make_map_f16(w, 3, bd, bbox);
+}
+
 static uint32_t g_desc_hi_override = 0, g_idesc_xor = 0;
 static int g_terms = 3;
 void tc_set_terms(int terms) {

@@ -73,6 +73,49 @@ struct GemmOperand {
 TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int heads, int images, float* out,
                              long long out_sn, long long out_sy, long long out_sx, float alpha, int num_sms);
 
+// ---- fused GroupNorm + SiLU + split + 3x3 convolution (tc_gn_conv.cu): the A operand is produced inside the kernel ----
+struct GnAffine {
+  const float* gamma = nullptr;   // nullptr: no normalisation (raw split)
+  const float* beta = nullptr;
+  float eps = 1e-6f;
+  int groups = 32;
+  bool silu = true;
+  const float* ss = nullptr;      // optional per-(image, channel) [scale(C) | shift(C)] rows (use_scale_shift_norm, unet.py:250-252)
+  int ss_ld = 0;
+};
+struct TcGnParams {
+  TcParams t;                     // tiling, B operand, epilogue (tile = 128 pixels of one row; pairs only)
+  const float* x;                 // fp32 NHWC source of the 3x3 taps, row pitch x_ld
+  int x_ld;
+  const float* xs;                // optional fp32 NHWC source of the 1x1 side input (nin_shortcut), row pitch xs_ld
+  int xs_ld;
+  const StatAcc* st_in;           // per-(image, channel) sums of x (View::st)
+  int st_ld_in;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int groups;
+  const float* ss;
+  int ss_ld;
+  int silu, norm;
+  int desc_mode;                  // 0: shifted start address only; 1: + base-offset field (descriptor bits [49,52))
+};
+struct TcGnLaunch {
+  CUtensorMap bh, bl, b2;
+  TcGnParams g;
+  int BN = 128;
+  int grid = 0;
+  double flops = 0;
+};
+// x: fp32 activation with its GroupNorm sums; side: raw fp32 input of a 1x1 shortcut riding as extra K blocks (may be null);
+// w_hi/w_lo as for tc_make_launch with Ktot = 9*x.C + side.C.
+bool tc_gn_eligible(const View& x, const View* side, int Cout, const View& out);
+TcGnLaunch tc_make_gn_launch(const View& x, const GnAffine& gn, const View* side, const __half* w_hi, const __half* w_lo, int Cout,
+                             const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr, int num_sms);
+void tc_gn_run(const TcGnLaunch& L, cudaStream_t stream);
+void tc_debug_gn_desc_mode(int mode);   // tests: how the shifted A start address is described to the tensor core
+void tc_debug_gn_fused(int on);         // 1 (default): eligible layers use the fused kernel; 0: always gn_apply + conv_tc
+
 // debug knobs (tests only): override descriptor words for the NEXT launches built
 void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor);
 void tc_debug_force_bn(int bn);

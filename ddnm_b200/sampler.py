@@ -105,8 +105,8 @@ def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, n
 
         def run_range(k0, k1, chunk):
             rc = _lib.lib().ddnm_sample_range(eng, A_funcs._h, C.byref(s), k0, k1, _lib.ptr(out), _lib.ptr(x0p), C.byref(have_x0),
-                                             _lib.ptr(yv), _lib.ptr(chunk), n, _lib.ptr(labels), _lib.ptr(grad), fn, None,
-                                             _lib.cur_stream())
+                                             _lib.ptr(yv), _lib.ptr(chunk), n, _lib.ptr(labels), _lib.ptr(grad),
+                                             None if fn is None else C.cast(fn, C.c_void_p), None, _lib.cur_stream())
             if failure:
                 raise failure[0]
             _lib.check(rc)

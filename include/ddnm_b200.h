@@ -203,6 +203,16 @@ int ddnm_conv_direct(const float* x, int N, int H, int W, int Cin, const float* 
 int ddnm_conv_tc_bench(int N, int H, int W, int Cin, int Cout, int mode, int iters, float* ms_per_iter, double* flops);
 int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const float* gamma, const float* beta, float eps,
                    int silu, float* out, void* stream);
+/* The fused form the engine uses for the wide layers (rows >= 128 pixels): out = conv3x3(silu?(groupnorm(x))) [+ conv1x1(side_x)] + bias
+ * [+ residual] with the GroupNorm / SiLU / fp16 split applied INSIDE the convolution kernel (models.py:115-134 conv1 / conv2 +
+ * nin_shortcut).  gamma == NULL: no normalisation.  iters > 0 additionally times `iters` launches into *ms_per_iter. */
+int ddnm_conv_gn_tc(const float* x, int N, int H, int W, int Cin, int groups, const float* gamma, const float* beta, float eps, int silu,
+                    const float* w, const float* bias, int Cout, const float* side_x, int CinSide, const float* side_w,
+                    const float* residual, float* out, int iters, float* ms_per_iter, void* stream);
+/* tests: 0 = shifted start address only, 1 = shifted start address + descriptor base-offset field */
+int ddnm_tc_debug_gn_desc_mode(int mode);
+/* 1 (default): eligible layers run the fused GroupNorm convolution; 0: always gn_apply_kernel + conv_tc_kernel */
+int ddnm_tc_debug_gn_fused(int on);
 int ddnm_tc_debug_override(unsigned desc_hi, unsigned idesc_xor);
 /* tuning experiments: force the N-tile width of conv launches built afterwards (0 = heuristic) */
 int ddnm_tc_debug_force_bn(int bn);

@@ -1,0 +1,58 @@
+"""Diagnostic (GPU): the fused GroupNorm convolution against fp64 for both descriptor modes, plus timing vs the unfused pair."""
+import ctypes as C
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from ddnm_b200 import _lib   # noqa: E402
+
+dev = "cuda"
+
+
+def run(N, H, W, Cin, Cout, side_c=0, res=False, norm=True, silu=True, iters=0, seed=0):
+    L = _lib.lib()
+    torch.manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, device=dev) * 1.5 + 0.3
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    g, be = torch.randn(Cin, device=dev), torch.randn(Cin, device=dev)
+    side = torch.randn(N, side_c, H, W, device=dev) if side_c else None
+    sw = torch.randn(Cout, side_c, 1, 1, device=dev) / side_c ** 0.5 if side_c else None
+    r = torch.randn(N, Cout, H, W, device=dev) if res else None
+    nhwc = lambda t: None if t is None else t.permute(0, 2, 3, 1).contiguous()   # noqa: E731
+    out = torch.empty(N, H, W, Cout, device=dev)
+    ms = C.c_float(0)
+    xs, ss, rs = nhwc(x), nhwc(side), nhwc(r)
+    _lib.check(L.ddnm_conv_gn_tc(_lib.ptr(xs), N, H, W, Cin, 32, _lib.ptr(g) if norm else None, _lib.ptr(be) if norm else None, 1e-6,
+                                 int(silu), _lib.ptr(w), _lib.ptr(b), Cout, _lib.ptr(ss), side_c,
+                                 _lib.ptr(sw.contiguous()) if sw is not None else None, _lib.ptr(rs), _lib.ptr(out), iters, C.byref(ms), None))
+    torch.cuda.synchronize()
+    xd = x.double().cpu()
+    h = F.group_norm(xd, 32, g.double().cpu(), be.double().cpu(), 1e-6) if norm else xd
+    if silu and norm:
+        h = h * torch.sigmoid(h)
+    ref = F.conv2d(h, w.double().cpu(), b.double().cpu(), padding=1)
+    if side is not None:
+        ref = ref + F.conv2d(side.double().cpu(), sw.double().cpu())
+    if r is not None:
+        ref = ref + r.double().cpu()
+    got = out.permute(0, 3, 1, 2).double().cpu()
+    err = (got - ref).abs().max().item()
+    return err, ref.abs().max().item(), ms.value
+
+
+if __name__ == "__main__":
+    L = _lib.lib()
+    for mode in (0, 1):
+        L.ddnm_tc_debug_gn_desc_mode(mode)
+        for shape in [(2, 128, 128, 128, 128), (1, 256, 256, 64, 128), (2, 128, 128, 128, 256)]:
+            try:
+                err, sc, _ = run(*shape)
+                print(f"desc_mode {mode} shape {shape}: max err {err:.3e} (ref absmax {sc:.2f})", flush=True)
+            except Exception as e:
+                print(f"desc_mode {mode} shape {shape}: FAILED {str(e)[:200]}", flush=True)
+                sys.exit(1)

@@ -13,7 +13,6 @@ sys.path.insert(0, ROOT)
 from ddnm_b200 import operators as E                                   # noqa: E402
 from ddnm_b200.model import Model                                       # noqa: E402
 from ddnm_b200.sampler import sample_device                             # noqa: E402
-from ddnm_b200.schedule import linear_betas                             # noqa: E402
 from ddnm_b200.weights import random_state_dict                         # noqa: E402
 
 ns = types.SimpleNamespace
@@ -28,7 +27,8 @@ def main():
     model = Model(mcfg)
     model.load_state_dict(random_state_dict(mcfg, 1234))
     conf = ns(diffusion=ns(num_diffusion_timesteps=1000), time_travel=ns(T_sampling=2, travel_length=1, travel_repeat=1))
-    betas = linear_betas().to(dev)
+    import numpy as np
+    betas = torch.from_numpy(np.linspace(1e-4, 2e-2, 1000, dtype="float64")).float().to(dev)
     torch.manual_seed(0)
     x_orig = torch.rand(B, 3, 256, 256, device=dev) * 2 - 1
     x_T = torch.randn(B, 3, 256, 256, device=dev)
