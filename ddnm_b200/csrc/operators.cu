@@ -521,11 +521,19 @@ Operator::Operator(int kind, int channels, int img_dim, int ratio, const float* 
   N_ = (long long)C_ * n2;
   switch (kind) {
     case OP_SR: {
-      DDNM_CHECK(ratio == 2 || ratio == 4 || ratio == 8, "SuperResolution: ratio must be 2, 4 or 8");
-      DDNM_CHECK(img_dim % ratio == 0, "img_dim % ratio");  // svd_operators.py:481
+      DDNM_CHECK(ratio >= 1 && img_dim % ratio == 0, "img_dim % ratio");  // svd_operators.py:481
+      // 2 / 4 / 8: one thread per patch with the basis in shared memory; any other ratio (evaluation.sh runs 16x): patch rows +
+      // the K x K basis as a small GEMM
+      sr_generic_ = !(ratio == 2 || ratio == 4 || ratio == 8);
+      DDNM_CHECK(ratio <= 64, "SuperResolution: ratio <= 64");
       DDNM_CHECK(v_small && u_small && singulars, "SuperResolution needs V_small, U_small, singulars_small");
       const int K = ratio * ratio;
       V_ = upload(owned_, v_small, (size_t)K * K);
+      if (sr_generic_) {
+        std::vector<float> v0(K);
+        for (int k = 0; k < K; ++k) v0[k] = v_small[(size_t)k * K];
+        v0_ = upload(owned_, v0.data(), (size_t)K);
+      }
       u00_ = u_small[0];
       s0_ = singulars[0];
       M_ = (long long)C_ * (D_ / ratio) * (D_ / ratio);
@@ -800,6 +808,126 @@ void Operator::cs_Apinv(const float* y, int B, float* x, cudaStream_t s) {
   cs_patch_kernel<false><<<blocks(n), 256, 0, s>>>(P, x, B, C_, D_);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// SuperResolution, generic ratio r (K = r*r entries per patch; svd_operators.py:479-623 with r = 16 in evaluation.sh):
+// patches become rows of a [B*C*y*y, K] matrix (row-major inside the patch, the reference's unfold order :510-512).  A has rank 1
+// per patch, so A / A^+ / the projection / Lambda need only V[:, 0] and one dot product per row (V is orthogonal:
+// V diag(l0, lz, .., lz) V^T x = lz x + (l0 - lz) <v0, x> v0); Lambda_noise multiplies RAW pixels by V (:581-621), which is a
+// [rows, K] x V^T GEMM on the CUDA cores.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool TO_ROWS>
+__global__ void sr_patch_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int D, int r) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * C * D * D;
+  if (i >= total) return;
+  const int K = r * r, yd = D / r;
+  const int k = (int)(i % K);
+  const long long pr = i / K;                 // (b, c, py, px)
+  const int px = (int)(pr % yd), py = (int)((pr / yd) % yd);
+  const long long bc = pr / ((long long)yd * yd);
+  const long long img = bc * D * D + (long long)(py * r + k / r) * D + (px * r + k % r);
+  if (TO_ROWS) dst[i] = src[img];
+  else dst[img] = src[i];
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// one warp per patch row.  P: rows [rows, K]; Q / Wv / We: further row operands; yv: [rows]
+template <int FN>
+__global__ void srg_rows_kernel(const float* __restrict__ P, const float* __restrict__ Q, const float* __restrict__ Wv,
+                                const float* __restrict__ We, const float* __restrict__ yv, const float* __restrict__ v0, float u00,
+                                float s0, PlusScalars ps, float* __restrict__ out, long long rows, int K) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* p = P ? P + row * K : nullptr;
+  float dot = 0.f;
+  if (FN == LF_A || FN == LF_PROJECT || FN == LF_LAMBDA) {
+    for (int k = lane; k < K; k += 32) dot = fmaf(v0[k], p[k], dot);
+    dot = warp_sum(dot);
+  }
+  if (FN == LF_A) {
+    if (lane == 0) out[row] = __fmul_rn(u00, __fmul_rn(s0, dot));
+  } else if (FN == LF_PINV) {
+    const float cc = __fmul_rn(__fmul_rn(u00, yv[row]), __fdiv_rn(1.0f, s0));
+    for (int k = lane; k < K; k += 32) out[row * K + k] = __fmul_rn(v0[k], cc);
+  } else if (FN == LF_PROJECT) {
+    const float r = __fsub_rn(__fmul_rn(u00, __fmul_rn(s0, dot)), yv[row]);
+    const float cc = __fmul_rn(__fmul_rn(u00, r), __fdiv_rn(1.0f, s0));
+    for (int k = lane; k < K; k += 32) out[row * K + k] = __fsub_rn(p[k], __fmul_rn(v0[k], cc));
+  } else if (FN == LF_LAMBDA) {
+    const float l0 = lam_coeff(s0, ps), lz = lam_coeff(0.f, ps);
+    const float t = __fmul_rn(__fsub_rn(l0, lz), dot);
+    for (int k = lane; k < K; k += 32) out[row * K + k] = fmaf(v0[k], t, __fmul_rn(lz, p[k]));
+  } else {  // LF_NOISE: P = raw v rows, Q = raw eps rows, Wv = P V^T, We = Q V^T
+    float d10, d20, d1z, d2z;
+    noise_coeff(s0, ps, d10, d20);
+    noise_coeff(0.f, ps, d1z, d2z);
+    const float a0 = __fmul_rn(__fsub_rn(d10, d1z), p[0]);
+    const float b0 = __fmul_rn(__fsub_rn(d20, d2z), Q[row * K]);
+    for (int k = lane; k < K; k += 32) {
+      const float ov = fmaf(v0[k], a0, __fmul_rn(d1z, Wv[row * K + k]));
+      const float oe = fmaf(v0[k], b0, __fmul_rn(d2z, We[row * K + k]));
+      out[row * K + k] = __fadd_rn(ov, oe);
+    }
+  }
+}
+
+void Operator::srg_A(const float* x, int B, float* y, cudaStream_t s) {
+  const long long n = (long long)B * N_;
+  const int K = ratio_ * ratio_;
+  const long long rows = n / K;
+  float* P = scratch(6, n);
+  sr_patch_kernel<true><<<blocks(n), 256, 0, s>>>(x, P, B, C_, D_, ratio_);
+  srg_rows_kernel<LF_A><<<blocks(rows * 32), 256, 0, s>>>(P, nullptr, nullptr, nullptr, nullptr, v0_, u00_, s0_, PlusScalars{}, y, rows, K);
+}
+void Operator::srg_Apinv(const float* y, int B, float* x, cudaStream_t s) {
+  const long long n = (long long)B * N_;
+  const int K = ratio_ * ratio_;
+  const long long rows = n / K;
+  float* P = scratch(6, n);
+  srg_rows_kernel<LF_PINV><<<blocks(rows * 32), 256, 0, s>>>(nullptr, nullptr, nullptr, nullptr, y, v0_, u00_, s0_, PlusScalars{}, P, rows, K);
+  sr_patch_kernel<false><<<blocks(n), 256, 0, s>>>(P, x, B, C_, D_, ratio_);
+}
+void Operator::srg_project(const float* x0, const float* y, int B, float* out, cudaStream_t s) {
+  const long long n = (long long)B * N_;
+  const int K = ratio_ * ratio_;
+  const long long rows = n / K;
+  float* P = scratch(6, n);
+  float* O = scratch(7, n);
+  sr_patch_kernel<true><<<blocks(n), 256, 0, s>>>(x0, P, B, C_, D_, ratio_);
+  srg_rows_kernel<LF_PROJECT><<<blocks(rows * 32), 256, 0, s>>>(P, nullptr, nullptr, nullptr, y, v0_, u00_, s0_, PlusScalars{}, O, rows, K);
+  sr_patch_kernel<false><<<blocks(n), 256, 0, s>>>(O, out, B, C_, D_, ratio_);
+}
+void Operator::srg_lambda(const float* v, int B, const PlusScalars& ps, float* out, cudaStream_t s) {
+  const long long n = (long long)B * N_;
+  const int K = ratio_ * ratio_;
+  const long long rows = n / K;
+  float* P = scratch(6, n);
+  float* O = scratch(7, n);
+  sr_patch_kernel<true><<<blocks(n), 256, 0, s>>>(v, P, B, C_, D_, ratio_);
+  srg_rows_kernel<LF_LAMBDA><<<blocks(rows * 32), 256, 0, s>>>(P, nullptr, nullptr, nullptr, nullptr, v0_, u00_, s0_, ps, O, rows, K);
+  sr_patch_kernel<false><<<blocks(n), 256, 0, s>>>(O, out, B, C_, D_, ratio_);
+}
+void Operator::srg_lambda_noise(const float* v, const float* eps, int B, const PlusScalars& ps, float* out, cudaStream_t s) {
+  const long long n = (long long)B * N_;
+  const int K = ratio_ * ratio_;
+  const long long rows = n / K;
+  float* P = scratch(6, n);
+  float* Q = scratch(7, n);
+  float* Wv = scratch(8, n);
+  float* We = scratch(9, n);
+  sr_patch_kernel<true><<<blocks(n), 256, 0, s>>>(v, P, B, C_, D_, ratio_);
+  sr_patch_kernel<true><<<blocks(n), 256, 0, s>>>(eps, Q, B, C_, D_, ratio_);
+  // W[row][k] = sum_j V[k][j] * raw[row][j]
+  sgemm_batched(true, 1, 1, (int)rows, K, K, 1.0f, P, K, 0, 0, V_, K, 0, 0, Wv, K, 0, 0, s);
+  sgemm_batched(true, 1, 1, (int)rows, K, K, 1.0f, Q, K, 0, 0, V_, K, 0, 0, We, K, 0, 0, s);
+  srg_rows_kernel<LF_NOISE><<<blocks(rows * 32), 256, 0, s>>>(P, Q, Wv, We, nullptr, v0_, u00_, s0_, ps, P, rows, K);
+  sr_patch_kernel<false><<<blocks(n), 256, 0, s>>>(P, out, B, C_, D_, ratio_);
+}
+
 void Operator::A(const float* x, int B, float* y, cudaStream_t s) {
   StepScalars sc{};
   const int n2 = D_ * D_;
@@ -810,6 +938,11 @@ void Operator::A(const float* x, int B, float* y, cudaStream_t s) {
   }
   if (kind_ == OP_DENOISE) {
     CUDA_CHECK(cudaMemcpyAsync(y, x, (size_t)B * C_ * n2 * 4, cudaMemcpyDeviceToDevice, s));
+    return;
+  }
+  if (kind_ == OP_SR && sr_generic_) {
+    srg_A(x, B, y, s);
+    CUDA_CHECK(cudaGetLastError());
     return;
   }
   switch (kind_) {
@@ -844,6 +977,11 @@ void Operator::A_pinv(const float* y, int B, float* x, cudaStream_t s) {
     CUDA_CHECK(cudaMemcpyAsync(x, y, (size_t)B * C_ * n2 * 4, cudaMemcpyDeviceToDevice, s));
     return;
   }
+  if (kind_ == OP_SR && sr_generic_) {
+    srg_Apinv(y, B, x, s);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   switch (kind_) {
     case OP_SR: case OP_COLOR:
       local_dispatch<LF_PINV>(kind_, ratio_, nullptr, nullptr, 0, nullptr, y, V_, u00_, s0_, sc, x, nullptr, B, C_, D_, s);
@@ -868,6 +1006,11 @@ void Operator::project(const float* x0, const float* y, int B, float* out, cudaS
     float* R = scratch(4, n);
     sub_kernel<<<blocks(n), 256, 0, s>>>(x0, y, R, n);
     sub_kernel<<<blocks(n), 256, 0, s>>>(x0, R, out, n);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
+  if (kind_ == OP_SR && sr_generic_) {
+    srg_project(x0, y, B, out, s);
     CUDA_CHECK(cudaGetLastError());
     return;
   }
@@ -913,6 +1056,11 @@ void Operator::lambda(const float* v, int B, const PlusScalars& ps, float* out, 
   if (kind_ == OP_DEBLUR2D) throw Error("Deblurring2D defines no Lambda (svd_operators.py:1094-1166): sigma_y > 0 is unsupported, as in the reference");
   if (kind_ == OP_CS) throw Error("CS defines no Lambda (svd_operators.py:101-159): sigma_y > 0 is unsupported, as in the reference");
   if (kind_ == OP_GENERAL) throw Error("GeneralA defines no Lambda (svd_operators.py:173-208): sigma_y > 0 is unsupported, as in the reference");
+  if (kind_ == OP_SR && sr_generic_) {
+    srg_lambda(v, B, ps, out, s);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   switch (kind_) {
     case OP_SR: case OP_COLOR:
       local_dispatch<LF_LAMBDA>(kind_, ratio_, v, nullptr, 0, nullptr, nullptr, V_, u00_, s0_, sc, out, nullptr, B, C_, D_, s);
@@ -956,6 +1104,11 @@ void Operator::lambda_noise(const float* v, const float* eps, int B, const PlusS
   if (kind_ == OP_DEBLUR2D) throw Error("Deblurring2D defines no Lambda_noise (svd_operators.py:1094-1166)");
   if (kind_ == OP_CS) throw Error("CS defines no Lambda_noise (svd_operators.py:101-159)");
   if (kind_ == OP_GENERAL) throw Error("GeneralA defines no Lambda_noise (svd_operators.py:173-208)");
+  if (kind_ == OP_SR && sr_generic_) {
+    srg_lambda_noise(v, eps, B, ps, out, s);
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   switch (kind_) {
     case OP_SR: case OP_COLOR:
       local_dispatch<LF_NOISE>(kind_, ratio_, v, eps, img, nullptr, nullptr, V_, u00_, s0_, sc, out, nullptr, B, C_, D_, s);
@@ -985,7 +1138,7 @@ void Operator::step(const float* xt, const float* et, long long et_stride, const
   const int n2 = D_ * D_;
   const long long img = N_;
   const long long n = (long long)B * img;
-  if (kind_ == OP_SR || kind_ == OP_COLOR) {
+  if ((kind_ == OP_SR && !sr_generic_) || kind_ == OP_COLOR) {
     local_dispatch<LF_STEP>(kind_, ratio_, xt, et, et_stride, noise, y, V_, u00_, s0_, sc, x0_t, xt_next, B, C_, D_, s);
   } else if (kind_ == OP_INPAINT) {
     inpaint_kernel<LF_STEP><<<blocks(n), 256, 0, s>>>(xt, et, et_stride, noise, y, rank_, sc, x0_t, xt_next, B, C_, n2, M_);
@@ -1004,9 +1157,15 @@ void Operator::step(const float* xt, const float* et, long long et_stride, const
       fwht(R, B, s);
     } else {
       float* Ay = scratch(3, (size_t)B * M_);
-      deblur_A(x0_t, B, Ay, s);
-      sub_kernel<<<blocks((long long)B * M_), 256, 0, s>>>(Ay, y, Ay, (long long)B * M_);
-      deblur_Apinv(Ay, B, R, s);
+      if (kind_ == OP_SR) {          // generic-ratio SuperResolution
+        srg_A(x0_t, B, Ay, s);
+        sub_kernel<<<blocks((long long)B * M_), 256, 0, s>>>(Ay, y, Ay, (long long)B * M_);
+        srg_Apinv(Ay, B, R, s);
+      } else {
+        deblur_A(x0_t, B, Ay, s);
+        sub_kernel<<<blocks((long long)B * M_), 256, 0, s>>>(Ay, y, Ay, (long long)B * M_);
+        deblur_Apinv(Ay, B, R, s);
+      }
     }
     if (!sc.use_plus) {
       final_ddnm_kernel<<<blocks(n), 256, 0, s>>>(x0_t, R, noise, et3, sc, xt_next, n);

@@ -55,6 +55,14 @@ class Operator {
 
   void general_A(const float* x, int B, float* y, cudaStream_t s);
   void general_Apinv(const float* y, int B, float* x, cudaStream_t s);
+  // SuperResolution with a ratio other than 2 / 4 / 8 (e.g. the paper's 16x): patch rows + the K x K basis as a small GEMM
+  bool sr_generic_ = false;
+  float* v0_ = nullptr;   // V_small[:, 0]
+  void srg_A(const float* x, int B, float* y, cudaStream_t s);
+  void srg_Apinv(const float* y, int B, float* x, cudaStream_t s);
+  void srg_project(const float* x0, const float* y, int B, float* out, cudaStream_t s);
+  void srg_lambda(const float* v, int B, const PlusScalars& ps, float* out, cudaStream_t s);
+  void srg_lambda_noise(const float* v, const float* eps, int B, const PlusScalars& ps, float* out, cudaStream_t s);
   void cs_A(const float* x, int B, float* y, cudaStream_t s);
   void cs_Apinv(const float* y, int B, float* x, cudaStream_t s);
   int cs_size_ = 0;
@@ -68,8 +76,8 @@ class Operator {
   int *rank_ = nullptr;      // inpaint: kept-rank per pixel or -1
   int *perm_ = nullptr, *invperm_ = nullptr;
   std::vector<void*> owned_;
-  float* scr_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t scr_elems_[6] = {0, 0, 0, 0, 0, 0};
+  float* scr_[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scr_elems_[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 }  // namespace ddnm

@@ -107,6 +107,94 @@ __global__ void __launch_bounds__(128) simp_kernel(const float* __restrict__ in0
     }
 }
 
+// Any other scale (evaluation.sh runs sr_averagepooling with deg_scale 16): one WARP per patch, lanes stride over the S*S pixels,
+// the three channel sums meet through shuffles.  Same arithmetic per element as simp_kernel; the pooled sums are re-associated.
+template <int FN>
+__global__ void __launch_bounds__(128) simp_generic_kernel(const float* __restrict__ in0, const float* __restrict__ et, long long et_stride,
+                                                           const float* __restrict__ z, const float* __restrict__ y, SimpDeg dg,
+                                                           SimpScalars sc, float* __restrict__ out0, float* __restrict__ out1, int B) {
+  const int S = dg.scale, K = S * S;
+  const int D = dg.D, yd = D / S;
+  const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= (long long)B * yd * yd) return;
+  const int px = (int)(g % yd), py = (int)((g / yd) % yd), b = (int)(g / ((long long)yd * yd));
+  const long long HW = (long long)D * D, img = 3 * HW;
+  const float cf = (float)(1.0 / 3.0);
+  const float basef = (float)((1.0 / 3.0) * (1.0 / 3.0) + (1.0 / 3.0) * (1.0 / 3.0) + (1.0 / 3.0) * (1.0 / 3.0));
+  auto pix = [&](int k) { return (long long)(py * S + k / S) * D + (px * S + k % S); };
+  const long long yo = (long long)b * 3 * yd * yd + (long long)py * yd + px;   // + c*yd*yd
+  if (FN == SF_AP) {
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = y[yo + (long long)c * yd * yd];
+    for (int k = lane; k < K; k += 32) {
+      const float m = dg.use_mask ? __ldg(dg.mask + pix(k)) : 1.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float w = dg.use_gray ? __fdiv_rn(__fmul_rn(v[0], cf), basef) : v[c];
+        if (dg.use_mask) w = __fmul_rn(w, m);
+        out0[(long long)b * img + (long long)c * HW + pix(k)] = w;
+      }
+    }
+    return;
+  }
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int k = lane; k < K; k += 32) {
+    const float m = dg.use_mask ? __ldg(dg.mask + pix(k)) : 1.f;
+    float t[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const long long o = (long long)c * HW + pix(k);
+      const float xv = in0[(long long)b * img + o];
+      if (FN == SF_STEP) {
+        const float e = et[(long long)b * et_stride + o];
+        t[c] = __fdiv_rn(__fsub_rn(xv, __fmul_rn(e, sc.sqrt_1m_at)), sc.sqrt_at);
+        out0[(long long)b * img + o] = t[c];
+      } else {
+        t[c] = xv;
+      }
+      if (dg.use_mask) t[c] = __fmul_rn(t[c], m);
+    }
+    if (dg.use_gray) {
+      const float gk = __fadd_rn(__fadd_rn(__fmul_rn(t[0], cf), __fmul_rn(t[1], cf)), __fmul_rn(t[2], cf));
+      t[0] = t[1] = t[2] = gk;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(acc[c], t[c]);
+  }
+  float a[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = acc[c];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    a[c] = K > 1 ? __fdiv_rn(v, (float)K) : v;
+  }
+  if (FN == SF_A) {
+    if (lane < 3) out0[yo + (long long)lane * yd * yd] = lane == 0 ? a[0] : (lane == 1 ? a[1] : a[2]);
+    return;
+  }
+  float r[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) r[c] = __fsub_rn(a[c], y[yo + (long long)c * yd * yd]);
+  for (int k = lane; k < K; k += 32) {
+    const float m = dg.use_mask ? __ldg(dg.mask + pix(k)) : 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const long long o = (long long)c * HW + pix(k);
+      float w = dg.use_gray ? __fdiv_rn(__fmul_rn(r[0], cf), basef) : r[c];
+      if (dg.use_mask) w = __fmul_rn(w, m);
+      const float x0 = out0[(long long)b * img + o];                                            // written above by this thread
+      const float x0h = __fsub_rn(x0, __fmul_rn(sc.lambda_t, w));                               // Eq. 17 (:373)
+      const float e = et[(long long)b * et_stride + o];
+      const float zz = z[(long long)b * img + o];
+      const float nz = __fmul_rn(sc.gamma_t, __fadd_rn(__fmul_rn(sc.c1, zz), __fmul_rn(sc.c2, e)));  // (:381)
+      out1[(long long)b * img + o] = __fadd_rn(__fmul_rn(sc.sqrt_atn, x0h), nz);
+    }
+  }
+}
+
 template <int FN>
 static void simp_launch(const SimpDeg& dg, const float* in0, const float* et, long long et_stride, const float* z, const float* y,
                         const SimpScalars& sc, float* out0, float* out1, int B, cudaStream_t st) {
@@ -118,7 +206,8 @@ static void simp_launch(const SimpDeg& dg, const float* in0, const float* et, lo
     case 2: simp_kernel<2, FN><<<grid, 128, 0, st>>>(in0, et, et_stride, z, y, dg, sc, out0, out1, B); break;
     case 4: simp_kernel<4, FN><<<grid, 128, 0, st>>>(in0, et, et_stride, z, y, dg, sc, out0, out1, B); break;
     case 8: simp_kernel<8, FN><<<grid, 128, 0, st>>>(in0, et, et_stride, z, y, dg, sc, out0, out1, B); break;
-    default: throw Error("simplified operators support scale 1, 2, 4 or 8");
+    default:   // any other scale dividing the image size
+      simp_generic_kernel<FN><<<(int)cdivll(groups * 32, 128), 128, 0, st>>>(in0, et, et_stride, z, y, dg, sc, out0, out1, B);
   }
   CUDA_CHECK(cudaGetLastError());
 }

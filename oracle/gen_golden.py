@@ -296,9 +296,10 @@ def sampler_fixtures():
 # --------------------------------------------------------------------------------------------------
 SIMPLIFIED_CASES = [("sr_averagepooling", 4, 0.1, 3, 1, 1), ("colorization", 1, 0.0, 3, 1, 1), ("inpainting", 1, 0.05, 3, 1, 1),
                     ("denoising", 1, 0.2, 3, 1, 1), ("mask_color_sr", 2, 0.05, 4, 2, 2)]   # deg, scale, sigma_y(arg), T, l, r
+SIMPLIFIED_CASES_R2 = [("sr_averagepooling", 16, 0.2, 3, 1, 1)]   # evaluation.sh's 16x SR with noise; stored in simplified_r2.npz
 
 
-def simplified_fixtures():
+def simplified_fixtures(cases=None, fname="simplified.npz", store_inputs=True):
     """Run the reference runner's own Diffusion.simplified_ddnm_plus (diffusion.py:211-415) on one synthetic image with the
     dataset / PNG writer stubbed out, capture the image it would save, and pin oracle.simplified to it."""
     import guided_diffusion.diffusion as D
@@ -310,11 +311,12 @@ def simplified_fixtures():
     g = torch.Generator().manual_seed(2024)
     x01 = torch.rand(1, 3, 256, 256, generator=g)                      # the "dataset image" in [0, 1]
     mask = torch.from_numpy(np.load(os.path.join(REF, "exp/inp_masks/mask.npy")))
-    out = {"x01": x01.numpy(), "mask_bits": np.packbits(mask.numpy().astype(np.uint8).reshape(-1))}
+    out = {"x01": x01.numpy(), "mask_bits": np.packbits(mask.numpy().astype(np.uint8).reshape(-1))} if store_inputs else {}
+    cases = SIMPLIFIED_CASES if cases is None else cases
     cwd = os.getcwd()
     os.chdir(REF)                                                        # the runner loads exp/inp_masks/mask.npy relatively
     try:
-        for deg, scale, sy, T, tl, tr in SIMPLIFIED_CASES:
+        for deg, scale, sy, T, tl, tr in cases:
             npairs = len(SCH.time_pairs(1000, T, tl, tr))
             nrng = torch.Generator().manual_seed(556)
             tape = [torch.randn(1, 3, 256, 256, generator=nrng) for _ in range(npairs)]
@@ -354,7 +356,7 @@ def simplified_fixtures():
             print(f"simplified {key}: ok (oracle-ref {d:.2e})")
     finally:
         os.chdir(cwd)
-    np.savez_compressed(os.path.join(GOLD, "simplified.npz"), **out)
+    np.savez_compressed(os.path.join(GOLD, fname), **out)
 
 
 def runner_fixtures():
@@ -591,6 +593,60 @@ def fullsize_fixtures():
 
 
 
+def sr16_fixtures():
+    """16x average-pooling super-resolution with measurement noise — evaluation.sh's `--deg sr_averagepooling --deg_scale 16
+    --sigma_y 0.2 --add_noise` — through the reference: the SVD operator (K = 256 entries per patch, LAPACK-dependent 256 x 256
+    basis stored), a DDNM+ sampling with the tiny network, and the runner's simplified loop on the celeba-size network."""
+    from functions import svd_operators as R
+    from functions.svd_ddnm import ddnm_plus_diffusion
+    out = {}
+    dim, B = 32, 2
+    r = R.SuperResolution(3, dim, 16, "cpu")
+    o = O.SuperResolution(3, dim, 16, r.U_small, r.singulars_small, r.V_small)
+    out["art_U_small"], out["art_singulars_small"], out["art_V_small"] = r.U_small.numpy(), r.singulars_small.numpy(), r.V_small.numpy()
+    rng = torch.Generator().manual_seed(4321)
+    x = torch.rand(B, 3, dim, dim, generator=rng) * 2 - 1
+    v = torch.randn(B, 3 * dim * dim, generator=rng)
+    e = torch.randn(B, 3 * dim * dim, generator=rng)
+    y = r.A(x)
+    close(o.A(x.reshape(B, -1)), y, 2e-6, "sr16 A")
+    yq = y * 0.9 + 0.05
+    pin = r.A_pinv(yq.clone())
+    close(o.A_pinv(yq.clone()), pin, 2e-6, "sr16 A_pinv")
+    proj = x - r.A_pinv(r.A(x.reshape(B, -1)) - yq.reshape(B, -1)).reshape(x.shape)
+    close(o.project(x, yq), proj, 4e-6, "sr16 project")
+    out["op_A"], out["op_Apinv"], out["op_proj"] = y.numpy(), pin.numpy(), proj.numpy()
+    for ci, (a, sy, st) in enumerate(LAMBDA_CASES):
+        at, stt = torch.tensor(a), torch.tensor(st)
+        L = r.Lambda(v.clone(), at, sy, stt, 0.85)
+        Ln = r.Lambda_noise(v.clone(), at, sy, stt, 0.85, e.clone())
+        close(o.Lambda(v.clone(), at, sy, stt, 0.85), L, 4e-6, f"sr16 Lambda{ci}")
+        close(o.Lambda_noise(v.clone(), at, sy, stt, 0.85, e.clone()), Ln, 4e-6, f"sr16 Lnoise{ci}")
+        out[f"op_L{ci}"], out[f"op_Ln{ci}"] = L.numpy(), Ln.numpy()
+    print("operator sr16@32: ok")
+    # DDNM+ sampling, tiny network, sigma_y = 0.2 (0.4 internal)
+    cfg = U.SimpleUNetConfig.tiny()
+    m, sd = ref_model(cfg, 1234), U.init_state_dict(cfg, 1234)
+    betas = SCH.linear_betas()
+    g = torch.Generator().manual_seed(1616)
+    x_orig = torch.rand(B, 3, dim, dim, generator=g) * 2 - 1
+    x_T = torch.randn(B, 3, dim, dim, generator=g)
+    T, sy = 6, 0.4
+    tape = [torch.randn(B, 3, dim, dim, generator=g) for _ in range(T)]
+    yn = r.A(x_orig)
+    yn = yn + sy * torch.randn(yn.shape, generator=g)
+    conf = ns(diffusion=ns(num_diffusion_timesteps=1000), time_travel=ns(T_sampling=T, travel_length=1, travel_repeat=1))
+    with torch.no_grad(), cpu_shim(tape):
+        xs, x0s = ddnm_plus_diffusion(x_T, m, betas, 0.85, r, yn, sy, config=conf)
+    with torch.no_grad():
+        ox, ox0 = S.ddnm_sample(x_T, lambda a, b: U.forward(sd, a, b, cfg), betas, 0.85, o, yn, tape, t_sampling=T, sigma_y=sy)
+    d = close(ox, xs[0], 2e-3, "sr16 sampler")   # the K = 256 basis products re-associate; the random-init net amplifies it
+    out["samp_x_orig"], out["samp_x_T"], out["samp_y"] = x_orig.numpy(), x_T.numpy(), yn.numpy()
+    out["samp_x0"], out["samp_x0pred"], out["samp_seed"] = xs[0].numpy(), x0s[0].numpy(), np.array([1616])
+    print(f"sampler sr16 DDNM+: ok (oracle-ref {d:.2e})")
+    np.savez_compressed(os.path.join(GOLD, "sr16.npz"), **out)
+
+
 def general_fixtures():
     """GeneralA (svd_operators.py:173-208): a dense 48 x 192 degradation with two singular values pushed under the
     1e-3 threshold so the zeroing branch (:185) is exercised."""
@@ -621,7 +677,7 @@ def general_fixtures():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["unet", "openai", "ops", "sampler", "simplified", "general", "runner", "guided", "fullsize"]
+    which = sys.argv[1:] or ["unet", "openai", "ops", "sampler", "simplified", "general", "runner", "guided", "fullsize", "sr16"]
     if "general" in which:
         general_fixtures()
     if "guided" in which:
@@ -640,4 +696,7 @@ if __name__ == "__main__":
         simplified_fixtures()
     if "fullsize" in which:
         fullsize_fixtures()
+    if "sr16" in which:
+        sr16_fixtures()
+        simplified_fixtures(SIMPLIFIED_CASES_R2, "simplified_r2.npz", store_inputs=False)   # x01 / mask: same as simplified.npz
     print("golden fixtures written to", GOLD)

@@ -75,15 +75,16 @@ def test_fullsize_sampler_vs_reference(full, case):
     d1 = float(np.abs(x0s[0][:, :, ::4, ::4].numpy() - ref1).max())
     resid = float((oop.A(xs[0].reshape(1, -1)) - y).abs().max()) if sy == 0.0 else None
     _log(dict(test="fullsize_sampler_vs_reference", case=key, T=T, pairs=npairs, drift_x0=d0, drift_x0pred=d1,
-              x0pred_absmax=float(np.abs(ref1).max()), data_residual=resid))
-    # Short schedules: north_star's tolerance (absolute part scaled by the tensor's magnitude, x0_pred is O(10) early on).
-    # cfg1 (20 steps): the random-init network amplifies rounding differences — the oracle itself sits 3e-4 from the reference
-    # (gen_golden) — so the end-to-end gate is the drift bound below PLUS the exact data-consistency of the result; the per-step
-    # tolerance is enforced by test_fullsize_teacher_forced_steps.
-    atol0 = 3e-3 if T >= 10 else 1e-4
+              x0_absmax=float(np.abs(ref0).max()), x0pred_absmax=float(np.abs(ref1).max()), data_residual=resid))
+    # north_star's tolerance, rtol 1e-3 / atol 1e-4 with the absolute part following the tensor's magnitude: with random-init
+    # weights x_0 / x0_pred are not image-scaled (|x| up to 475 for cfg1, 74 for the imagenet cases).  Measured drifts (logged
+    # above; profiles/r02_fullsize_drift.jsonl): 1.2e-3 on |x| <= 475 after the 20 steps of cfg1 — the oracle itself sits 3e-4
+    # from the reference there (gen_golden) — and 3e-5 .. 8e-4 on the short schedules.  The per-step tolerance is enforced
+    # separately by test_fullsize_teacher_forced_steps (measured 2e-6 / 1.6e-5 of scale).
+    sc0 = max(1.0, float(np.abs(ref0).max()))
     sc1 = max(1.0, float(np.abs(ref1).max()))
-    assert_close(xs[0][:, :, ::4, ::4], ref0, 1e-3, atol0, f"{key}: x_0 vs reference")
-    assert_close(x0s[0][:, :, ::4, ::4], ref1, 1e-3, atol0 * sc1, f"{key}: x0_pred vs reference")
+    assert_close(xs[0][:, :, ::4, ::4], ref0, 1e-3, 1e-4 * sc0, f"{key}: x_0 vs reference")
+    assert_close(x0s[0][:, :, ::4, ::4], ref1, 1e-3, 1e-4 * sc1, f"{key}: x0_pred vs reference")
     sums = full[key + "_sums"]
     assert abs(xs[0].double().sum().item() - sums[0]) <= 2e-3 * sums[1]
     if sy == 0.0:
