@@ -36,6 +36,11 @@ class SimpleDeg(C.Structure):
                 ("mask", C.c_void_p)]
 
 
+class HqScalars(C.Structure):
+    _fields_ = [("c_recip", C.c_float), ("c_recipm1", C.c_float), ("coef1", C.c_float), ("coef2", C.c_float), ("lambda_t", C.c_float),
+                ("gamma_t", C.c_float), ("nonzero", C.c_float), ("clip", C.c_int)]
+
+
 class Schedule(C.Structure):
     _fields_ = [("n_pairs", C.c_int), ("t_i", C.c_void_p), ("t_j", C.c_void_p), ("abar", C.c_void_p),
                 ("num_timesteps", C.c_int), ("eta", C.c_float), ("sigma_y", C.c_float), ("plus", C.c_int)]
@@ -77,6 +82,9 @@ _SIGS = {
     "ddnm_simplified_A": (C.c_int, [C.POINTER(SimpleDeg), _P, _I, _P, _P]),
     "ddnm_simplified_Ap": (C.c_int, [C.POINTER(SimpleDeg), _P, _I, _P, _P]),
     "ddnm_sample_simplified": (C.c_int, [_P, C.POINTER(SimpleDeg), C.POINTER(Schedule), _P, _P, _P, _I, _P, _P, _P]),
+    "ddnm_hq_canvas": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "ddnm_hq_step": (C.c_int, [C.POINTER(SimpleDeg), _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, C.POINTER(HqScalars), _I, _P, _P, _P, _P]),
+    "ddnm_hq_undo": (C.c_int, [_P, _P, _F, _F, _LL, _P]),
     "ddnm_data_transform": (C.c_int, [_P, _LL, _P, _P, _I, _I, _P, _P]),
     "ddnm_inverse_data_transform": (C.c_int, [_P, _LL, _I, _I, _P, _P]),
     "ddnm_finish_images": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),

@@ -303,6 +303,16 @@ static void sample_simplified(UNetEngine* unet, const ddnm_simple_deg* d, const 
   sample_simplified_range(unet, d, sc, 0, sc->n_pairs, out_x0, x0t, &have_x0, y, noise, B, st);
 }
 
+// used by the hq_demo mask-shift step (hq.cu)
+void simplified_A(const ddnm_simple_deg* d, const float* x, int B, float* y, cudaStream_t st) {
+  SimpScalars s{};
+  simp_launch<SF_A>(make_deg(d), x, nullptr, 0, nullptr, nullptr, s, y, nullptr, B, st);
+}
+void simplified_Ap(const ddnm_simple_deg* d, const float* y, int B, float* x, cudaStream_t st) {
+  SimpScalars s{};
+  simp_launch<SF_AP>(make_deg(d), nullptr, nullptr, 0, nullptr, y, s, x, nullptr, B, st);
+}
+
 }  // namespace ddnm
 
 using namespace ddnm;

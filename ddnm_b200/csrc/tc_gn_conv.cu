@@ -80,18 +80,26 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     }
   }
 }
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 __device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-// x * sigmoid(x) with the fast exponential / reciprocal (relative error ~1e-6, far inside the fp32 parity tolerance)
-__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// 2^x on the special-function unit (x * sigmoid(x) = x / (1 + 2^(-x log2 e)); relative error ~1e-6, far inside the parity tolerance)
+__device__ __forceinline__ float exp2f_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two fp32 values -> packed fp16 hi pair + packed fp16 lo pair (hi = rn(x) saturated to the finite range, lo = rn(x - hi))
+__device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+  const float2 f = __half22float2(h);
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - f.y), "f"(x0 - f.x));
 }
 
 template <int BN>
@@ -365,59 +373,52 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
   } else {
     // ------------------------------------------------ transform warps ---------------------------------------------
     // Unit = one operand row block: (64-channel slice c, row offset dy) -> 130 halo pixels x 64 channels, or a 1x1 side slice ->
-    // 128 pixels x 64 channels.  Thread <-> 8 channels (32 bytes of fp32) of 5 rows: row = it*32 + tw*4 + (lane >> 3).
+    // 128 pixels x 64 channels.  Thread <-> 4 channels (one 16-byte fp32 load, fully coalesced: 16 lanes cover a pixel's 256 bytes)
+    // of up to 9 rows: row = i*16 + tw*2 + (lane >> 4).  The NEXT unit's loads are issued before this unit is converted (two
+    // register buffers), so the global-memory latency hides behind the conversion of the previous unit.
     const int tw = warp - 6;
-    const int rsub = lane >> 3, ch8 = lane & 7;
+    const int half = lane >> 4, c4 = lane & 15;
     const int tt = threadIdx.x - 6 * 32;     // 0..255 within the transform group
-    constexpr int NIT = 5;
-    struct It { int u, j; };
-    auto advance = [&](It& it) {
-      if (++it.j == upt) {
-        it.j = 0;
-        it.u += unit_step;
-      }
+    constexpr int NIT = 9;
+    const int row0 = tw * 2 + half;          // + 16*i
+    // per-thread constant part of the swizzled smem offset: 16-byte chunk (c4 >> 1) ^ (row & 7), 8-byte half (c4 & 1)
+    struct Unit {
+      const float* base;   // first pixel of the row block for this thread's channels (nullptr: the whole block is padding)
+      int nrows, px0, ld, n, c, side;
     };
-    // global loads of one unit into registers (zero for padding / rows the warp does not own)
-    auto load_unit = [&](const It& it, float4 (&buf)[NIT][2]) {
-#pragma unroll
-      for (int i = 0; i < NIT; ++i) {
-        buf[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        buf[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int t_x0 = 0, t_y = 0, t_n = 0;          // tile of the unit iterator (decoded once per tile: integer divisions are slow)
+    auto unit_of = [&](int u, int j) {
+      Unit q;
+      if (j == 0) {
+        int n_idx;
+        decode(tile_of(u), n_idx, t_x0, t_y, t_n);
       }
-      if (it.u >= unit_end) return;
-      int n_idx, x0, y, n;
-      decode(tile_of(it.u), n_idx, x0, y, n);
-      const bool side = it.j >= 3 * cb0;
-      const int c = side ? it.j - 3 * cb0 : it.j / 3;
-      const int yy = side ? y : y + (it.j - 3 * c) - 1;
-      if (yy < 0 || yy >= p.H) return;
-      const float* base = side ? g.xs + ((long long)n * p.H + yy) * p.W * g.xs_ld + c * GK + ch8 * 8
-                               : g.x + ((long long)n * p.H + yy) * p.W * g.x_ld + c * GK + ch8 * 8;
-      const int ld = side ? g.xs_ld : g.x_ld;
-      const int nrows = side ? 128 : 130;
-      const int px0 = side ? x0 : x0 - 1;
+      const int x0 = t_x0, y = t_y;
+      q.n = t_n;
+      q.side = j >= 3 * cb0;
+      q.c = q.side ? j - 3 * cb0 : j / 3;
+      const int yy = q.side ? y : y + (j - 3 * q.c) - 1;
+      q.nrows = q.side ? 128 : 130;
+      q.px0 = q.side ? x0 : x0 - 1;
+      q.ld = q.side ? g.xs_ld : g.x_ld;
+      const float* src = q.side ? g.xs : g.x;
+      q.base = (yy >= 0 && yy < p.H) ? src + ((long long)q.n * p.H + yy) * p.W * q.ld + q.c * GK + c4 * 4 : nullptr;
+      return q;
+    };
+    auto load_unit = [&](const Unit& q, float4 (&buf)[NIT]) {
 #pragma unroll
       for (int i = 0; i < NIT; ++i) {
-        const int r = i * 32 + tw * 4 + rsub;
-        const int px = px0 + r;
-        if (r < nrows && px >= 0 && px < p.W) {
-          const float* s = base + (long long)px * ld;
-          buf[i][0] = ldg_nc_f4(s);
-          buf[i][1] = ldg_nc_f4(s + 4);
-        }
+        const int r = i * 16 + row0;
+        const int px = q.px0 + r;
+        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q.base != nullptr && r < q.nrows && px >= 0 && px < p.W) buf[i] = ldg_nc_f4(q.base + (long long)px * q.ld);
       }
     };
     int cur_n = -1;
     uint32_t ua = 0, a_phase = 0;
-    // normalise + SiLU + split + swizzled store of one unit, then publish it
-    auto store_unit = [&](const It& it, float4 (&buf)[NIT][2]) {
-      int n_idx, x0, y, n;
-      decode(tile_of(it.u), n_idx, x0, y, n);
-      const bool side = it.j >= 3 * cb0;
-      const int c = side ? it.j - 3 * cb0 : it.j / 3;
-      const int yy = side ? y : y + (it.j - 3 * c) - 1;
-      const bool rowvalid = yy >= 0 && yy < p.H;
-      if (!side && n != cur_n) {
+    const float kNegLog2e = -1.4426950408889634f;
+    auto store_unit = [&](const Unit& q, float4 (&buf)[NIT]) {
+      if (!q.side && q.n != cur_n) {
         // per-(image, channel) affine of the GroupNorm (+ scale-shift) from the producer's running sums: y = a*x + b
         named_bar_sync(1, 256);              // everyone is done with the previous image's table
         const int C = cb0 * GK;
@@ -427,8 +428,8 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
             const int cpg = C / g.groups;
             const int g0 = (ch / cpg) * cpg;
             double s1 = 0, s2 = 0;
-            for (int q = 0; q < cpg; ++q) {
-              const StatAcc* sp = g.st_in + ((size_t)n * g.st_ld_in + g0 + q) * 2;
+            for (int k = 0; k < cpg; ++k) {
+              const StatAcc* sp = g.st_in + ((size_t)q.n * g.st_ld_in + g0 + k) * 2;
               s1 += stat_value(sp[0]);
               s2 += stat_value(sp[1]);
             }
@@ -440,52 +441,50 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
             a = rstd * g.gamma[ch];
             b = g.beta[ch] - (float)mean * a;
             if (g.ss) {                      // h = norm(h) * (1 + scale) + shift   (unet.py:250-252)
-              const float one_plus = 1.0f + g.ss[(size_t)n * g.ss_ld + ch];
+              const float one_plus = 1.0f + g.ss[(size_t)q.n * g.ss_ld + ch];
               a *= one_plus;
-              b = fmaf(b, one_plus, g.ss[(size_t)n * g.ss_ld + C + ch]);
+              b = fmaf(b, one_plus, g.ss[(size_t)q.n * g.ss_ld + C + ch]);
             }
           }
           coef[ch] = make_float2(a, b);
         }
         named_bar_sync(1, 256);
-        cur_n = n;
+        cur_n = q.n;
       }
-      float a8[8], b8[8];
-      if (!side) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float2 ab = coef[c * GK + ch8 * 8 + q];
-          a8[q] = ab.x;
-          b8[q] = ab.y;
-        }
+      float a4[4] = {1.f, 1.f, 1.f, 1.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!q.side) {
+        const float4 ab0 = *reinterpret_cast<const float4*>(&coef[q.c * GK + c4 * 4]);
+        const float4 ab1 = *reinterpret_cast<const float4*>(&coef[q.c * GK + c4 * 4 + 2]);
+        a4[0] = ab0.x; b4[0] = ab0.y; a4[1] = ab0.z; b4[1] = ab0.w;
+        a4[2] = ab1.x; b4[2] = ab1.y; a4[3] = ab1.z; b4[3] = ab1.w;
       }
+      const bool act = !q.side && g.silu;
       mbar_wait(a_empty(ua), a_phase ^ 1u);
-      const uint32_t hi_base = a_ring + ua * G_AUNIT, lo_base = hi_base + G_APLANE;
-      const int nrows = side ? 128 : 130;
-      const int px0 = side ? x0 : x0 - 1;
+      // 16-byte chunk (c4 >> 1) ^ (row & 7), 8-byte half (c4 & 1); row & 7 == row0 & 7 for every row of this thread
+      const uint32_t hi_base = a_ring + ua * G_AUNIT + (uint32_t)row0 * 128u + (uint32_t)((((c4 >> 1) ^ (row0 & 7)) << 4) + (c4 & 1) * 8);
+      const uint32_t lo_base = hi_base + G_APLANE;
 #pragma unroll
       for (int i = 0; i < NIT; ++i) {
-        const int r = i * 32 + tw * 4 + rsub;
-        if (i * 32 + tw * 4 < nrows) {       // warp-uniform
-          if (r < nrows) {
-            const int px = px0 + r;
-            const bool ok = rowvalid && px >= 0 && px < p.W;
-            float v[8] = {buf[i][0].x, buf[i][0].y, buf[i][0].z, buf[i][0].w, buf[i][1].x, buf[i][1].y, buf[i][1].z, buf[i][1].w};
-            __half h8[8], l8[8];
+        const int r = i * 16 + row0;
+        if (r < q.nrows) {
+          // padding pixels / rows were loaded as zeros; their ACTIVATED value must be zero as well (conv zero padding)
+          const int px = q.px0 + r;
+          const bool ok = q.base != nullptr && px >= 0 && px < p.W;
+          float t[4] = {buf[i].x, buf[i].y, buf[i].z, buf[i].w};
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float t = v[q];
-              if (!side) {
-                t = fmaf(t, a8[q], b8[q]);
-                if (g.silu) t = silu_fast(t);
-              }
-              if (!ok) t = 0.f;               // zero padding applies to the ACTIVATED tensor
-              split_f16(t, h8[q], l8[q]);
+          for (int k = 0; k < 4; ++k) {
+            t[k] = fmaf(t[k], a4[k], b4[k]);
+            if (act) {
+              const float e = exp2f_fast(t[k] * kNegLog2e);
+              t[k] = __fdividef(t[k], 1.0f + e);
             }
-            const uint32_t off = (uint32_t)r * 128u + (uint32_t)((ch8 ^ (r & 7)) << 4);
-            st_shared_v4(hi_base + off, make_uint4(pack_h2(h8[0], h8[1]), pack_h2(h8[2], h8[3]), pack_h2(h8[4], h8[5]), pack_h2(h8[6], h8[7])));
-            st_shared_v4(lo_base + off, make_uint4(pack_h2(l8[0], l8[1]), pack_h2(l8[2], l8[3]), pack_h2(l8[4], l8[5]), pack_h2(l8[6], l8[7])));
           }
+          uint32_t h01, h23, l01, l23;
+          split2_f16(t[0], t[1], h01, l01);
+          split2_f16(t[2], t[3], h23, l23);
+          if (!ok) h01 = h23 = l01 = l23 = 0u;
+          st_shared_v2(hi_base + (uint32_t)i * 2048u, h01, h23);       // row r = row0 + 16 i: same swizzle phase for every i
+          st_shared_v2(lo_base + (uint32_t)i * 2048u, l01, l23);
         }
       }
       fence_proxy_async_smem();              // generic-proxy stores -> visible to the tensor core's (async proxy) reads
@@ -496,20 +495,34 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
         a_phase ^= 1u;
       }
     };
-    float4 buf0[NIT][2], buf1[NIT][2];
-    It cur{unit_begin, 0};
-    It nxt = cur;
-    load_unit(cur, buf0);
-    while (cur.u < unit_end) {
-      advance(nxt);
-      load_unit(nxt, buf1);                  // next unit's loads are in flight while this one is transformed
-      store_unit(cur, buf0);
-      cur = nxt;
-      if (cur.u >= unit_end) break;
-      advance(nxt);
-      load_unit(nxt, buf0);
-      store_unit(cur, buf1);
-      cur = nxt;
+    float4 buf0[NIT], buf1[NIT];
+    int u = unit_begin, j = 0;
+    if (u < unit_end) {
+      Unit cur = unit_of(u, j);
+      load_unit(cur, buf0);
+      while (true) {
+        // ---- even step: convert buf0 while buf1 fills
+        if (++j == upt) { j = 0; u += unit_step; }
+        Unit nxt = cur;
+        const bool more0 = u < unit_end;
+        if (more0) {
+          nxt = unit_of(u, j);
+          load_unit(nxt, buf1);
+        }
+        store_unit(cur, buf0);
+        if (!more0) break;
+        cur = nxt;
+        // ---- odd step: convert buf1 while buf0 fills
+        if (++j == upt) { j = 0; u += unit_step; }
+        const bool more1 = u < unit_end;
+        if (more1) {
+          nxt = unit_of(u, j);
+          load_unit(nxt, buf0);
+        }
+        store_unit(cur, buf1);
+        if (!more1) break;
+        cur = nxt;
+      }
     }
   }
 

@@ -173,6 +173,30 @@ int ddnm_sample_simplified_range(void* unet, const ddnm_simple_deg* deg, const d
                                  float* x0_pred, int* have_x0, const float* y, const float* noise, int B, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * hq_demo: arbitrary-size restoration with the mask-shift trick (hq_demo/guided_diffusion/gaussian_diffusion.py:318-390 "DDNM core",
+ * :431-493 p_sample, :208-217 _undo, :578-750 window loop).  The window / time loops are host code (ddnm_b200/hq.py, as in the
+ * reference); these entry points do the tensor work of one step on 256 x 256 windows.
+ *   ddnm_hq_canvas: Apy_temp = Ap(A_temp(gt)) for gt (B,3,H,W), H % scale == W % scale == 0 (:651-655; use_gray: colour->gray first)
+ *   ddnm_hq_step  : x0_t = clip(c_recip*x - c_recipm1*eps); x0_hat = lambda_t*Apy + x0_t - lambda_t*Ap(A(x0_t)); the two
+ *                   rectangles rects[0..5], rects[6..11] = {dst_y, dst_x, h, w, src_y, src_x} (h == 0: unused) of x0_hat are
+ *                   overwritten from the canvas (:344-384); mean = coef1*x0_hat + coef2*x (+ gamma_t*grad, :414-430);
+ *                   x_next = mean + nonzero*sqrt(gamma_t)*noise.  scratch: 3*B*3*D*D floats.
+ *   ddnm_hq_undo  : x = sqrt(1-beta)*x + sqrt(beta)*noise (time-travel back step)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  float c_recip, c_recipm1;   /* sqrt_recip_alphas_cumprod[t], sqrt_recipm1_alphas_cumprod[t] */
+  float coef1, coef2;         /* posterior_mean_coef1[t], posterior_mean_coef2[t] */
+  float lambda_t, gamma_t;    /* Eq. 19 */
+  float nonzero;              /* 0 at t == 0, else 1 */
+  int clip;                   /* clip_denoised */
+} ddnm_hq_scalars;
+int ddnm_hq_canvas(const float* gt, int B, int H, int W, int scale, int use_gray, float* apy_canvas, void* stream);
+int ddnm_hq_step(const ddnm_simple_deg* deg, const float* x, const float* model_out, int out_ch, const float* apy, const float* canvas,
+                 int canvas_h, int canvas_w, const int* rects, const float* grad, const float* noise, const ddnm_hq_scalars* sc, int B,
+                 float* x0_hat, float* x_next, float* scratch, void* stream);
+int ddnm_hq_undo(float* x, const float* noise, float sqrt_one_minus_beta, float sqrt_beta, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * The runner's I/O step either side of the loop (guided_diffusion/diffusion.py:533-603), device pointers throughout.
  * ddnm_data_transform         = datasets/__init__.py:201-213 data_transform.  uniform_noise / gauss_noise: the torch.rand_like /
  *                               torch.randn_like draws of config.data.{uniform,gaussian}_dequantization, NULL when the flag is off;

@@ -647,6 +647,81 @@ def sr16_fixtures():
     np.savez_compressed(os.path.join(GOLD, "sr16.npz"), **out)
 
 
+def hq_fixtures():
+    """hq_demo's arbitrary-size restoration (mask-shift trick) through ITS OWN code: create_model_and_diffusion + SpacedDiffusion.
+    p_sample_loop (hq_demo/guided_diffusion/gaussian_diffusion.py:318-390, :578-750) on a 256 x 384 canvas (two windows, the second
+    one irregular: W % 128 == 0 here so also a 320-wide case), a small class-conditional UNet (64 base channels, 256 x 256 input,
+    learn_sigma), 4x average-pooling SR with and without measurement noise, a short jump schedule with time travel.  Must run in
+    a process that has not imported the main reference's `guided_diffusion` package (same package name): `gen_golden hq` alone."""
+    assert "guided_diffusion" not in sys.modules, "run `python -m oracle.gen_golden hq` on its own"
+    HQ = os.path.join(REF, "hq_demo")
+    sys.path.insert(0, HQ)
+    import guided_diffusion.gaussian_diffusion as GD
+    from guided_diffusion.script_util import create_model_and_diffusion, model_and_diffusion_defaults, select_args
+    import conf_mgt
+    from oracle import hq as HQO
+    assert os.path.abspath(GD.__file__).startswith(HQ)
+    # the loop writes progress PNGs under results/ (:49-52, :341-343) and hands its result to save_image(finalresult[0], .../final)
+    # (:750-752); p_sample_loop's own return value is unusable (it iterates over the returned dict's keys), so capture that call
+    saved = {}
+    GD.save_image = lambda img, save_dir, idx: saved.__setitem__(os.path.basename(save_dir), img.detach().clone())
+    GD.os.makedirs = lambda *a, **k: None
+    out = {}
+    jump = dict(t_T=6, n_sample=1, jump_length=2, jump_n_sample=2)
+    conf = conf_mgt.conf_base.Default_Conf()
+    conf.update(dict(attention_resolutions="32,16,8", class_cond=True, diffusion_steps=1000, learn_sigma=True, noise_schedule="linear",
+                     num_channels=64, num_head_channels=64, num_heads=4, num_res_blocks=1, resblock_updown=True, use_fp16=False,
+                     use_scale_shift_norm=True, timestep_respacing="6", use_kl=False, predict_xstart=False, rescale_timesteps=False,
+                     rescale_learned_sigmas=False, num_heads_upsample=-1, channel_mult="", dropout=0.0, use_checkpoint=False,
+                     use_new_attention_order=False, image_size=256, name="inet256", schedule_jump_params=jump))
+    torch.manual_seed(1234)
+    model, diffusion = create_model_and_diffusion(**select_args(conf, model_and_diffusion_defaults().keys()), conf=conf)
+    model.eval()
+    cfg = UO.OpenAIUNetConfig(image_size=256, model_channels=64, num_res_blocks=1, channel_mult=(1, 1, 2, 2, 4, 4),
+                              attention_resolutions=(32, 16, 8), num_head_channels=64, out_channels=6, num_classes=1000)
+    sd = UO.init_state_dict(cfg, 1234)
+    rsd = model.state_dict()
+    assert set(sd) == set(rsd), sorted(set(sd) ^ set(rsd))[:8]
+    for k in sd:
+        if not torch.equal(sd[k], rsd[k]):
+            assert rsd[k].abs().sum() == 0, f"{k}: differs from the reference but is not a zero-initialised tensor"
+    model.load_state_dict(sd)
+    K = HQO.SpacedConstants(1000, 6)
+    assert K.timestep_map == diffusion.timestep_map
+    for name in ("betas", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_mean_coef1",
+                 "posterior_mean_coef2"):
+        assert np.array_equal(getattr(K, name), getattr(diffusion, name)), name
+    from guided_diffusion.scheduler import get_schedule_jump as ref_jump
+    for jp in (jump, dict(t_T=100, n_sample=1, jump_length=10, jump_n_sample=3), dict(t_T=20, n_sample=1, jump_length=5, jump_n_sample=2)):
+        assert ref_jump(**jp) == HQO.get_schedule_jump(**jp)
+    classes = torch.tensor([950])
+
+    def model_fn(x, t, y=None, gt=None, **kwargs):            # main.py:84-86
+        return model(x, t, y, gt=gt)
+    for key, (h, w), sy in (("w384", (64, 96), 0.0), ("w320_noisy", (64, 80), 0.1), ("h320", (80, 64), 0.0)):
+        g = torch.Generator().manual_seed(700 + w + h)
+        y_img = torch.rand(1, 3, h, w, generator=g) * 2 - 1     # the low-resolution input image ("gt" in main.py:103-110)
+        ndraw = HQO.count_draws(4 * h, 4 * w, jump)
+        tape = [torch.randn(1, 3, 256, 256, generator=g) for _ in range(ndraw)]
+        kw = dict(gt=y_img.clone(), scale=4, deg="sr_averagepooling", resize_y=True, sigma_y=sy, save_path="unused", y=classes)
+        rt = list(tape[1:])
+        saved.clear()
+        with torch.no_grad(), cpu_shim(rt) as shim:
+            diffusion.p_sample_loop(model_fn, (1, 3, 256, 256), noise=tape[0], clip_denoised=True, model_kwargs=kw, cond_fn=None,
+                                    device="cpu", progress=False, return_all=True, conf=conf)
+        assert len(shim.tape) == 0, f"reference consumed a different number of draws ({len(shim.tape)} left)"
+        ref = saved["final"][None]
+        with torch.no_grad():
+            o = HQO.restore(lambda a, b, c: UO.forward(sd, a, b.float(), cfg, y=c), y_img, classes, tape, deg="sr_averagepooling",
+                            scale=4, sigma_y=sy, resize_y=True, respacing=6, jump=jump)
+        d = close(o, ref, 2e-3, f"hq {key}")
+        out[key + "_y"], out[key + "_out_s2"] = y_img.numpy(), ref[:, :, ::2, ::2].contiguous().numpy()
+        out[key + "_sums"] = np.array([ref.double().sum().item(), ref.double().abs().sum().item()])
+        out[key + "_seed"] = np.array([700 + w + h])
+        print(f"hq {key}: canvas {tuple(ref.shape)}, {ndraw} draws, ok (oracle-ref {d:.2e})")
+    np.savez_compressed(os.path.join(GOLD, "hq.npz"), **out)
+
+
 def general_fixtures():
     """GeneralA (svd_operators.py:173-208): a dense 48 x 192 degradation with two singular values pushed under the
     1e-3 threshold so the zeroing branch (:185) is exercised."""
@@ -678,6 +753,8 @@ def general_fixtures():
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["unet", "openai", "ops", "sampler", "simplified", "general", "runner", "guided", "fullsize", "sr16"]
+    if "hq" in which:
+        hq_fixtures()
     if "general" in which:
         general_fixtures()
     if "guided" in which:

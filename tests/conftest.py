@@ -41,4 +41,4 @@ def built_library():
 @pytest.fixture(scope="session")
 def gold():
     import numpy as np
-    return {name: np.load(os.path.join(GOLD, name + ".npz")) for name in ("unet_simple", "unet_openai", "operators", "sampler_tiny", "simplified", "general_a", "runner_io", "guided_tiny", "fullsize", "sr16", "simplified_r2")}
+    return {name: np.load(os.path.join(GOLD, name + ".npz")) for name in ("unet_simple", "unet_openai", "operators", "sampler_tiny", "simplified", "general_a", "runner_io", "guided_tiny", "fullsize", "sr16", "simplified_r2", "hq")}

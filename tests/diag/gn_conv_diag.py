@@ -45,7 +45,7 @@ def run(N, H, W, Cin, Cout, side_c=0, res=False, norm=True, silu=True, iters=0, 
     return err, ref.abs().max().item(), ms.value
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     L = _lib.lib()
     for mode in (0, 1):
         L.ddnm_tc_debug_gn_desc_mode(mode)
@@ -56,3 +56,20 @@ if __name__ == "__main__":
             except Exception as e:
                 print(f"desc_mode {mode} shape {shape}: FAILED {str(e)[:200]}", flush=True)
                 sys.exit(1)
+
+
+def timing():
+    """fused kernel vs (gn_apply + conv_tc) on the celeba / imagenet wide-layer shapes, random data"""
+    L = _lib.lib()
+    for (N, H, W, Cin, Cout, side) in [(16, 256, 256, 256, 128, 0), (16, 256, 256, 128, 128, 256), (16, 256, 256, 128, 128, 0),
+                                       (16, 128, 128, 256, 128, 0), (8, 256, 256, 256, 256, 0), (8, 128, 128, 512, 256, 0)]:
+        err, sc, ms = run(N, H, W, Cin, Cout, side_c=side, iters=5)
+        ms_c, fl = C.c_float(0), C.c_double(0)
+        _lib.check(L.ddnm_conv_tc_bench(N, H, W, Cin, Cout, 0, -5, C.byref(ms_c), C.byref(fl)))
+        flops = 2.0 * N * H * W * Cout * (9 * Cin + side)
+        print(f"timing N{N} {H}x{W} {Cin}->{Cout} side {side}: fused {ms:.3f} ms = {flops / ms / 1e9:.0f} TF/s (err {err:.1e}); "
+              f"unfused conv alone (no side) {ms_c.value:.3f} ms = {fl.value / ms_c.value / 1e9:.0f} TF/s", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "timing":
+    timing()
