@@ -414,6 +414,29 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
         if (q.base != nullptr && r < q.nrows && px >= 0 && px < p.W) buf[i] = ldg_nc_f4(q.base + (long long)px * q.ld);
       }
     };
+    // L2 prefetch of a unit a few units ahead of its register loads: the register double buffer covers one unit of work (~1 us),
+    // not a loaded HBM round trip; with the lines already in L2 it does.  Thread tt <-> one 128-byte line: row tt >> 1, half tt & 1.
+    int f_x0 = 0, f_y = 0, f_n = 0;
+    auto prefetch_unit = [&](int u, int j) {
+      if (j == 0) {
+        int n_idx;
+        decode(tile_of(u), n_idx, f_x0, f_y, f_n);
+      }
+      const bool side = j >= 3 * cb0;
+      const int c = side ? j - 3 * cb0 : j / 3;
+      const int yy = side ? f_y : f_y + (j - 3 * c) - 1;
+      if (yy < 0 || yy >= p.H) return;
+      const int ld = side ? g.xs_ld : g.x_ld;
+      const float* rowp = (side ? g.xs : g.x) + ((long long)f_n * p.H + yy) * p.W * ld + c * GK + (tt & 1) * 32;
+      const int px0 = side ? f_x0 : f_x0 - 1;
+      const int nrows = side ? 128 : 130;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int r = (tt >> 1) + 128 * k;
+        const int px = px0 + r;
+        if (r < nrows && px >= 0 && px < p.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + (long long)px * ld));
+      }
+    };
     int cur_n = -1;
     uint32_t ua = 0, a_phase = 0;
     const float kNegLog2e = -1.4426950408889634f;
@@ -497,7 +520,17 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
     };
     float4 buf0[NIT], buf1[NIT];
     int u = unit_begin, j = 0;
+    constexpr int PF_DIST = 4;               // units between the L2 prefetch and the register loads
+    int fu = unit_begin, fj = 0;
+    auto prefetch_next = [&]() {
+      if (fu < unit_end) {
+        prefetch_unit(fu, fj);
+        if (++fj == upt) { fj = 0; fu += unit_step; }
+      }
+    };
     if (u < unit_end) {
+#pragma unroll 1
+      for (int k = 0; k < PF_DIST + 1; ++k) prefetch_next();
       Unit cur = unit_of(u, j);
       load_unit(cur, buf0);
       while (true) {
@@ -509,6 +542,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
           nxt = unit_of(u, j);
           load_unit(nxt, buf1);
         }
+        prefetch_next();
         store_unit(cur, buf0);
         if (!more0) break;
         cur = nxt;
@@ -519,6 +553,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
           nxt = unit_of(u, j);
           load_unit(nxt, buf0);
         }
+        prefetch_next();
         store_unit(cur, buf1);
         if (!more1) break;
         cur = nxt;
