@@ -74,6 +74,24 @@ class _EngineModel:
         self._engines[batch] = h
         return h
 
+    def engine_for(self, batch):
+        """(handle, engine batch) able to run `batch` rows: the engine built for exactly that batch if it exists, else the smallest
+        existing engine with a LARGER batch (a dataset's ragged last batch is padded to it instead of building a second engine with
+        its own copy of every weight and its own multi-GiB workspace), else a new engine of that size."""
+        if batch in self._engines:
+            return self._engines[batch], batch
+        bigger = sorted(b for b in self._engines if b > batch)
+        if bigger:
+            return self._engines[bigger[0]], bigger[0]
+        return self.engine(batch), batch
+
+    @staticmethod
+    def pad_rows(t, rows):
+        """t with its leading dimension padded to `rows` by repeating the last row (rows of a batch are independent trajectories)."""
+        if t is None or t.shape[0] == rows:
+            return t
+        return torch.cat([t, t[-1:].expand(rows - t.shape[0], *t.shape[1:])], dim=0).contiguous()
+
     def __call__(self, x, t, y=None):
         return self.forward(x, t, y)
 
@@ -84,17 +102,19 @@ class _EngineModel:
         assert (y is not None) == (self.num_classes is not None), "must specify y if and only if the model is class-conditional"
         assert x.is_cuda and x.dtype == torch.float32, "ddnm_b200 denoisers run on CUDA fp32 tensors"
         assert x.shape[2] == x.shape[3] == self.resolution     # models.py:302
-        x = x.contiguous()
-        t = t.to(device=x.device, dtype=torch.float32).contiguous()
-        out = torch.empty(x.shape[0], self.out_ch, self.resolution, self.resolution, device=x.device, dtype=torch.float32)
-        h = self.engine(x.shape[0])
+        n = x.shape[0]
+        t = t.to(device=x.device, dtype=torch.float32)
+        if y is not None:
+            assert y.shape == (n,)                              # unet.py:652
+        h, eb = self.engine_for(n)
+        x, t = self.pad_rows(x.contiguous(), eb), self.pad_rows(t.contiguous(), eb)
+        out = torch.empty(eb, self.out_ch, self.resolution, self.resolution, device=x.device, dtype=torch.float32)
         if y is None:
             _lib.check(_lib.lib().ddnm_unet_forward(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(out), _lib.cur_stream()))
         else:
-            assert y.shape == (x.shape[0],)                     # unet.py:652
-            labels = y.to(device=x.device, dtype=torch.int32).contiguous()
+            labels = self.pad_rows(y.to(device=x.device, dtype=torch.int32).contiguous(), eb)
             _lib.check(_lib.lib().ddnm_unet_forward_cond(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(labels), _lib.ptr(out), _lib.cur_stream()))
-        return out
+        return out[:n] if eb != n else out
 
     # --- extras ---
     def read_tap(self, batch, name, shape):

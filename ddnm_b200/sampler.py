@@ -24,14 +24,20 @@ class_num = 951
 NOISE_CHUNK_BYTES = 256 << 20
 
 
-def _chunked(n_pairs, x, run_range):
+def _chunked(n_pairs, x, run_range, rows=None):
     """Drive ``run_range(k0, k1, noise_chunk)`` over the schedule with the Gaussian draws produced chunk by chunk on a side stream
-    (double-buffered), in the reference's generator order: pair k gets the k-th ``randn_like(x)`` after the caller's last draw."""
-    per_pair = x.numel() * 4
+    (double-buffered), in the reference's generator order: pair k gets the k-th ``randn_like(x)`` after the caller's last draw.
+    ``rows`` > x.shape[0]: the chunk buffers carry that many rows (a batch padded to a larger engine); only the real rows are drawn,
+    with exactly the generator consumption of ``randn_like(x)``, the padding rows stay zero."""
+    n = x.shape[0]
+    rows = n if rows is None else rows
+    shape = (rows,) + tuple(x.shape[1:])
+    per_pair = rows * x[0].numel() * 4
     K = max(1, min(n_pairs, NOISE_CHUNK_BYTES // per_pair))
     main = torch.cuda.current_stream()
     side = torch.cuda.Stream()
-    bufs = [torch.empty((K,) + tuple(x.shape), device=x.device, dtype=torch.float32) for _ in range(2 if n_pairs > K else 1)]
+    mk = torch.zeros if rows != n else torch.empty
+    bufs = [mk((K,) + shape, device=x.device, dtype=torch.float32) for _ in range(2 if n_pairs > K else 1)]
     consumed = [None, None]
     side.wait_stream(main)                                  # the buffers' allocation / earlier use of their memory
     chunks = [(k0, min(n_pairs, k0 + K)) for k0 in range(0, n_pairs, K)]
@@ -43,7 +49,10 @@ def _chunked(n_pairs, x, run_range):
             if consumed[c % 2] is not None:
                 side.wait_event(consumed[c % 2])
             for k in range(k1 - k0):
-                b[k].normal_()                              # == torch.randn_like(x): same generator consumption, no extra copy
+                if rows == n:
+                    b[k].normal_()                          # == torch.randn_like(x): same generator consumption, no extra copy
+                else:
+                    b[k, :n] = torch.randn_like(x)
             ev = torch.cuda.Event()
             ev.record(side)
         return ev
@@ -93,9 +102,13 @@ def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, n
         s.n_pairs, s.t_i, s.t_j, s.abar = len(pairs), ti.ctypes.data, tj.ctypes.data, abar.ctypes.data
         s.num_timesteps, s.eta, s.sigma_y = int(config.diffusion.num_diffusion_timesteps), float(eta), float(sigma_y)
         s.plus = 1 if plus else 0
-        out = x.clone()                                     # the iterate, updated in place range by range
-        x0p = torch.empty_like(x)
-        eng = model.engine(n)
+        # a ragged last batch rides on an existing bigger engine, padded (classifier guidance keeps the exact size: cls_fn sees n rows)
+        eng, eb = (model.engine(n), n) if cls_fn is not None else model.engine_for(n)
+        out = model.pad_rows(x, eb).clone()                 # the iterate, updated in place range by range
+        x0p = torch.empty_like(out)
+        yv = model.pad_rows(yv, eb)
+        if noise is not None and eb != n:
+            noise = torch.cat([noise, noise[:, -1:].expand(noise.shape[0], eb - n, *noise.shape[2:])], dim=1).contiguous()
         have_x0 = C.c_int(0)
         if cls_fn is None:
             labels = grad = fn = None
@@ -105,7 +118,7 @@ def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, n
 
         def run_range(k0, k1, chunk):
             rc = _lib.lib().ddnm_sample_range(eng, A_funcs._h, C.byref(s), k0, k1, _lib.ptr(out), _lib.ptr(x0p), C.byref(have_x0),
-                                             _lib.ptr(yv), _lib.ptr(chunk), n, _lib.ptr(labels), _lib.ptr(grad),
+                                             _lib.ptr(yv), _lib.ptr(chunk), eb, _lib.ptr(labels), _lib.ptr(grad),
                                              None if fn is None else C.cast(fn, C.c_void_p), None, _lib.cur_stream())
             if failure:
                 raise failure[0]
@@ -113,7 +126,9 @@ def _run(x, model, b, eta, A_funcs, y, sigma_y, plus, cls_fn, classes, config, n
         if noise is not None:
             run_range(0, len(pairs), noise)
         else:
-            _chunked(len(pairs), x, run_range)
+            _chunked(len(pairs), x, run_range, rows=eb)
+        if eb != n:
+            out, x0p = out[:n], x0p[:n]
         if not to_host:
             return out, x0p
         return [out.to("cpu")], [x0p.to("cpu")]

@@ -291,6 +291,37 @@ def test_unet_batch_rows_independent():
         assert_close(m(x[i:i + 1], t[i:i + 1]), full[i:i + 1], 1e-5, 1e-5, f"row {i}")
 
 
+def test_ragged_last_batch_reuses_the_bigger_engine(gold):
+    """A dataset's last, smaller batch is padded to the engine that already exists (no second engine with its own weight copy and
+    workspace); rows are independent, so the real rows' results are those of an engine built for exactly that batch."""
+    from ddnm_b200.sampler import ddnm_diffusion
+    cfg = U.SimpleUNetConfig.tiny()
+    torch.manual_seed(9)
+    x = torch.randn(4, 3, 32, 32, device=dev)
+    t = torch.tensor([10.0, 500.0, 999.0, 0.0], device=dev)
+    big = _engine_model(cfg)
+    full = big(x, t)
+    part = big(x[:3], t[:3])
+    assert list(big._engines) == [4], "the 3-row call must ride on the 4-row engine"
+    exact = _engine_model(cfg)
+    ref = exact(x[:3], t[:3])
+    assert torch.equal(part, ref) and torch.equal(part, full[:3])
+    oop = oracle_ops(gold["operators"], 32)["sr4"]
+    eop = engine_op("sr4", oop, 32)
+    y = eop.A(x)
+    conf = sampler_config(5, 1, 1)
+    betas = SCH.linear_betas().to(dev)
+    tape = torch.randn(5, 3, 3, 32, 32, device=dev)
+    a = ddnm_diffusion(x[:3], big, betas, 0.85, eop, y[:3], config=conf, noise=tape)
+    b = ddnm_diffusion(x[:3], exact, betas, 0.85, eop, y[:3], config=conf, noise=tape)
+    assert list(big._engines) == [4] and torch.equal(a[0][0], b[0][0]) and torch.equal(a[1][0], b[1][0])
+    torch.manual_seed(3)
+    c = ddnm_diffusion(x[:3], big, betas, 0.85, eop, y[:3], config=conf)          # draws inside: same generator consumption
+    torch.manual_seed(3)
+    d = ddnm_diffusion(x[:3], exact, betas, 0.85, eop, y[:3], config=conf)
+    assert torch.equal(c[0][0], d[0][0])
+
+
 def _engine_openai(cfg, graph=True):
     from ddnm_b200.model import create_model
     m = create_model(**openai_model_kwargs(cfg))
