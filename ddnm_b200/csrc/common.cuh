@@ -67,6 +67,39 @@ struct StatAcc {
   long long hi;
 };
 
+// Programmatic dependent launch (PDL): consecutive kernels of the forward carry cudaLaunchAttributeProgrammaticStreamSerialization,
+// so a kernel's CTAs may be scheduled (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) while the
+// previous kernel's last CTAs drain; pdl_prologue() at the top of every such kernel (1) releases ITS successor and (2) blocks
+// until the predecessor grid has completed and flushed, before any dependent global access.  Captured into the CUDA graph these
+// become programmatic edges.  DDNM_PDL=0 launches everything fully serialised (A/B measurements).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = cluster;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  if (e != cudaSuccess) throw Error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in cudaLaunchKernelEx");
+}
+
 // A strided NHWC fp32 activation view: element (n, y, x, c) at p[((n*H + y)*W + x)*ld + c].
 // ld >= C lets a tensor live inside a channel slice of a wider (concat) buffer.
 // st (optional): per-(image, channel) running sums for GroupNorm, st[(n*st_ld + c)*2 + {0,1}] = {sum, sum of squares}
@@ -95,6 +128,11 @@ struct SplitView {
 };
 
 #ifdef __CUDACC__
+// see launch_pdl: release the successor grid, then wait for the predecessor grid (no-ops without a programmatic dependency)
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA, tcgen05.  Addresses are 32-bit shared-window addresses.
 // ---------------------------------------------------------------------------------------------

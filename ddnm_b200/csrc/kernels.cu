@@ -1,10 +1,20 @@
 // SIMT kernels (see kernels.cuh).  Reference semantics cited per kernel.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "tc_gemm.cuh"
 
 namespace ddnm {
 
 static constexpr int MAX_C = 2048;  // widest concat in either UNet
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = std::getenv("DDNM_PDL");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
 
 __device__ __forceinline__ float swishf(float x) { return x / (1.0f + expf(-x)); }
 
@@ -16,6 +26,7 @@ __device__ __forceinline__ float swishf(float x) { return x / (1.0f + expf(-x));
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const float* __restrict__ x, int HW, int C, int ld, int pix_per_cta,
                                 StatAcc* __restrict__ stats, int st_ld) {
+  pdl_prologue();
   const int n = blockIdx.y;
   const int C4 = C >> 2;
   const int rows = blockDim.x / C4;
@@ -67,7 +78,7 @@ void gn_stats(const View& x, cudaStream_t st) {
   long long want = cdivll((long long)HW * x.N, 592);
   int ppc = (int)std::max<long long>(rows * 4, cdivll(want, rows) * rows);
   dim3 grid(cdiv(HW, ppc), x.N);
-  gn_stats_kernel<<<grid, threads, 0, st>>>(x.p, HW, x.C, x.ld, ppc, x.st, x.st_ld);
+  launch_pdl(gn_stats_kernel, grid, dim3(threads), 0, st, 1, (const float*)x.p, HW, x.C, x.ld, ppc, x.st, x.st_ld);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -85,6 +96,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
                                 __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ out32,
                                 const float* __restrict__ ss, int ss_ld, __half* __restrict__ raw_hi,
                                 __half* __restrict__ raw_lo) {
+  pdl_prologue();
   // dynamic smem: [2*C] doubles (the image's per-channel sums, staged with ONE independent load per channel) then sc[C], sh[C].
   // (Summing a group's sums straight from global memory made every thread walk a chain of 2*cpg dependent-issue loads,
   // ~10-16 us of latency in front of every CTA's first pixel.)
@@ -243,11 +255,11 @@ static void gn_apply_launch(const View& x, int groups, bool normalise, const flo
   dim3 grid(cdiv(HW, ppc), x.N);
   const size_t smem = (size_t)x.C * 24;   // 2 doubles + 2 floats per channel (<= 48 KiB at MAX_C)
   if (out32)
-    gn_apply_kernel<true><<<grid, threads, smem, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, x.st_ld, gamma, beta, eps, silu, mode,
-                                                 ppc, nullptr, nullptr, out32, ss, ss_ld, nullptr, nullptr);
+    launch_pdl(gn_apply_kernel<true>, grid, dim3(threads), smem, st, 1, (const float*)x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, x.st_ld, gamma,
+               beta, eps, (int)silu, mode, ppc, (__half*)nullptr, (__half*)nullptr, out32, ss, ss_ld, (__half*)nullptr, (__half*)nullptr);
   else
-    gn_apply_kernel<false><<<grid, threads, smem, st>>>(x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, x.st_ld, gamma, beta, eps, silu, mode,
-                                                  ppc, hi, lo, nullptr, ss, ss_ld, raw_hi, raw_lo);
+    launch_pdl(gn_apply_kernel<false>, grid, dim3(threads), smem, st, 1, (const float*)x.p, x.H, x.W, x.C, x.ld, x.N, groups, stats, x.st_ld, gamma,
+               beta, eps, (int)silu, mode, ppc, hi, lo, (float*)nullptr, ss, ss_ld, raw_hi, raw_lo);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -270,6 +282,7 @@ template <int CIN>
 __global__ void __launch_bounds__(256) conv_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ out,
                                                              int H, int W, int Cout, int ld) {
+  pdl_prologue();
   constexpr int KT = CIN * 9;
   constexpr int TW = 64, TH = 8;  // output tile per CTA: one warp per row
   __shared__ float tile[CIN][TH + 2][TW + 2];
@@ -321,7 +334,7 @@ void conv3x3_small_cin(const float* x, int Cin, const float* w, const float* bia
   DDNM_CHECK(Cin == 3, "stem convolution expects 3 input channels");
   DDNM_CHECK(out.C % 4 == 0, "stem Cout % 4");
   dim3 grid(cdiv(out.W, 64), cdiv(out.H, 8), out.N * cdiv(out.C, 128));
-  conv_small_cin_kernel<3><<<grid, 256, 0, st>>>(x, w, bias, out.p, out.H, out.W, out.C, out.ld);
+  launch_pdl(conv_small_cin_kernel<3>, grid, dim3(256), 0, st, 1, x, w, bias, out.p, out.H, out.W, out.C, out.ld);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -446,6 +459,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float a
                                                     long long sa, long long sa2, const float* __restrict__ B, int ldb,
                                                     long long sb, long long sb2, float* __restrict__ C, int ldc, long long sc,
                                                     long long sc2, int inner_n) {
+  pdl_prologue();
   __shared__ float As[16][64 + 4], Bs[16][64 + 4];
   const int bo = blockIdx.z / inner_n, bi = blockIdx.z % inner_n;
   A += bo * sa + bi * sa2; B += bo * sb + bi * sb2; C += bo * sc + bi * sc2;
@@ -497,14 +511,15 @@ void sgemm_batched(bool bt, int outer_n, int inner_n, int M, int N, int K, float
   dim3 grid(cdiv(N, 64), cdiv(M, 64), outer_n * inner_n);
   DDNM_CHECK(grid.z <= 65535, "too many GEMM batches for one launch");
   if (bt)
-    sgemm_kernel<true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sa, sa2, B, ldb, sb, sb2, C, ldc, sc, sc2, inner_n);
+    launch_pdl(sgemm_kernel<true>, grid, dim3(256), 0, st, 1, M, N, K, alpha, A, lda, sa, sa2, B, ldb, sb, sb2, C, ldc, sc, sc2, inner_n);
   else
-    sgemm_kernel<false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, sa, sa2, B, ldb, sb, sb2, C, ldc, sc, sc2, inner_n);
+    launch_pdl(sgemm_kernel<false>, grid, dim3(256), 0, st, 1, M, N, K, alpha, A, lda, sa, sa2, B, ldb, sb, sb2, C, ldc, sc, sc2, inner_n);
   CUDA_CHECK(cudaGetLastError());
 }
 
 // softmax over the last dim, one warp per row (F.softmax(w_, dim=2), models.py:179)
 __global__ void softmax_kernel(float* __restrict__ x, long long rows, int cols) {
+  pdl_prologue();
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -527,6 +542,7 @@ __global__ void softmax_kernel(float* __restrict__ x, long long rows, int cols) 
 // softmax over the last dim with the probabilities emitted as fp16 (hi, lo) planes — the A operand of the P.V GEMM
 __global__ void softmax_split_kernel(const float* __restrict__ x, long long rows, int cols, __half* __restrict__ hi,
                                      __half* __restrict__ lo) {
+  pdl_prologue();
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -550,13 +566,14 @@ __global__ void softmax_split_kernel(const float* __restrict__ x, long long rows
 }
 void softmax_split(const float* x, long long rows, int cols, __half* hi, __half* lo, cudaStream_t st) {
   DDNM_CHECK(cols % 2 == 0, "softmax_split: even row length");
-  softmax_split_kernel<<<(int)cdivll(rows * 32, 256), 256, 0, st>>>(x, rows, cols, hi, lo);
+  launch_pdl(softmax_split_kernel, dim3((unsigned)cdivll(rows * 32, 256)), dim3(256), 0, st, 1, x, rows, cols, hi, lo);
   CUDA_CHECK(cudaGetLastError());
 }
 
 // V^T planes for the P.V GEMM: src[(img*T + t)*ld + head*head_stride + off + c] -> dst[((img*heads + head)*ch + c)*T + t]
 __global__ void transpose_split_kernel(const float* __restrict__ src, int ld, int head_stride, int off, int T, int heads, int ch,
                                        __half* __restrict__ hi, __half* __restrict__ lo) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int img = blockIdx.z / heads, head = blockIdx.z % heads;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -580,12 +597,12 @@ __global__ void transpose_split_kernel(const float* __restrict__ src, int ld, in
 void transpose_split(const float* src, int ld, int head_stride, int off, int images, int T, int heads, int ch, __half* hi,
                      __half* lo, cudaStream_t st) {
   dim3 grid(cdiv(T, 32), cdiv(ch, 32), images * heads);
-  transpose_split_kernel<<<grid, 256, 0, st>>>(src, ld, head_stride, off, T, heads, ch, hi, lo);
+  launch_pdl(transpose_split_kernel, grid, dim3(256), 0, st, 1, src, ld, head_stride, off, T, heads, ch, hi, lo);
   CUDA_CHECK(cudaGetLastError());
 }
 
 void softmax_rows(float* x, long long rows, int cols, cudaStream_t st) {
-  softmax_kernel<<<(int)cdivll(rows * 32, 256), 256, 0, st>>>(x, rows, cols);
+  launch_pdl(softmax_kernel, dim3((unsigned)cdivll(rows * 32, 256)), dim3(256), 0, st, 1, x, rows, cols);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -693,6 +710,7 @@ void nchw_to_nhwc(const float* src, int N, int C, int H, int W, const View& dst,
   CUDA_CHECK(cudaGetLastError());
 }
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ s, int N, int C, int H, int W, int ld, float* __restrict__ d) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)N * C * H * W;
   if (i >= total) return;
@@ -703,7 +721,7 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ s, int N, int C, i
 }
 void nhwc_to_nchw(const View& src, float* dst, cudaStream_t st) {
   const long long total = src.pixels() * src.C;
-  nhwc_to_nchw_kernel<<<(int)cdivll(total, 256), 256, 0, st>>>(src.p, src.N, src.C, src.H, src.W, src.ld, dst);
+  launch_pdl(nhwc_to_nchw_kernel, dim3((unsigned)cdivll(total, 256)), dim3(256), 0, st, 1, (const float*)src.p, src.N, src.C, src.H, src.W, src.ld, dst);
   CUDA_CHECK(cudaGetLastError());
 }
 

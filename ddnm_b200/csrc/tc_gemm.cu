@@ -74,6 +74,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
+  pdl_prologue();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int KB = p.kb0 + p.kb1;
@@ -686,23 +687,8 @@ static void launch_bn(const TcLaunch& L, cudaStream_t stream) {
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set))
     CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, PAIR, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  if (PAIR) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(L.grid);
-    cfg.blockDim = dim3(320);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, PAIR, DUAL>, L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.b2, L.p));
-  } else {
-    conv_tc_kernel<BN, PAIR, DUAL><<<L.grid, 320, Cfg::SMEM_BYTES, stream>>>(L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.b2, L.p);
-  }
+  launch_pdl(conv_tc_kernel<BN, PAIR, DUAL>, dim3(L.grid), dim3(320), (size_t)Cfg::SMEM_BYTES, stream, PAIR ? 2 : 1, L.a0h, L.a0l, L.a1h, L.a1l,
+             L.bh, L.bl, L.b2, L.p);
   CUDA_CHECK(cudaGetLastError());
 }
 

@@ -114,7 +114,7 @@ TcGnLaunch tc_make_gn_launch(const View& x, const GnAffine& gn, const View* side
                              const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr, int num_sms);
 void tc_gn_run(const TcGnLaunch& L, cudaStream_t stream);
 void tc_debug_gn_desc_mode(int mode);   // tests: how the shifted A start address is described to the tensor core
-void tc_debug_gn_fused(int on);         // 1 (default): eligible layers use the fused kernel; 0: always gn_apply + conv_tc
+void tc_debug_gn_fused(int on);         // 1: eligible layers use the fused kernel; 0 (default): gn_apply + conv_tc
 
 // debug knobs (tests only): override descriptor words for the NEXT launches built
 void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor);

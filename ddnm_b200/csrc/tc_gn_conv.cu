@@ -126,6 +126,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
   float2* coef = reinterpret_cast<float2*>(gen_base + Cfg::RING_BYTES + 256);
 
+  pdl_prologue();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cb0 = p.cb0;                       // 64-channel slices of the normalised 3x3 input
@@ -490,9 +491,13 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
       for (int i = 0; i < NIT; ++i) {
         const int r = i * 16 + row0;
         if (r < q.nrows) {
-          // padding pixels / rows were loaded as zeros; their ACTIVATED value must be zero as well (conv zero padding)
+          // padding pixels / rows: the ACTIVATED value is zero (conv zero padding), whatever silu(b) would be
           const int px = q.px0 + r;
-          const bool ok = q.base != nullptr && px >= 0 && px < p.W;
+          if (q.base == nullptr || px < 0 || px >= p.W) {
+            st_shared_v2(hi_base + (uint32_t)i * 2048u, 0u, 0u);
+            st_shared_v2(lo_base + (uint32_t)i * 2048u, 0u, 0u);
+            continue;
+          }
           float t[4] = {buf[i].x, buf[i].y, buf[i].z, buf[i].w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -505,7 +510,6 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
           uint32_t h01, h23, l01, l23;
           split2_f16(t[0], t[1], h01, l01);
           split2_f16(t[2], t[3], h23, l23);
-          if (!ok) h01 = h23 = l01 = l23 = 0u;
           st_shared_v2(hi_base + (uint32_t)i * 2048u, h01, h23);       // row r = row0 + 16 i: same swizzle phase for every i
           st_shared_v2(lo_base + (uint32_t)i * 2048u, l01, l23);
         }
@@ -579,12 +583,13 @@ static int env_int(const char* name, int dflt) {
 }
 static int g_gn_desc_mode = env_int("DDNM_GN_DESC_MODE", 0);
 void tc_debug_gn_desc_mode(int mode) { g_gn_desc_mode = mode; }
-static int g_gn_enable = env_int("DDNM_GN_FUSED", 1);
+// Default OFF until the kernel beats gn_apply + conv_tc on the B200 (profiles/r02_gn_fused_*.md): round-2 measurements put it at
+// parity on the Cout = 256 layers and behind on the Cout = 128 ones (the transform warps, not the tensor pipe, pace it).
+static int g_gn_enable = env_int("DDNM_GN_FUSED", 0);
 void tc_debug_gn_fused(int on) { g_gn_enable = on; }
 bool tc_gn_enabled() { return g_gn_enable != 0; }
 
-bool tc_gn_eligible(const View& x, const View* side, int Cout, const View& out) {
-  if (!g_gn_enable) return false;
+static bool gn_shape_ok(const View& x, const View* side, int Cout, const View& out) {
   if (out.W % 128 != 0 || x.C % GK != 0 || x.C > G_MAXC || Cout % 128 != 0) return false;
   if (x.H != out.H || x.W != out.W || x.N != out.N) return false;
   if (((long long)out.N * out.H * (out.W / 128)) % 2 != 0) return false;
@@ -593,11 +598,13 @@ bool tc_gn_eligible(const View& x, const View* side, int Cout, const View& out) 
   return true;
 }
 
+bool tc_gn_eligible(const View& x, const View* side, int Cout, const View& out) { return g_gn_enable != 0 && gn_shape_ok(x, side, Cout, out); }
+
 CUtensorMap tc_make_weight_map(const __half* w, int Ktot, int Cout, int box_rows);   // tc_gemm.cu
 
 TcGnLaunch tc_make_gn_launch(const View& x, const GnAffine& gn, const View* side, const __half* w_hi, const __half* w_lo, int Cout,
                              const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr, int num_sms) {
-  DDNM_CHECK(tc_gn_eligible(x, side, Cout, out), "fused GroupNorm convolution: unsupported shape");
+  DDNM_CHECK(gn_shape_ok(x, side, Cout, out), "fused GroupNorm convolution: unsupported shape");
   TcGnLaunch L;
   TcParams& p = L.g.t;
   p.H = out.H; p.W = out.W; p.N = out.N;
@@ -645,19 +652,7 @@ static void launch_gn(const TcGnLaunch& L, cudaStream_t stream) {
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set))
     CUDA_CHECK(cudaFuncSetAttribute(conv_gn_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(L.grid);
-  cfg.blockDim = dim3(G_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gn_tc_kernel<BN>, L.bh, L.bl, L.b2, L.g));
+  launch_pdl(conv_gn_tc_kernel<BN>, dim3(L.grid), dim3(G_THREADS), (size_t)Cfg::SMEM_BYTES, stream, 2, L.bh, L.bl, L.b2, L.g);
   CUDA_CHECK(cudaGetLastError());
 }
 

@@ -235,7 +235,8 @@ int ddnm_conv_gn_tc(const float* x, int N, int H, int W, int Cin, int groups, co
                     const float* residual, float* out, int iters, float* ms_per_iter, void* stream);
 /* tests: 0 = shifted start address only, 1 = shifted start address + descriptor base-offset field */
 int ddnm_tc_debug_gn_desc_mode(int mode);
-/* 1 (default): eligible layers run the fused GroupNorm convolution; 0: always gn_apply_kernel + conv_tc_kernel */
+/* 1: eligible layers (3x3, rows >= 128 pixels) of engines built afterwards run the fused GroupNorm convolution; 0 (default, also env
+ * DDNM_GN_FUSED): gn_apply_kernel + conv_tc_kernel */
 int ddnm_tc_debug_gn_fused(int on);
 int ddnm_tc_debug_override(unsigned desc_hi, unsigned idesc_xor);
 /* tuning experiments: force the N-tile width of conv launches built afterwards (0 = heuristic) */

@@ -191,6 +191,57 @@ def _pair_fusions(lib):
     assert_close(_conv_tc(lib, x, w, b, side=side, side_w=sw), _conv_ref(x, w, b, side=side, side_w=sw), 1e-4, 5e-5, "pair: 1x1 side input")
 
 
+@pytest.mark.parametrize("shape", [(2, 128, 128, 128, 128, 0, False), (1, 256, 256, 64, 128, 0, True), (2, 128, 128, 128, 256, 0, False),
+                                   (2, 128, 128, 64, 128, 192, False), (1, 256, 256, 128, 256, 64, False), (4, 128, 128, 64, 128, 0, True)], ids=str)
+def test_fused_groupnorm_conv_vs_fp64(lib, shape):
+    """conv_gn_tc_kernel: GroupNorm + SiLU + fp16 split applied INSIDE the tcgen05 convolution (transform warps write the swizzled
+    A operand, one 130-pixel halo row per (dy, 64-channel slice) feeding the three dx taps through shifted descriptors), with the
+    1x1 side input (nin_shortcut) and the residual epilogue — against an fp64 group_norm -> silu -> conv2d."""
+    N, H, W, Cin, Cout, side_c, res = shape
+    L = lib.lib()
+    torch.manual_seed(11)
+    x = torch.randn(N, Cin, H, W, device=dev) * 1.5 + 0.3
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    g, be = torch.randn(Cin, device=dev), torch.randn(Cin, device=dev)
+    side = torch.randn(N, side_c, H, W, device=dev) if side_c else None
+    sw = (torch.randn(Cout, side_c, 1, 1, device=dev) / side_c ** 0.5).contiguous() if side_c else None
+    r = torch.randn(N, Cout, H, W, device=dev) if res else None
+    nhwc = lambda t: None if t is None else t.permute(0, 2, 3, 1).contiguous()   # noqa: E731
+    out = torch.empty(N, H, W, Cout, device=dev)
+    xs, ss, rs = nhwc(x), nhwc(side), nhwc(r)
+    lib.check(L.ddnm_conv_gn_tc(lib.ptr(xs), N, H, W, Cin, 32, lib.ptr(g), lib.ptr(be), 1e-6, 1, lib.ptr(w), lib.ptr(b), Cout, lib.ptr(ss), side_c,
+                                lib.ptr(sw), lib.ptr(rs), lib.ptr(out), 0, None, None))
+    torch.cuda.synchronize()
+    h = F.group_norm(x.double().cpu(), 32, g.double().cpu(), be.double().cpu(), 1e-6)
+    ref = F.conv2d(h * torch.sigmoid(h), w.double().cpu(), b.double().cpu(), padding=1)
+    if side is not None:
+        ref = ref + F.conv2d(side.double().cpu(), sw.double().cpu())
+    if r is not None:
+        ref = ref + r.double().cpu()
+    assert_close(out.permute(0, 3, 1, 2), ref, 1e-4, 1e-4, f"fused GroupNorm conv {shape}")
+
+
+def test_fused_and_unfused_engines_agree():
+    """The celeba network with the wide layers on the fused kernel vs the same network forced onto gn_apply + conv_tc."""
+    from ddnm_b200 import _lib as LL
+    cfg = U.SimpleUNetConfig.celeba_hq()
+    torch.manual_seed(23)
+    x = torch.randn(2, 3, 256, 256, device=dev)
+    t = torch.tensor([650.0, 12.0], device=dev)
+    LL.check(LL.lib().ddnm_tc_debug_gn_fused(1))
+    try:
+        fused = _engine_model(cfg)
+        a = fused(x, t)
+        LL.check(LL.lib().ddnm_tc_debug_gn_fused(0))
+        plain = _engine_model(cfg)
+        b = plain(x, t)
+    finally:
+        LL.lib().ddnm_tc_debug_gn_fused(0)
+    assert fused.info(2)["launches"] < plain.info(2)["launches"], "the fused engine must have fewer launches"
+    assert_close(a, b, 1e-4, 2e-5, "fused vs unfused celeba forward")
+
+
 def test_groupnorm_silu(lib):
     torch.manual_seed(3)
     for (N, H, W, Cc) in [(2, 16, 16, 64), (1, 32, 32, 384), (2, 8, 8, 1024)]:

@@ -46,8 +46,12 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_th
         "l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed"]
 
 
-def full(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def full(src, dst, peak_gbs=None):
+    """src: a .ncu-rep, or the `--page raw --csv` export of one made on the GPU box (reports are too large to bring back)."""
+    if src.endswith(".csv"):
+        out = open(src).read()
+    else:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -58,6 +62,17 @@ def full(src, dst):
             for w in WANT:
                 if w in idx:
                     f.write(f"| {w} | {r[idx[w]]} | {units[idx[w]]} |\n")
+            try:   # achieved DRAM bandwidth of the launch against the measured copy peak (MEASURED_PEAKS.json)
+                def val(name):
+                    x, u = float(r[idx[name]].replace(",", "")), units[idx[name]]
+                    return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1}[u]
+                byts = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+                sec = val("gpu__time_duration.sum")
+                gbs = byts / sec / 1e9
+                pk = peak_gbs or __import__("json").load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
+                f.write(f"| **DRAM traffic / duration** | {gbs:.0f} | GB/s = {gbs / pk * 100:.0f} % of the measured {pk:.0f} GB/s copy peak |\n")
+            except Exception:
+                pass
             f.write("\n")
     print(open(dst).read())
 
