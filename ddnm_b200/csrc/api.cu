@@ -323,6 +323,11 @@ int ddnm_conv_gn_tc(const float* x, int N, int H, int W, int Cin, int groups, co
   CUDA_CHECK(cudaStreamSynchronize(s));
   DDNM_API_END
 }
+int ddnm_tc_debug_gn_counters(long long* dev_buf) {
+  DDNM_API_BEGIN
+  tc_debug_gn_counters(dev_buf);
+  DDNM_API_END
+}
 int ddnm_tc_debug_gn_desc_mode(int mode) {
   DDNM_API_BEGIN
   tc_debug_gn_desc_mode(mode);

@@ -217,20 +217,28 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
     // ------------------------------------------------ UMMA issuer -------------------------------------------------
     if (lane == 0 && leader) {
       uint32_t sb_i = 0, b_phase = 0, ua = 0, a_phase = 0, acc = 0, acc_phase = 0;
+      long long w_a = 0, w_b = 0, w_t = 0, t_all = g.dbg ? clock64() : 0;
+      const bool prof = g.dbg != nullptr;
       const uint32_t idesc_wide = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)(256 >> 3) << 17);   // N = 256
       for (int u = unit_begin; u < unit_end; u += unit_step) {
+        long long q0 = prof ? clock64() : 0;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        if (prof) w_t += clock64() - q0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
         bool first = true;
         for (int j = 0; j < upt; ++j) {
           const bool side = j >= 3 * cb0;
           const int ntap = side ? 1 : 3;
+          q0 = prof ? clock64() : 0;
           mbar_wait_cluster(a_full(ua), a_phase);
+          if (prof) w_a += clock64() - q0;
           tc_fence_after();
           const uint32_t au = a_ring + ua * G_AUNIT;
           for (int dxi = 0; dxi < ntap; ++dxi) {
+            q0 = prof ? clock64() : 0;
             mbar_wait(b_full(sb_i), b_phase);
+            if (prof) w_b += clock64() - q0;
             tc_fence_after();
             // A rows: main units hold pixels x0-1 .. x0+128 in rows 0..129, tap dx reads rows dx+1 .. dx+128; side units hold
             // pixels x0 .. x0+127 in rows 0..127.  One operand row = 128 bytes, so the shift is a start-address offset; the swizzle
@@ -274,6 +282,10 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
         umma_commit_pair(tfull_bar(acc));
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
+      }
+      if (prof) {
+        long long* d = g.dbg + (size_t)blockIdx.x * 16;
+        d[8] = clock64() - t_all; d[9] = w_a; d[10] = w_b; d[11] = w_t;
       }
     }
   } else if (warp < 6) {
@@ -438,6 +450,10 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
         if (r < nrows && px >= 0 && px < p.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + (long long)px * ld));
       }
     };
+    // diag counters (g.dbg): clocks this warp spent waiting for a free A slot / for its register loads / converting + storing /
+    // in the proxy fence + arrive, and the number of units
+    long long c_empty = 0, c_load = 0, c_conv = 0, c_pub = 0, c_units = 0;
+    const bool prof = g.dbg != nullptr;
     int cur_n = -1;
     uint32_t ua = 0, a_phase = 0;
     const float kNegLog2e = -1.4426950408889634f;
@@ -483,7 +499,16 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
         a4[2] = ab1.x; b4[2] = ab1.y; a4[3] = ab1.z; b4[3] = ab1.w;
       }
       const bool act = !q.side && g.silu;
+      long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      if (prof) t0 = clock64();
       mbar_wait(a_empty(ua), a_phase ^ 1u);
+      if (prof) {
+        t1 = clock64();
+        // touch the last-issued load of this buffer: the scoreboard wait for the register loads lands here, not in the conversion
+        uint32_t sink;
+        asm volatile("mov.b32 %0, %1;" : "=r"(sink) : "f"(buf[NIT - 1].x + buf[0].x));
+        t2 = clock64() + (sink & 0u);
+      }
       // 16-byte chunk (c4 >> 1) ^ (row & 7), 8-byte half (c4 & 1); row & 7 == row0 & 7 for every row of this thread
       const uint32_t hi_base = a_ring + ua * G_AUNIT + (uint32_t)row0 * 128u + (uint32_t)((((c4 >> 1) ^ (row0 & 7)) << 4) + (c4 & 1) * 8);
       const uint32_t lo_base = hi_base + G_APLANE;
@@ -514,9 +539,13 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
           st_shared_v2(lo_base + (uint32_t)i * 2048u, l01, l23);
         }
       }
+      if (prof) t3 = clock64();
       fence_proxy_async_smem();              // generic-proxy stores -> visible to the tensor core's (async proxy) reads
       __syncwarp();
       if (lane == 0) mbar_arrive_leader_release(a_full(ua));
+      if (prof) {
+        c_empty += t1 - t0; c_load += t2 - t1; c_conv += t3 - t2; c_pub += clock64() - t3; ++c_units;
+      }
       if (++ua == G_NA) {
         ua = 0;
         a_phase ^= 1u;
@@ -563,6 +592,10 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
         cur = nxt;
       }
     }
+    if (prof && tw == 0 && lane == 0) {
+      long long* d = g.dbg + (size_t)blockIdx.x * 16;
+      d[0] = c_units; d[1] = c_empty; d[2] = c_load; d[3] = c_conv; d[4] = c_pub;
+    }
   }
 
   tc_fence_before();
@@ -581,6 +614,8 @@ static int env_int(const char* name, int dflt) {
   const char* v = std::getenv(name);
   return v && *v ? std::atoi(v) : dflt;
 }
+static long long* g_gn_dbg = nullptr;
+void tc_debug_gn_counters(long long* dev_buf) { g_gn_dbg = dev_buf; }
 static int g_gn_desc_mode = env_int("DDNM_GN_DESC_MODE", 0);
 void tc_debug_gn_desc_mode(int mode) { g_gn_desc_mode = mode; }
 // Default OFF until the kernel beats gn_apply + conv_tc on the B200 (profiles/r02_gn_fused_*.md): round-2 measurements put it at
@@ -635,6 +670,7 @@ TcGnLaunch tc_make_gn_launch(const View& x, const GnAffine& gn, const View* side
   g.st_in = x.st; g.st_ld_in = x.st_ld;
   g.gamma = gn.gamma; g.beta = gn.beta; g.eps = gn.eps; g.groups = gn.groups; g.ss = gn.ss; g.ss_ld = gn.ss_ld; g.silu = gn.silu ? 1 : 0;
   g.desc_mode = g_gn_desc_mode;
+  g.dbg = g_gn_dbg;
   const int Ktot = (p.kb0 + p.kb1) * GK;
   const bool pd = L.BN == 128;
   L.bh = tc_make_weight_map(w_hi, Ktot, Cout, pd ? L.BN : L.BN / 2);

@@ -233,6 +233,10 @@ int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const
 int ddnm_conv_gn_tc(const float* x, int N, int H, int W, int Cin, int groups, const float* gamma, const float* beta, float eps, int silu,
                     const float* w, const float* bias, int Cout, const float* side_x, int CinSide, const float* side_w,
                     const float* residual, float* out, int iters, float* ms_per_iter, void* stream);
+/* diag: device buffer of 16 int64 per CTA (>= 148 CTAs) that fused launches BUILT afterwards fill with clock counters — transform
+ * warp 0: [0] units, [1] waiting for a free A slot, [2] waiting for its register loads, [3] converting + storing, [4] fence + arrive;
+ * UMMA issuer (leader CTAs): [8] total, [9] waiting for A units, [10] for B stages, [11] for a free accumulator.  NULL = off */
+int ddnm_tc_debug_gn_counters(long long* dev_buf);
 /* tests: 0 = shifted start address only, 1 = shifted start address + descriptor base-offset field */
 int ddnm_tc_debug_gn_desc_mode(int mode);
 /* 1: eligible layers (3x3, rows >= 128 pixels) of engines built afterwards run the fused GroupNorm convolution; 0 (default, also env
