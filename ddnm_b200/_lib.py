@@ -95,6 +95,7 @@ _SIGS = {
     "ddnm_conv_gn_tc": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _P, _I, _P, _I, _P, _P, _P, _I, C.POINTER(_F), _P]),
     "ddnm_tc_debug_gn_desc_mode": (C.c_int, [_I]),
     "ddnm_tc_debug_gn_counters": (C.c_int, [_P]),
+    "ddnm_tc_debug_gn_pf_dist": (C.c_int, [_I]),
     "ddnm_tc_debug_gn_fused": (C.c_int, [_I]),
     "ddnm_tc_debug_override": (C.c_int, [C.c_uint, C.c_uint]),
     "ddnm_tc_debug_force_bn": (C.c_int, [_I]),

@@ -328,6 +328,11 @@ int ddnm_tc_debug_gn_counters(long long* dev_buf) {
   tc_debug_gn_counters(dev_buf);
   DDNM_API_END
 }
+int ddnm_tc_debug_gn_pf_dist(int d) {
+  DDNM_API_BEGIN
+  tc_debug_gn_pf_dist(d);
+  DDNM_API_END
+}
 int ddnm_tc_debug_gn_desc_mode(int mode) {
   DDNM_API_BEGIN
   tc_debug_gn_desc_mode(mode);

@@ -99,6 +99,7 @@ struct TcGnParams {
   int ss_ld;
   int silu, norm;
   int desc_mode;                  // 0: shifted start address only; 1: + base-offset field (descriptor bits [49,52))
+  int pf_dist;                    // L2 prefetch distance in units (0 = none)
   long long* dbg;                 // optional (tests/diag): per-CTA clock counters, 16 per CTA — see conv_gn_tc_kernel
 };
 struct TcGnLaunch {
@@ -116,6 +117,7 @@ TcGnLaunch tc_make_gn_launch(const View& x, const GnAffine& gn, const View* side
 void tc_gn_run(const TcGnLaunch& L, cudaStream_t stream);
 void tc_debug_gn_desc_mode(int mode);   // tests: how the shifted A start address is described to the tensor core
 void tc_debug_gn_counters(long long* dev_buf);   // diag: where the fused kernel's warps spend their clocks (nullptr = off)
+void tc_debug_gn_pf_dist(int d);       // diag: L2 prefetch distance of fused launches built afterwards
 void tc_debug_gn_fused(int on);         // 1: eligible layers use the fused kernel; 0 (default): gn_apply + conv_tc
 
 // debug knobs (tests only): override descriptor words for the NEXT launches built

@@ -4,8 +4,8 @@
 //
 // What the unfused path does in two kernels with an HBM round trip in between (gn_apply_kernel writes the fp16 hi/lo planes,
 // conv_tc_kernel reads them back 9 times through L2), this kernel does in one: the A operand of the implicit GEMM is produced
-// INSIDE the convolution kernel.  Eight "transform" warps read the raw fp32 activation rows straight from global memory into
-// registers, apply the per-(image, channel) GroupNorm affine + SiLU (computed from the producer's running sums, View::st),
+// INSIDE the convolution kernel.  Eight "transform" warps (two groups taking alternate units) read the raw fp32 activation rows
+// straight from global memory into registers, apply the per-(image, channel) GroupNorm affine + SiLU (computed from the producer's running sums, View::st),
 // split to fp16 hi/lo and store the 128B-swizzled K-major operand rows into shared memory — ONE halo row of 130 pixels per
 // (row offset dy, 64-channel slice), which then feeds the THREE taps dx = -1, 0, +1 through UMMA descriptors whose start
 // address is shifted by one 128-byte operand row per tap.  So per element the normalisation runs 3x (once per dy) instead of
@@ -49,7 +49,7 @@ struct GnCfg {
   static constexpr int ACC_COLS = 256;                 // PD: two partial accumulators of 128 columns; BN = 256: one of 256
   static constexpr int TMEM_COLS = 512;
   static constexpr int RING_BYTES = G_NA * G_AUNIT + NB * B_STAGE;
-  static constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + G_MAXC * 8 /*coefficients*/;
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * G_MAXC * 8 /*coefficient tables of the two transform groups*/;
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory capacity");
 };
 
@@ -158,7 +158,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
     tma_prefetch_desc(&tm_bl);
     tma_prefetch_desc(&tm_b2);
     for (int s = 0; s < G_NA; ++s) {
-      mbar_init(a_full(s), 16);                // one arrival per transform warp of BOTH CTAs (used in the leader only)
+      mbar_init(a_full(s), 8);                 // one arrival per warp of the transform GROUP that filled the unit, both CTAs (leader's copy)
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < NB; ++s) {
@@ -285,7 +285,7 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
       }
       if (prof) {
         long long* d = g.dbg + (size_t)blockIdx.x * 16;
-        d[8] = clock64() - t_all; d[9] = w_a; d[10] = w_b; d[11] = w_t;
+        d[10] = clock64() - t_all; d[11] = w_a; d[12] = w_b; d[13] = w_t;
       }
     }
   } else if (warp < 6) {
@@ -386,90 +386,60 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
   } else {
     // ------------------------------------------------ transform warps ---------------------------------------------
     // Unit = one operand row block: (64-channel slice c, row offset dy) -> 130 halo pixels x 64 channels, or a 1x1 side slice ->
-    // 128 pixels x 64 channels.  Thread <-> 4 channels (one 16-byte fp32 load, fully coalesced: 16 lanes cover a pixel's 256 bytes)
-    // of up to 9 rows: row = i*16 + tw*2 + (lane >> 4).  The NEXT unit's loads are issued before this unit is converted (two
-    // register buffers), so the global-memory latency hides behind the conversion of the previous unit.
-    const int tw = warp - 6;
+    // 128 pixels x 64 channels.  The 8 warps form TWO groups of 4 that take alternate units: a group issues all loads of its unit
+    // (thread <-> 4 channels = one coalesced 16-byte load per row, 17 rows: row = i*8 + tw*2 + (lane >> 4)), converts, stores,
+    // fences and publishes; while it waits for memory the other group converts ITS unit.  (A register double buffer inside one
+    // group does not work: the generic->async proxy fence that must precede the publish is a MEMBAR that waits for the thread's
+    // outstanding global loads, i.e. for the prefetch — measured with ncu: stall_membar / long-scoreboard on the fence.)
+    const int grp = (warp - 6) >> 2;         // 0 / 1
+    const int tw = (warp - 6) & 3;
     const int half = lane >> 4, c4 = lane & 15;
-    const int tt = threadIdx.x - 6 * 32;     // 0..255 within the transform group
-    constexpr int NIT = 9;
-    const int row0 = tw * 2 + half;          // + 16*i
-    // per-thread constant part of the swizzled smem offset: 16-byte chunk (c4 >> 1) ^ (row & 7), 8-byte half (c4 & 1)
-    struct Unit {
-      const float* base;   // first pixel of the row block for this thread's channels (nullptr: the whole block is padding)
-      int nrows, px0, ld, n, c, side;
-    };
-    int t_x0 = 0, t_y = 0, t_n = 0;          // tile of the unit iterator (decoded once per tile: integer divisions are slow)
-    auto unit_of = [&](int u, int j) {
-      Unit q;
-      if (j == 0) {
+    const int gt = threadIdx.x - (6 + 4 * grp) * 32;   // 0..127 within the group
+    constexpr int NIT = 17;
+    const int row0 = tw * 2 + half;          // + 8*i   (so row & 7 == row0 & 7 for every row of this thread)
+    float2* gcoef = coef + grp * G_MAXC;     // per-group coefficient table (the groups may be in different images)
+    long long c_empty = 0, c_load = 0, c_conv = 0, c_pub = 0, c_units = 0;
+    const bool prof = g.dbg != nullptr;
+    const float kNegLog2e = -1.4426950408889634f;
+    int cur_n = -1;
+    int t_x0 = 0, t_y = 0, t_n = 0, t_u = -1;
+    // this group's units: sequence index q = grp, grp + 2, ... over (tile, j); A ring slot q % G_NA
+    int u = unit_begin, j = grp;
+    while (j >= upt) { j -= upt; u += unit_step; }
+    for (long long q = grp; u < unit_end; q += 2) {
+      if (u != t_u) {                        // decode once per tile (integer divisions are slow)
         int n_idx;
         decode(tile_of(u), n_idx, t_x0, t_y, t_n);
-      }
-      const int x0 = t_x0, y = t_y;
-      q.n = t_n;
-      q.side = j >= 3 * cb0;
-      q.c = q.side ? j - 3 * cb0 : j / 3;
-      const int yy = q.side ? y : y + (j - 3 * q.c) - 1;
-      q.nrows = q.side ? 128 : 130;
-      q.px0 = q.side ? x0 : x0 - 1;
-      q.ld = q.side ? g.xs_ld : g.x_ld;
-      const float* src = q.side ? g.xs : g.x;
-      q.base = (yy >= 0 && yy < p.H) ? src + ((long long)q.n * p.H + yy) * p.W * q.ld + q.c * GK + c4 * 4 : nullptr;
-      return q;
-    };
-    auto load_unit = [&](const Unit& q, float4 (&buf)[NIT]) {
-#pragma unroll
-      for (int i = 0; i < NIT; ++i) {
-        const int r = i * 16 + row0;
-        const int px = q.px0 + r;
-        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q.base != nullptr && r < q.nrows && px >= 0 && px < p.W) buf[i] = ldg_nc_f4(q.base + (long long)px * q.ld);
-      }
-    };
-    // L2 prefetch of a unit a few units ahead of its register loads: the register double buffer covers one unit of work (~1 us),
-    // not a loaded HBM round trip; with the lines already in L2 it does.  Thread tt <-> one 128-byte line: row tt >> 1, half tt & 1.
-    int f_x0 = 0, f_y = 0, f_n = 0;
-    auto prefetch_unit = [&](int u, int j) {
-      if (j == 0) {
-        int n_idx;
-        decode(tile_of(u), n_idx, f_x0, f_y, f_n);
+        t_u = u;
       }
       const bool side = j >= 3 * cb0;
       const int c = side ? j - 3 * cb0 : j / 3;
-      const int yy = side ? f_y : f_y + (j - 3 * c) - 1;
-      if (yy < 0 || yy >= p.H) return;
-      const int ld = side ? g.xs_ld : g.x_ld;
-      const float* rowp = (side ? g.xs : g.x) + ((long long)f_n * p.H + yy) * p.W * ld + c * GK + (tt & 1) * 32;
-      const int px0 = side ? f_x0 : f_x0 - 1;
+      const int yy = side ? t_y : t_y + (j - 3 * c) - 1;
       const int nrows = side ? 128 : 130;
+      const int px0 = side ? t_x0 : t_x0 - 1;
+      const int ld = side ? g.xs_ld : g.x_ld;
+      const float* base = (yy >= 0 && yy < p.H) ? (side ? g.xs : g.x) + ((long long)t_n * p.H + yy) * p.W * ld + c * GK + c4 * 4 : nullptr;
+      // ---- all loads of the unit in flight
+      float4 buf[NIT];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int r = (tt >> 1) + 128 * k;
+      for (int i = 0; i < NIT; ++i) {
+        const int r = i * 8 + row0;
         const int px = px0 + r;
-        if (r < nrows && px >= 0 && px < p.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + (long long)px * ld));
+        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (base != nullptr && r < nrows && px >= 0 && px < p.W) buf[i] = ldg_nc_f4(base + (long long)px * ld);
       }
-    };
-    // diag counters (g.dbg): clocks this warp spent waiting for a free A slot / for its register loads / converting + storing /
-    // in the proxy fence + arrive, and the number of units
-    long long c_empty = 0, c_load = 0, c_conv = 0, c_pub = 0, c_units = 0;
-    const bool prof = g.dbg != nullptr;
-    int cur_n = -1;
-    uint32_t ua = 0, a_phase = 0;
-    const float kNegLog2e = -1.4426950408889634f;
-    auto store_unit = [&](const Unit& q, float4 (&buf)[NIT]) {
-      if (!q.side && q.n != cur_n) {
-        // per-(image, channel) affine of the GroupNorm (+ scale-shift) from the producer's running sums: y = a*x + b
-        named_bar_sync(1, 256);              // everyone is done with the previous image's table
+      // ---- per-(image, channel) affine of the GroupNorm (+ scale-shift) from the producer's running sums: y = a*x + b
+      if (!side && t_n != cur_n) {
+        named_bar_sync(1 + grp, 128);        // the group is done with the previous image's table
         const int C = cb0 * GK;
-        for (int ch = tt; ch < C; ch += 256) {
+        for (int ch = gt; ch < C; ch += 128) {
           float a = 1.f, b = 0.f;
           if (g.norm) {
             const int cpg = C / g.groups;
             const int g0 = (ch / cpg) * cpg;
             double s1 = 0, s2 = 0;
             for (int k = 0; k < cpg; ++k) {
-              const StatAcc* sp = g.st_in + ((size_t)q.n * g.st_ld_in + g0 + k) * 2;
+              const StatAcc* sp = g.st_in + ((size_t)t_n * g.st_ld_in + g0 + k) * 2;
               s1 += stat_value(sp[0]);
               s2 += stat_value(sp[1]);
             }
@@ -481,46 +451,46 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
             a = rstd * g.gamma[ch];
             b = g.beta[ch] - (float)mean * a;
             if (g.ss) {                      // h = norm(h) * (1 + scale) + shift   (unet.py:250-252)
-              const float one_plus = 1.0f + g.ss[(size_t)q.n * g.ss_ld + ch];
+              const float one_plus = 1.0f + g.ss[(size_t)t_n * g.ss_ld + ch];
               a *= one_plus;
-              b = fmaf(b, one_plus, g.ss[(size_t)q.n * g.ss_ld + C + ch]);
+              b = fmaf(b, one_plus, g.ss[(size_t)t_n * g.ss_ld + C + ch]);
             }
           }
-          coef[ch] = make_float2(a, b);
+          gcoef[ch] = make_float2(a, b);
         }
-        named_bar_sync(1, 256);
-        cur_n = q.n;
+        named_bar_sync(1 + grp, 128);
+        cur_n = t_n;
       }
       float a4[4] = {1.f, 1.f, 1.f, 1.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (!q.side) {
-        const float4 ab0 = *reinterpret_cast<const float4*>(&coef[q.c * GK + c4 * 4]);
-        const float4 ab1 = *reinterpret_cast<const float4*>(&coef[q.c * GK + c4 * 4 + 2]);
+      if (!side) {
+        const float4 ab0 = *reinterpret_cast<const float4*>(&gcoef[c * GK + c4 * 4]);
+        const float4 ab1 = *reinterpret_cast<const float4*>(&gcoef[c * GK + c4 * 4 + 2]);
         a4[0] = ab0.x; b4[0] = ab0.y; a4[1] = ab0.z; b4[1] = ab0.w;
         a4[2] = ab1.x; b4[2] = ab1.y; a4[3] = ab1.z; b4[3] = ab1.w;
       }
-      const bool act = !q.side && g.silu;
+      const bool act = !side && g.silu;
+      const uint32_t ua = (uint32_t)(q % G_NA), a_phase = (uint32_t)((q / G_NA) & 1);
       long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
       if (prof) t0 = clock64();
       mbar_wait(a_empty(ua), a_phase ^ 1u);
       if (prof) {
         t1 = clock64();
-        // touch the last-issued load of this buffer: the scoreboard wait for the register loads lands here, not in the conversion
-        uint32_t sink;
+        uint32_t sink;   // touch the last-issued load: the scoreboard wait for the unit's loads lands here, not in the conversion
         asm volatile("mov.b32 %0, %1;" : "=r"(sink) : "f"(buf[NIT - 1].x + buf[0].x));
         t2 = clock64() + (sink & 0u);
       }
-      // 16-byte chunk (c4 >> 1) ^ (row & 7), 8-byte half (c4 & 1); row & 7 == row0 & 7 for every row of this thread
+      // 16-byte chunk (c4 >> 1) ^ (row & 7), 8-byte half (c4 & 1)
       const uint32_t hi_base = a_ring + ua * G_AUNIT + (uint32_t)row0 * 128u + (uint32_t)((((c4 >> 1) ^ (row0 & 7)) << 4) + (c4 & 1) * 8);
       const uint32_t lo_base = hi_base + G_APLANE;
 #pragma unroll
       for (int i = 0; i < NIT; ++i) {
-        const int r = i * 16 + row0;
-        if (r < q.nrows) {
+        const int r = i * 8 + row0;
+        if (r < nrows) {
           // padding pixels / rows: the ACTIVATED value is zero (conv zero padding), whatever silu(b) would be
-          const int px = q.px0 + r;
-          if (q.base == nullptr || px < 0 || px >= p.W) {
-            st_shared_v2(hi_base + (uint32_t)i * 2048u, 0u, 0u);
-            st_shared_v2(lo_base + (uint32_t)i * 2048u, 0u, 0u);
+          const int px = px0 + r;
+          if (base == nullptr || px < 0 || px >= p.W) {
+            st_shared_v2(hi_base + (uint32_t)i * 1024u, 0u, 0u);
+            st_shared_v2(lo_base + (uint32_t)i * 1024u, 0u, 0u);
             continue;
           }
           float t[4] = {buf[i].x, buf[i].y, buf[i].z, buf[i].w};
@@ -535,65 +505,23 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
           uint32_t h01, h23, l01, l23;
           split2_f16(t[0], t[1], h01, l01);
           split2_f16(t[2], t[3], h23, l23);
-          st_shared_v2(hi_base + (uint32_t)i * 2048u, h01, h23);       // row r = row0 + 16 i: same swizzle phase for every i
-          st_shared_v2(lo_base + (uint32_t)i * 2048u, l01, l23);
+          st_shared_v2(hi_base + (uint32_t)i * 1024u, h01, h23);
+          st_shared_v2(lo_base + (uint32_t)i * 1024u, l01, l23);
         }
       }
       if (prof) t3 = clock64();
       fence_proxy_async_smem();              // generic-proxy stores -> visible to the tensor core's (async proxy) reads
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader_release(a_full(ua));
+      // plain (release.cta) arrive: a .release.cluster arrive adds MEMBAR.ALL.CTA + ERRBAR
+      if (lane == 0) mbar_arrive_leader(a_full(ua));
       if (prof) {
         c_empty += t1 - t0; c_load += t2 - t1; c_conv += t3 - t2; c_pub += clock64() - t3; ++c_units;
       }
-      if (++ua == G_NA) {
-        ua = 0;
-        a_phase ^= 1u;
-      }
-    };
-    float4 buf0[NIT], buf1[NIT];
-    int u = unit_begin, j = 0;
-    constexpr int PF_DIST = 4;               // units between the L2 prefetch and the register loads
-    int fu = unit_begin, fj = 0;
-    auto prefetch_next = [&]() {
-      if (fu < unit_end) {
-        prefetch_unit(fu, fj);
-        if (++fj == upt) { fj = 0; fu += unit_step; }
-      }
-    };
-    if (u < unit_end) {
-#pragma unroll 1
-      for (int k = 0; k < PF_DIST + 1; ++k) prefetch_next();
-      Unit cur = unit_of(u, j);
-      load_unit(cur, buf0);
-      while (true) {
-        // ---- even step: convert buf0 while buf1 fills
-        if (++j == upt) { j = 0; u += unit_step; }
-        Unit nxt = cur;
-        const bool more0 = u < unit_end;
-        if (more0) {
-          nxt = unit_of(u, j);
-          load_unit(nxt, buf1);
-        }
-        prefetch_next();
-        store_unit(cur, buf0);
-        if (!more0) break;
-        cur = nxt;
-        // ---- odd step: convert buf1 while buf0 fills
-        if (++j == upt) { j = 0; u += unit_step; }
-        const bool more1 = u < unit_end;
-        if (more1) {
-          nxt = unit_of(u, j);
-          load_unit(nxt, buf0);
-        }
-        prefetch_next();
-        store_unit(cur, buf1);
-        if (!more1) break;
-        cur = nxt;
-      }
+      j += 2;
+      while (j >= upt) { j -= upt; u += unit_step; }
     }
     if (prof && tw == 0 && lane == 0) {
-      long long* d = g.dbg + (size_t)blockIdx.x * 16;
+      long long* d = g.dbg + (size_t)blockIdx.x * 16 + grp * 5;
       d[0] = c_units; d[1] = c_empty; d[2] = c_load; d[3] = c_conv; d[4] = c_pub;
     }
   }
@@ -617,6 +545,8 @@ static int env_int(const char* name, int dflt) {
 static long long* g_gn_dbg = nullptr;
 void tc_debug_gn_counters(long long* dev_buf) { g_gn_dbg = dev_buf; }
 static int g_gn_desc_mode = env_int("DDNM_GN_DESC_MODE", 0);
+static int g_gn_pf_dist = env_int("DDNM_GN_PF_DIST", 0);
+void tc_debug_gn_pf_dist(int d) { g_gn_pf_dist = d; }
 void tc_debug_gn_desc_mode(int mode) { g_gn_desc_mode = mode; }
 // Default OFF until the kernel beats gn_apply + conv_tc on the B200 (profiles/r02_gn_fused_*.md): round-2 measurements put it at
 // parity on the Cout = 256 layers and behind on the Cout = 128 ones (the transform warps, not the tensor pipe, pace it).
@@ -671,6 +601,7 @@ TcGnLaunch tc_make_gn_launch(const View& x, const GnAffine& gn, const View* side
   g.gamma = gn.gamma; g.beta = gn.beta; g.eps = gn.eps; g.groups = gn.groups; g.ss = gn.ss; g.ss_ld = gn.ss_ld; g.silu = gn.silu ? 1 : 0;
   g.desc_mode = g_gn_desc_mode;
   g.dbg = g_gn_dbg;
+  g.pf_dist = g_gn_pf_dist;
   const int Ktot = (p.kb0 + p.kb1) * GK;
   const bool pd = L.BN == 128;
   L.bh = tc_make_weight_map(w_hi, Ktot, Cout, pd ? L.BN : L.BN / 2);

@@ -233,10 +233,12 @@ int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const
 int ddnm_conv_gn_tc(const float* x, int N, int H, int W, int Cin, int groups, const float* gamma, const float* beta, float eps, int silu,
                     const float* w, const float* bias, int Cout, const float* side_x, int CinSide, const float* side_w,
                     const float* residual, float* out, int iters, float* ms_per_iter, void* stream);
-/* diag: device buffer of 16 int64 per CTA (>= 148 CTAs) that fused launches BUILT afterwards fill with clock counters — transform
- * warp 0: [0] units, [1] waiting for a free A slot, [2] waiting for its register loads, [3] converting + storing, [4] fence + arrive;
- * UMMA issuer (leader CTAs): [8] total, [9] waiting for A units, [10] for B stages, [11] for a free accumulator.  NULL = off */
+/* diag: device buffer of 16 int64 per CTA (>= 148 CTAs) that fused launches BUILT afterwards fill with clock counters — first warp
+ * of transform group g at [5g..5g+4]: units, waiting for a free A slot, waiting for its register loads, converting + storing,
+ * fence + arrive; UMMA issuer (leader CTAs): [10] total, [11] waiting for A units, [12] for B stages, [13] for a free accumulator */
 int ddnm_tc_debug_gn_counters(long long* dev_buf);
+/* diag: L2 prefetch distance (in A units) of fused launches built afterwards; 0 = none (default, env DDNM_GN_PF_DIST) */
+int ddnm_tc_debug_gn_pf_dist(int d);
 /* tests: 0 = shifted start address only, 1 = shifted start address + descriptor base-offset field */
 int ddnm_tc_debug_gn_desc_mode(int mode);
 /* 1: eligible layers (3x3, rows >= 128 pixels) of engines built afterwards run the fused GroupNorm convolution; 0 (default, also env

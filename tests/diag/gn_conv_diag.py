@@ -62,6 +62,9 @@ def timing():
     """fused kernel vs (gn_apply + conv_tc) on the celeba / imagenet wide-layer shapes, random data"""
     L = _lib.lib()
     dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+    pf = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    L.ddnm_tc_debug_gn_pf_dist(pf)
+    print(f"--- L2 prefetch distance {pf}")
     for (N, H, W, Cin, Cout, side) in [(16, 256, 256, 256, 128, 0), (16, 256, 256, 128, 128, 256), (16, 256, 256, 128, 128, 0),
                                        (16, 128, 128, 256, 128, 0), (8, 256, 256, 256, 256, 0), (8, 128, 128, 512, 256, 0)]:
         err, sc, ms = run(N, H, W, Cin, Cout, side_c=side, iters=5)
@@ -75,12 +78,12 @@ def timing():
         L.ddnm_tc_debug_gn_counters(None)
         d = dbg.reshape(148, 16).double().cpu()
         tr = d[d[:, 0] > 0]
-        mm = d[d[:, 8] > 0]
+        mm = d[d[:, 10] > 0]
         per = lambda k: (tr[:, k] / tr[:, 0]).mean().item()     # noqa: E731
-        print(f"   transform warp 0, clocks per unit: wait-free-slot {per(1):.0f}, wait-loads {per(2):.0f}, convert+store {per(3):.0f}, "
-              f"fence+arrive {per(4):.0f} (units per CTA {tr[:, 0].mean().item():.0f}); UMMA issuer: total {mm[:, 8].mean().item():.3g} clk, "
-              f"waiting for A {100 * (mm[:, 9] / mm[:, 8]).mean().item():.0f}%, B {100 * (mm[:, 10] / mm[:, 8]).mean().item():.0f}%, "
-              f"accumulator {100 * (mm[:, 11] / mm[:, 8]).mean().item():.0f}%", flush=True)
+        print(f"   transform group 0 (warp 0), clocks per unit of the group: wait-free-slot {per(1):.0f}, wait-loads {per(2):.0f}, convert+store {per(3):.0f}, "
+              f"fence+arrive {per(4):.0f} (units per CTA {tr[:, 0].mean().item():.0f}); UMMA issuer: total {mm[:, 10].mean().item():.3g} clk, "
+              f"waiting for A {100 * (mm[:, 11] / mm[:, 10]).mean().item():.0f}%, B {100 * (mm[:, 12] / mm[:, 10]).mean().item():.0f}%, "
+              f"accumulator {100 * (mm[:, 13] / mm[:, 10]).mean().item():.0f}%", flush=True)
         print(f"timing N{N} {H}x{W} {Cin}->{Cout} side {side}: fused {ms:.3f} ms = {flops / ms / 1e9:.0f} TF/s (err {err:.1e}); "
               f"unfused conv alone (no side) {ms_c.value:.3f} ms = {fl.value / ms_c.value / 1e9:.0f} TF/s", flush=True)
 

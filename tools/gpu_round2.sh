@@ -19,7 +19,7 @@ for step in "$@"; do
     ncu_ops) for op in sr4 inpaint wh deblur; do timeout 600 ncu --set full --clock-control none -k regex:"local_kernel|inpaint_kernel|fwht_rows|fwht_cols|wh_spec|sgemm_kernel|mul_table|final_" -c 10 -o gpurun_out/prof_op_${op}_$TAG -f python tools/profile_ops.py $op > gpurun_out/ncu_op_${op}_$TAG.log 2>&1; tail -1 gpurun_out/ncu_op_${op}_$TAG.log; ncu_export prof_op_${op}_$TAG; done ;;
     ncu_gn)  DDNM_GN_FUSED=0 timeout 600 ncu --set full --clock-control none -k regex:"gn_apply" -s 2 -c 5 -o gpurun_out/prof_gn_$TAG -f python tools/profile_ops.py sr4 > gpurun_out/ncu_gn_$TAG.log 2>&1; tail -1 gpurun_out/ncu_gn_$TAG.log; ncu_export prof_gn_$TAG ;;
     ncu_tc)  DDNM_GN_FUSED=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_gn" -s 16 -c 3 -o gpurun_out/prof_tcgn_$TAG -f python tools/profile_ops.py sr4 > gpurun_out/ncu_tc_$TAG.log 2>&1; tail -1 gpurun_out/ncu_tc_$TAG.log; ncu_export prof_tcgn_$TAG source ;;
-    timing)  timeout 600 python tests/diag/gn_conv_diag.py timing > gpurun_out/gn_timing_$TAG.log 2>&1; cat gpurun_out/gn_timing_$TAG.log | tail -8 ;;
+    timing)  timeout 600 python tests/diag/gn_conv_diag.py timing 0 > gpurun_out/gn_timing_$TAG.log 2>&1; cat gpurun_out/gn_timing_$TAG.log | tail -28 ;;
     ab)      DDNM_GN_FUSED=0 tools/gpu_session.sh ab_unfused_$TAG unet_bench:celeba:16:5 | tail -25; DDNM_GN_FUSED=1 tools/gpu_session.sh ab_fused_$TAG unet_bench:celeba:16:5 openai_bench:8:3 | tail -50 ;;
     abpdl)   DDNM_PDL=0 tools/gpu_session.sh ab_nopdl_$TAG unet_bench:celeba:16:5 | grep "unet bench"; DDNM_PDL=1 tools/gpu_session.sh ab_pdl_$TAG unet_bench:celeba:16:5 openai_bench:8:3 | grep "bench" ;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 1 --profile-steps 2 > gpurun_out/ncu_bench_$TAG.log 2>&1; tail -2 gpurun_out/ncu_bench_$TAG.log ;;
