@@ -226,8 +226,14 @@ int ddnm_conv_tc_bench(int N, int H, int W, int Cin, int Cout, int mode, int ite
   DDNM_API_BEGIN
   const bool random = iters < 0;
   if (random) iters = -iters;
+  // mode bits [4,8): epilogue features as the network uses them — 16: GroupNorm sums of the output, 32: residual add,
+  // 64: per-(image, channel) add (bias + temb row), 128: the layer is one parity phase of an upsample convolution (2x2 taps on the
+  // H x W source, strided stores into a 2H x 2W map)
+  const int feat = mode >> 4;
+  mode &= 15;
+  const bool up2 = (feat & 8) != 0;
   Tmp tmp;
-  const int taps = mode == TAPS_1X1 ? 1 : 9;
+  const int taps = up2 ? 4 : (mode == TAPS_1X1 ? 1 : 9);
   const size_t pe = (size_t)N * H * W * Cin;
   SplitView A;
   A.hi = tmp.get<__half>(pe); A.lo = tmp.get<__half>(pe); A.N = N; A.H = H; A.W = W; A.C = Cin;
@@ -244,8 +250,28 @@ int ddnm_conv_tc_bench(int N, int H, int W, int Cin, int Cout, int mode, int ite
     const long long wn = (long long)Cout * ktot;
     bench_fill_split<<<(unsigned)cdivll(wn, 256), 256>>>(wh, wl, wn, 0x9876u, 1.0f / sqrtf((float)ktot));
   }
-  float* o = tmp.get<float>((size_t)N * H * W * Cout);
-  TcLaunch L = tc_make_launch(A, mode, nullptr, wh, wl, 1, Cout, mkview(o, N, H, W, Cout), nullptr, 0, nullptr, 0, 1.0f, sm_count());
+  const int oH = up2 ? 2 * H : H, oW = up2 ? 2 * W : W;
+  const size_t oe = (size_t)N * oH * oW * Cout;
+  float* o = tmp.get<float>(oe);
+  View ov = mkview(o, N, oH, oW, Cout);
+  if (feat & 1) {
+    ov.st = tmp.get<StatAcc>((size_t)N * Cout * 2);
+    ov.st_ld = Cout;
+    CUDA_CHECK(cudaMemset(ov.st, 0, (size_t)N * Cout * 2 * sizeof(StatAcc)));
+  }
+  float* res = nullptr;
+  if (feat & 2) {
+    res = tmp.get<float>(oe);
+    CUDA_CHECK(cudaMemset(res, 0, oe * 4));
+    if (random) bench_fill_f32<<<(unsigned)cdivll((long long)oe, 256), 256>>>(res, (long long)oe, 0x777u);
+  }
+  float* ca = nullptr;
+  if (feat & 4) {
+    ca = tmp.get<float>((size_t)N * Cout);
+    CUDA_CHECK(cudaMemset(ca, 0, (size_t)N * Cout * 4));
+  }
+  TcLaunch L = up2 ? tc_make_up2_launch(A, wh, wl, Cout, ov, ca, Cout, 0, 0, sm_count())
+                   : tc_make_launch(A, mode, nullptr, wh, wl, 1, Cout, ov, ca, Cout, res, Cout, 1.0f, sm_count());
   for (int i = 0; i < 3; ++i) tc_run(L, 0);
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0));
@@ -357,6 +383,11 @@ int ddnm_tc_debug_dual_mode(int mode) {
 int ddnm_tc_debug_pair_dual(int on) {
   DDNM_API_BEGIN
   tc_debug_pair_dual(on);
+  DDNM_API_END
+}
+int ddnm_tc_debug_deal(int mode) {
+  DDNM_API_BEGIN
+  tc_debug_deal(mode);
   DDNM_API_END
 }
 int ddnm_tc_debug_force_bn(int bn) {

@@ -58,10 +58,11 @@ struct StreamBuf {
   StreamBuf& operator=(const StreamBuf&) = delete;
 };
 
-// One GroupNorm running sum: a 128-bit two's-complement fixed-point accumulator with 64 fractional bits.  Partial sums from many
-// CTAs are added with integer atomics, so the total does not depend on the order in which they arrive: a forward pass is
-// bit-reproducible run to run (floating-point atomics are not).  Range +-2^63, resolution 2^-64 (anything a float partial sum
-// below 2^-40 would lose is far under the fp32 noise of the statistics themselves).
+// One GroupNorm running sum: a two's-complement fixed-point accumulator with 48 fractional bits kept as two carry-free words
+// (value = (hi * 2^32 + lo) * 2^-48, see stat_add).  Partial sums from many CTAs are added with integer atomics, so the total
+// does not depend on the order in which they arrive: a forward pass is bit-reproducible run to run (floating-point atomics
+// are not).  Range +-2^47, resolution 2^-48 (what a float partial sum loses below that is far under the fp32 noise of the
+// statistics themselves).
 struct StatAcc {
   unsigned long long lo;
   long long hi;
@@ -288,29 +289,40 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                : "memory");
 }
 
-// acc += p, exactly (p is converted to the 128-bit fixed point without rounding unless it has bits below 2^-64) and independent
-// of the order of concurrent adds: the low word's carry is detected by the one thread whose add wrapped it.
+// acc += p, independent of the order of concurrent adds.  p is converted (exactly, unless it has bits below 2^-48) to a signed
+// fixed-point integer X with 48 fractional bits, and X = W1 * 2^32 + W0 (W0 = X mod 2^32 >= 0, W1 = floor(X / 2^32)) is added
+// as TWO independent integer reductions: acc->lo += W0 (up to 2^32 partial sums cannot wrap it), acc->hi += W1 (range +-2^47).
+// No carry crosses between the words, so neither atomic needs its return value: both compile to fire-and-forget RED
+// instructions (a carry-propagating 128-bit add needs the old low word back, a round trip to L2 per statistic that the
+// epilogue warps of the tensor-core kernels had to wait for).
 __device__ __forceinline__ void stat_add(StatAcc* acc, float p) {
   const int bits = __float_as_int(p);
   int ex = (bits >> 23) & 0xff;
   unsigned long long m = (unsigned long long)(bits & 0x7fffff);
   if (ex) m |= 0x800000ull; else ex = 1;          // |p| = m * 2^(ex - 150)
-  const int sh = ex - 150 + 64;                   // fixed = m * 2^sh
-  unsigned long long lo = 0, hi = 0;
-  if (sh >= 64) hi = m << min(sh - 64, 39);        // |p| >= 2^63 cannot occur for activation sums; clamp the shift
-  else if (sh > 0) { lo = m << sh; hi = m >> (64 - sh); }
+  const int sh = ex - 150 + 48;                   // X = m * 2^sh
+  unsigned long long lo = 0, hi = 0;              // |X| as a 128-bit integer
+  if (sh >= 64) hi = m << min(sh - 64, 7);         // |p| >= 2^47 cannot occur for activation sums; clamp the shift
+  else if (sh > 0) { lo = m << sh; hi = sh > 40 ? m >> (64 - sh) : 0ull; }
   else if (sh > -24) lo = m >> (-sh);
   if (bits < 0) {                                 // two's-complement negate
     lo = ~lo + 1ull;
     hi = ~hi + (lo == 0ull ? 1ull : 0ull);
   }
-  if ((lo | hi) == 0ull) return;
-  const unsigned long long old = atomicAdd(&acc->lo, lo);
-  const unsigned long long carry = (old + lo < old) ? 1ull : 0ull;
-  if ((hi | carry) != 0ull) atomicAdd(reinterpret_cast<unsigned long long*>(&acc->hi), hi + carry);
+  const unsigned long long w0 = lo & 0xffffffffull;
+  const unsigned long long w1 = (hi << 32) | (lo >> 32);
+  if (w0) atomicAdd(&acc->lo, w0);
+  if (w1) atomicAdd(reinterpret_cast<unsigned long long*>(&acc->hi), w1);
+}
+// sum += v with the rounding error of the addition collected in comp (Knuth two-sum): sum + comp is the running total to ~2^-48
+__device__ __forceinline__ void two_sum_acc(float& sum, float& comp, float v) {
+  const float s = __fadd_rn(sum, v);
+  const float bb = __fadd_rn(s, -sum);
+  comp = __fadd_rn(comp, __fadd_rn(__fadd_rn(sum, -__fadd_rn(s, -bb)), __fadd_rn(v, -bb)));
+  sum = s;
 }
 __device__ __forceinline__ double stat_value(const StatAcc& a) {
-  return ((double)a.hi * 18446744073709551616.0 + (double)a.lo) * (1.0 / 18446744073709551616.0);
+  return ((double)a.hi * 4294967296.0 + (double)a.lo) * (1.0 / 281474976710656.0);
 }
 
 // fp32 -> (hi, lo) fp16 pair: hi = rn(x) saturated to the finite fp16 range, lo = rn(x - hi).

@@ -80,14 +80,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
   const int KB = p.kb0 + p.kb1;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles;
-  // tiles are dealt round-robin: at any moment the 148 CTAs work on 148 consecutive tiles (adjacent rows of one image), which
-  // keeps their shared halo rows and the DRAM stream together (a contiguous range per CTA measured ~4 % slower)
+  // p.deal == 0: tiles are dealt round-robin — at any moment the 148 CTAs work on 148 consecutive tiles (adjacent rows of one image).
+  // p.deal == 1 (layers with one N tile and GroupNorm sums to produce): every CTA owns a CONTIGUOUS range of tiles, so its tiles lie
+  // in one or two images and the epilogue's running sums are flushed to the global accumulators once or twice per CTA instead
+  // of once per tile (with 128-tile images the round-robin order changes image at every step: 2048 same-address reductions per
+  // tile were costing the 128x128 layers +60 % — tests/diag epi_bench).
   // PAIR: the scheduling unit is a pair of M-adjacent tiles sharing one N tile; CTA `rank` of the cluster owns tile 2*mp + rank.
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
-  const int unit_begin = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
-  const int unit_end = PAIR ? total_tiles / 2 : total_tiles;
-  const int unit_step = PAIR ? (int)(gridDim.x / 2) : (int)gridDim.x;
+  const int n_units = PAIR ? total_tiles / 2 : total_tiles;
+  const int n_workers = PAIR ? (int)(gridDim.x / 2) : (int)gridDim.x;
+  const int worker = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int unit_begin = p.deal ? (int)((long long)worker * n_units / n_workers) : worker;
+  const int unit_end = p.deal ? (int)((long long)(worker + 1) * n_units / n_workers) : n_units;
+  const int unit_step = p.deal ? 1 : n_workers;
   auto tile_of = [&](int u) {
     if (!PAIR) return u;
     const int mp = u / p.n_tiles;
@@ -270,11 +276,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     const int yi = (r / p.bw) % p.bh;
     const int ni = r / (p.bw * p.bh);
     uint32_t acc = 0, acc_phase = 0;
-    float run_s[CW / 32], run_q[CW / 32];
+    // running GroupNorm sums of this warp's columns over the CTA's consecutive tiles of one image, as (value, compensation) pairs:
+    // a contiguous tile range accumulates tens of tiles before a flush, and the two-sum keeps that as exact as one flush per tile
+    float run_s[CW / 32], run_q[CW / 32], cmp_s[CW / 32], cmp_q[CW / 32];
 #pragma unroll
     for (int ch = 0; ch < CW / 32; ++ch) {
       run_s[ch] = 0.f;
       run_q[ch] = 0.f;
+      cmp_s[ch] = 0.f;
+      cmp_q[ch] = 0.f;
     }
     for (int u = unit_begin; u < unit_end; u += unit_step) {
       const int tile = tile_of(u);
@@ -380,8 +390,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
               sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, k);
             }
           }
-          run_s[(c0 - chalf * CW) >> 5] += ov[0];
-          run_q[(c0 - chalf * CW) >> 5] += sq[0];
+          two_sum_acc(run_s[(c0 - chalf * CW) >> 5], cmp_s[(c0 - chalf * CW) >> 5], ov[0]);
+          two_sum_acc(run_q[(c0 - chalf * CW) >> 5], cmp_q[(c0 - chalf * CW) >> 5], sq[0]);
         }
       }
       if (p.stats) {
@@ -401,13 +411,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
             for (int ch = 0; ch < CW / 32; ++ch) {
               StatAcc* d = p.stats + ((size_t)img_w * p.st_ld + n_idx * BN + chalf * CW + ch * 32 + lane) * 2;
               stat_add(d, run_s[ch]);        // integer accumulation: the total is independent of the arrival order
+              stat_add(d, cmp_s[ch]);
               stat_add(d + 1, run_q[ch]);
+              stat_add(d + 1, cmp_q[ch]);
             }
           }
 #pragma unroll
           for (int ch = 0; ch < CW / 32; ++ch) {
             run_s[ch] = 0.f;
             run_q[ch] = 0.f;
+            cmp_s[ch] = 0.f;
+            cmp_q[ch] = 0.f;
           }
         }
       }
@@ -498,6 +512,11 @@ static int g_force_bn = 0;
 void tc_debug_force_bn(int bn) {
   DDNM_CHECK(bn == 0 || bn == 64 || bn == 128 || bn == 256, "BN must be 0 (heuristic), 64, 128 or 256");
   g_force_bn = bn;
+}
+static int g_deal = -1;
+void tc_debug_deal(int mode) {
+  DDNM_CHECK(mode >= -1 && mode <= 1, "deal mode must be -1 (default rule), 0 (round-robin) or 1 (contiguous ranges)");
+  g_deal = mode;
 }
 void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor) {
   g_desc_hi_override = desc_hi;
@@ -615,6 +634,11 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   }
   const int total = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
   L.grid = L.pair ? 2 * std::min(total / 2, num_sms / 2) : std::min(total, num_sms);
+  // contiguous tile ranges per CTA where the GroupNorm sums of the output would otherwise be flushed at every tile: one N tile
+  // (so consecutive tiles of a range share their channels) and several tiles per CTA
+  const int workers = L.pair ? L.grid / 2 : L.grid, units = L.pair ? total / 2 : total;
+  p.deal = g_deal >= 0 ? g_deal : (out.st != nullptr && p.n_tiles == 1 && units >= 2 * workers ? 1 : 0);
+  if (p.n_tiles != 1) p.deal = 0;
   L.flops = 2.0 * (double)out.pixels() * Cout * Ktot;
   return L;
 }

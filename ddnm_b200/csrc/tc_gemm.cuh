@@ -35,6 +35,7 @@ struct TcParams {
   float alpha;                 // out = alpha*acc + chanadd + residual
   StatAcc* stats;              // optional GroupNorm sums of the OUTPUT: stats[(image*st_ld + co)*2 + {0,1}] += {sum, sumsq}
   int st_ld;
+  int deal = 0;                // tile -> CTA map: 0 round-robin, 1 one contiguous range per CTA (see conv_tc_kernel)
   int terms;                   // 3: hi*hi + hi*lo + lo*hi (fp32-grade, default); 1: hi*hi only (plain fp16 inputs, fast mode)
   uint32_t desc_hi;            // UMMA smem descriptor high word (SW128 K-major), see tc_gemm.cu
   uint32_t idesc;              // UMMA instruction descriptor
@@ -123,6 +124,7 @@ void tc_debug_gn_fused(int on);         // 1: eligible layers use the fused kern
 // debug knobs (tests only): override descriptor words for the NEXT launches built
 void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor);
 void tc_debug_force_bn(int bn);
+void tc_debug_deal(int mode);        // -1 (default): contiguous tile ranges where they pay (one N tile + GroupNorm sums), 0 / 1: force
 void tc_debug_pair_dual(int on);     // 1 (default): CTA pairs at BN = 128 use the PAIR + DUAL form
 void tc_debug_dual_mode(int mode);   // 1: DUAL kernel for single-CTA BN <= 128 launches (default), 0: never
 void tc_debug_pair_mode(int mode);   // -1: cost model decides (default), 0: never, 1: CTA pairs wherever legal

@@ -319,11 +319,12 @@ def group_cpu_threads():
             print(f"   threads {nt}: {time.time() - t0:.2f} s / image-forward", flush=True)
 
 
-def group_unet_bench(which="celeba", B=16, iters=5, prec="fp32", pair_dual=1):
+def group_unet_bench(which="celeba", B=16, iters=5, prec="fp32", pair_dual=1, deal=-1, tag=""):
     from oracle import unet_simple as U
     from ddnm_b200.model import Model
     B, iters = int(B), int(iters)
     _lib.check(L.ddnm_tc_debug_pair_dual(int(pair_dual)))
+    _lib.check(L.ddnm_tc_debug_deal(int(deal)))
     cfg = U.SimpleUNetConfig.tiny() if which == "tiny" else U.SimpleUNetConfig.celeba_hq()
     sd = U.init_state_dict(cfg, 1234)
     m = Model(_cfg_ns(cfg))
@@ -356,7 +357,77 @@ def group_unet_bench(which="celeba", B=16, iters=5, prec="fp32", pair_dual=1):
     for p in top:
         print(f"   top {p['name']:28s} {p['ms']:.3f} ms  {p['flops'] / max(p['ms'], 1e-9) / 1e9:.1f} TF/s  {p['bytes'] / max(p['ms'], 1e-9) / 1e6:.1f} GB/s")
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(prof, open(f"gpurun_out/unet_profile_{which}_B{B}.json", "w"))
+    json.dump(prof, open(f"gpurun_out/unet_profile_{which}_B{B}{tag}.json", "w"))
+
+
+def group_lanes(which="celeba", B=16, lanes=2, iters=5, openai=0):
+    """Prototype: the batch as `lanes` independent sub-batches, one engine + stream each — does the block scheduler overlap
+    one lane's HBM-bound GroupNorm passes with the other's tensor-core convolutions?"""
+    from oracle import unet_simple as U
+    from ddnm_b200.model import Model
+    B, lanes, iters = int(B), int(lanes), int(iters)
+    cfg = U.SimpleUNetConfig.tiny() if which == "tiny" else U.SimpleUNetConfig.celeba_hq()
+    sd = U.init_state_dict(cfg, 1234)
+    sub = B // lanes
+    ms_, xs, ts, ss = [], [], [], []
+    for l in range(lanes):
+        m = Model(_cfg_ns(cfg))
+        m.load_state_dict(sd)
+        ms_.append(m)
+        xs.append(torch.randn(sub, 3, cfg.resolution, cfg.resolution, device=dev))
+        ts.append(torch.full((sub,), 500.0, device=dev))
+        ss.append(torch.cuda.Stream())
+    for l in range(lanes):
+        for _ in range(3):
+            ms_[l](xs[l], ts[l])
+    torch.cuda.synchronize()
+    def run(n, concurrent):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        if concurrent:
+            start = torch.cuda.Event(); start.record()
+            for _ in range(n):
+                for l in range(lanes):
+                    with torch.cuda.stream(ss[l]):
+                        ms_[l](xs[l], ts[l])
+            for l in range(lanes):
+                torch.cuda.current_stream().wait_stream(ss[l])
+        else:
+            for _ in range(n):
+                for l in range(lanes):
+                    ms_[l](xs[l], ts[l])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    for l in range(lanes):
+        ss[l].wait_stream(torch.cuda.current_stream())
+    a = run(iters, False)
+    b = run(iters, True)
+    b2 = run(iters, True)
+    print(f"[lanes {which} B{B} = {lanes} x {sub}] serial {a:.2f} ms per {B} images; concurrent {b:.2f} / {b2:.2f} ms per {B} images")
+
+
+def group_epi_bench(iters=-20, deal=-1):
+    """Epilogue features as the network uses them (mode bits 16: GroupNorm sums, 32: residual, 64: channel add, 128: upsample phase)
+    on the layer shapes where the epilogue is exposed (short K)."""
+    ms, fl = C.c_float(), C.c_double()
+    iters = int(iters)
+    _lib.check(L.ddnm_tc_debug_deal(int(deal)))
+    print(f"[epi_bench] deal mode {deal}")
+    for (N, H, W, Cin, Cout) in [(16, 256, 256, 128, 128), (16, 128, 128, 128, 128), (16, 256, 256, 256, 128), (16, 64, 64, 256, 256),
+                                 (16, 32, 32, 256, 256), (16, 8, 8, 512, 512)]:
+        row = []
+        for feat in (0, 16, 32, 64, 16 + 64, 16 + 32 + 64):
+            _lib.check(L.ddnm_conv_tc_bench(N, H, W, Cin, Cout, feat, iters, C.byref(ms), C.byref(fl)))
+            row.append(f"{ms.value * 1e3:7.1f}")
+        print(f"[epi_bench] N{N} {H}x{W} {Cin}->{Cout} 3x3: plain {row[0]} | stats {row[1]} | residual {row[2]} | chanadd {row[3]} | stats+chanadd {row[4]} | all {row[5]} us", flush=True)
+    for (N, H, W, Cin, Cout) in [(16, 128, 128, 128, 128), (16, 64, 64, 256, 128), (16, 32, 32, 256, 256)]:
+        row = []
+        for feat in (128, 128 + 16, 128 + 64, 128 + 16 + 64):
+            _lib.check(L.ddnm_conv_tc_bench(N, H, W, Cin, Cout, feat, iters, C.byref(ms), C.byref(fl)))
+            row.append(f"{ms.value * 1e3:7.1f}")
+        print(f"[epi_bench] N{N} {H}x{W} {Cin}->{Cout} up-phase: plain {row[0]} | stats {row[1]} | chanadd {row[2]} | stats+chanadd {row[3]} us", flush=True)
 
 
 def group_eager(which="celeba", B=16, iters=3):
