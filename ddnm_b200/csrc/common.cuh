@@ -230,6 +230,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 32-byte global accesses (sm_100: LDG/STG .256): one whole sector per thread
+__device__ __forceinline__ void ldg_f32x8(const float* p, float* r) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_f32x8(float* p, const float* r) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]),
+               "f"(r[5]), "f"(r[6]), "f"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // --- CTA pair (cta_group::2): two SMs of one TPC execute one 256-row MMA; CTA rank 0 ("leader") issues it.  The shared::cluster

@@ -267,10 +267,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     }
   } else {
     // ------------------------------------------------ epilogue ----------------------------------------------------
-    // 8 epilogue warps: warp w may touch TMEM lanes 32*(w%4)..+31; the two warps sharing a lane quarter split the columns
+    // 8 epilogue warps: warp w may touch TMEM lanes 32*(w%4)..+31; the two warps sharing a lane quarter split the columns.
+    // Per tile a warp handles NCH chunks of 32 columns.  Latency is what the epilogue is made of (ncu: the warps sit on the long
+    // scoreboard), so nothing that does not depend on the accumulator waits for it: the residual rows of a chunk are requested one
+    // chunk earlier (across the tile boundary too, i.e. while the MMAs of the tile are still running), both partial accumulators are
+    // read with one wait, the TMEM stage goes back to the MMA issuer right after the last read, and rows move as 32-byte vectors
+    // (whole sectors per thread: half the LSU instructions of 16-byte accesses and no partial-sector writes).
     const int ew = warp & 3;
     const int chalf = (warp - 2) >> 2;
-    constexpr int CW = BN / 2;  // columns per epilogue warp
+    constexpr int CW = BN / 2;      // columns per epilogue warp
+    constexpr int NCH = CW / 32;    // 32-column chunks per warp and tile
     const int r = ew * 32 + lane;
     const int xi = r % p.bw;
     const int yi = (r / p.bw) % p.bh;
@@ -278,100 +284,113 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
     uint32_t acc = 0, acc_phase = 0;
     // running GroupNorm sums of this warp's columns over the CTA's consecutive tiles of one image, as (value, compensation) pairs:
     // a contiguous tile range accumulates tens of tiles before a flush, and the two-sum keeps that as exact as one flush per tile
-    float run_s[CW / 32], run_q[CW / 32], cmp_s[CW / 32], cmp_q[CW / 32];
+    float run_s[NCH], run_q[NCH], cmp_s[NCH], cmp_q[NCH];
 #pragma unroll
-    for (int ch = 0; ch < CW / 32; ++ch) {
+    for (int ch = 0; ch < NCH; ++ch) {
       run_s[ch] = 0.f;
       run_q[ch] = 0.f;
       cmp_s[ch] = 0.f;
       cmp_q[ch] = 0.f;
     }
-    for (int u = unit_begin; u < unit_end; u += unit_step) {
-      const int tile = tile_of(u);
-      int n_idx, x0, y0, n0;
-      decode(tile, n_idx, x0, y0, n0);
+    const bool dual_sum = DUAL && p.terms != 1;
+    struct Tile {
+      float* orow;
+      const float* rrow;      // residual source row (same pixel / nearest-upsampled / top-left of the 2x2 block to average)
+      const float* crow;
+      int n_idx, img_w;
+      bool valid;
+    };
+    auto setup = [&](int u, Tile& t) {
+      int x0, y0, n0;
+      decode(tile_of(u), t.n_idx, x0, y0, n0);
       const int n = n0 + ni;
-      const bool valid = n < p.N;
-      const long long pix = ((long long)n * p.H + (y0 + yi)) * p.W + (x0 + xi);
-      float* orow = p.out + (long long)n * p.out_sn + (long long)(y0 + yi) * p.out_sy + (long long)(x0 + xi) * p.out_sx + n_idx * BN;
-      // residual source row(s): same pixel, nearest-upsampled (x_upd of ResBlock(up=True), unet.py:240) or the 2x2
-      // average of a twice-as-large map (ResBlock(down=True))
-      const float* rrow = nullptr;
-      long long r_dx = 0, r_dy = 0;
+      t.valid = n < p.N;
+      t.img_w = n0 + (ew * 32) / (p.bw * p.bh);
+      t.orow = p.out + (long long)n * p.out_sn + (long long)(y0 + yi) * p.out_sy + (long long)(x0 + xi) * p.out_sx + t.n_idx * BN;
+      t.rrow = nullptr;
       if (p.residual) {
-        if (p.res_mode == 0) {
-          rrow = p.residual + pix * p.ldr + n_idx * BN;
-        } else if (p.res_mode == 1) {
-          const long long rp = ((long long)n * (p.H >> 1) + ((y0 + yi) >> 1)) * (p.W >> 1) + ((x0 + xi) >> 1);
-          rrow = p.residual + rp * p.ldr + n_idx * BN;
-        } else {
-          const long long rp = ((long long)n * (2 * p.H) + 2 * (y0 + yi)) * (2 * p.W) + 2 * (x0 + xi);
-          rrow = p.residual + rp * p.ldr + n_idx * BN;
-          r_dx = p.ldr;
-          r_dy = (long long)2 * p.W * p.ldr;
-        }
+        // same pixel, nearest-upsampled (x_upd of ResBlock(up=True), unet.py:240) or the 2x2 average of a twice-as-large map
+        // (ResBlock(down=True))
+        long long rp;
+        if (p.res_mode == 0) rp = ((long long)n * p.H + (y0 + yi)) * p.W + (x0 + xi);
+        else if (p.res_mode == 1) rp = ((long long)n * (p.H >> 1) + ((y0 + yi) >> 1)) * (p.W >> 1) + ((x0 + xi) >> 1);
+        else rp = ((long long)n * (2 * p.H) + 2 * (y0 + yi)) * (2 * p.W) + 2 * (x0 + xi);
+        t.rrow = p.residual + rp * p.ldr + t.n_idx * BN;
       }
-      const float* crow = p.chanadd ? p.chanadd + (long long)n * p.ca_ld + n_idx * BN : nullptr;
+      t.crow = p.chanadd ? p.chanadd + (long long)n * p.ca_ld + t.n_idx * BN : nullptr;
+    };
+    // residual columns [c0, c0 + 32) of a tile's row (zeros if there is none)
+    auto load_res = [&](const Tile& t, int c0, float (&rv)[32]) {
+      if (t.rrow != nullptr && t.valid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ldg_f32x8(t.rrow + c0 + 8 * j, &rv[8 * j]);
+        if (p.res_mode == 2) {
+          const long long r_dx = p.ldr, r_dy = (long long)2 * p.W * p.ldr;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float q1[8], q2[8], q3[8];
+            ldg_f32x8(t.rrow + r_dx + c0 + 8 * j, q1);
+            ldg_f32x8(t.rrow + r_dy + c0 + 8 * j, q2);
+            ldg_f32x8(t.rrow + r_dy + r_dx + c0 + 8 * j, q3);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rv[8 * j + i] = ((rv[8 * j + i] + q1[i]) + (q2[i] + q3[i])) * 0.25f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rv[j] = 0.f;
+      }
+    };
+    Tile cur, nxt;
+    float rvn[32];   // residual of the NEXT chunk to be processed, in flight
+    if (unit_begin < unit_end) {
+      setup(unit_begin, cur);
+      load_res(cur, chalf * CW, rvn);
+    }
+    for (int u = unit_begin; u < unit_end; u += unit_step) {
+      const bool has_next = u + unit_step < unit_end;
+      if (has_next) setup(u + unit_step, nxt);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * Cfg::ACC_COLS;
-      const bool dual_sum = DUAL && p.terms != 1;
-#pragma unroll 1
-      for (int c0 = chalf * CW; c0 < (chalf + 1) * CW; c0 += 32) {
-        // operands of the epilogue first (all loads in flight together, none ordered behind a store), then the accumulators
-        float4 cv[8], rv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          cv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (valid) {
-          if (crow) {
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int c0 = chalf * CW + ch * 32;
+        float rv[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cv[j] = __ldg(reinterpret_cast<const float4*>(crow + c0 + 4 * j));
-          }
-          if (rrow) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rv[j] = *reinterpret_cast<const float4*>(rrow + c0 + 4 * j);
-            if (p.res_mode == 2) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 q1 = *reinterpret_cast<const float4*>(rrow + r_dx + c0 + 4 * j);
-                const float4 q2 = *reinterpret_cast<const float4*>(rrow + r_dy + c0 + 4 * j);
-                const float4 q3 = *reinterpret_cast<const float4*>(rrow + r_dy + r_dx + c0 + 4 * j);
-                rv[j].x = ((rv[j].x + q1.x) + (q2.x + q3.x)) * 0.25f;
-                rv[j].y = ((rv[j].y + q1.y) + (q2.y + q3.y)) * 0.25f;
-                rv[j].z = ((rv[j].z + q1.z) + (q2.z + q3.z)) * 0.25f;
-                rv[j].w = ((rv[j].w + q1.w) + (q2.w + q3.w)) * 0.25f;
-              }
-            }
-          }
-        }
-        uint32_t v[32];
+        for (int j = 0; j < 32; ++j) rv[j] = rvn[j];
+        uint32_t v[32], v2[32];
         tmem_ld32(t0 + c0, v);
+        if (dual_sum) tmem_ld32(t0 + BN + c0, v2);   // the hi*lo partial sums kept in the stage's second half
+        if (ch + 1 < NCH) load_res(cur, c0 + 32, rvn);
+        else if (has_next) load_res(nxt, chalf * CW, rvn);
         tmem_ld_wait();
-        if (dual_sum) {   // add the hi*lo partial sums kept in the stage's second half
-          uint32_t v2[32];
-          tmem_ld32(t0 + BN + c0, v2);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        if (ch == NCH - 1) {
+          // every accumulator column this warp owns is in registers: hand the TMEM stage back before the arithmetic and the stores
+          tc_fence_before();
+          if (PAIR) mbar_arrive_leader(tempty_bar(acc));
+          else mbar_arrive(tempty_bar(acc));
         }
         float ov[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float4 o;
-          o.x = p.alpha * __uint_as_float(v[4 * j + 0]) + cv[j].x + rv[j].x;
-          o.y = p.alpha * __uint_as_float(v[4 * j + 1]) + cv[j].y + rv[j].y;
-          o.z = p.alpha * __uint_as_float(v[4 * j + 2]) + cv[j].z + rv[j].z;
-          o.w = p.alpha * __uint_as_float(v[4 * j + 3]) + cv[j].w + rv[j].w;
-          if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
-          ov[4 * j + 0] = o.x; ov[4 * j + 1] = o.y; ov[4 * j + 2] = o.z; ov[4 * j + 3] = o.w;
+          const float4 cv = cur.crow ? __ldg(reinterpret_cast<const float4*>(cur.crow + c0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float a0 = __uint_as_float(v[4 * j + 0]), a1 = __uint_as_float(v[4 * j + 1]);
+          float a2 = __uint_as_float(v[4 * j + 2]), a3 = __uint_as_float(v[4 * j + 3]);
+          if (dual_sum) {
+            a0 += __uint_as_float(v2[4 * j + 0]);
+            a1 += __uint_as_float(v2[4 * j + 1]);
+            a2 += __uint_as_float(v2[4 * j + 2]);
+            a3 += __uint_as_float(v2[4 * j + 3]);
+          }
+          ov[4 * j + 0] = cur.valid ? p.alpha * a0 + cv.x + rv[4 * j + 0] : 0.f;
+          ov[4 * j + 1] = cur.valid ? p.alpha * a1 + cv.y + rv[4 * j + 1] : 0.f;
+          ov[4 * j + 2] = cur.valid ? p.alpha * a2 + cv.z + rv[4 * j + 2] : 0.f;
+          ov[4 * j + 3] = cur.valid ? p.alpha * a3 + cv.w + rv[4 * j + 3] : 0.f;
         }
-        if (valid) {
+        if (cur.valid) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(orow + c0 + 4 * j) = make_float4(ov[4 * j], ov[4 * j + 1], ov[4 * j + 2], ov[4 * j + 3]);
+          for (int j = 0; j < 4; ++j) stg_f32x8(cur.orow + c0 + 8 * j, &ov[8 * j]);
         }
         if (p.stats) {
           // GroupNorm statistics of the tile: transpose-reduce the 32 rows x 32 columns this warp holds so that lane L
@@ -390,26 +409,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
               sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, k);
             }
           }
-          two_sum_acc(run_s[(c0 - chalf * CW) >> 5], cmp_s[(c0 - chalf * CW) >> 5], ov[0]);
-          two_sum_acc(run_q[(c0 - chalf * CW) >> 5], cmp_q[(c0 - chalf * CW) >> 5], sq[0]);
+          two_sum_acc(run_s[ch], cmp_s[ch], ov[0]);
+          two_sum_acc(run_q[ch], cmp_q[ch], sq[0]);
         }
       }
       if (p.stats) {
         // the warp's 32 rows lie in one image (>= 32 pixels per image): keep running sums while consecutive tiles stay in
         // the same image / channel block (the tile -> CTA map is static, so these fp32 partial sums are the same every run),
         // flush with one order-independent fixed-point add pair per column otherwise
-        const int img_w = n0 + (ew * 32) / (p.bw * p.bh);
-        int next_img = -1, next_nidx = -1;
-        if (u + unit_step < unit_end) {
-          int nx0, ny0, nn0;
-          decode(tile_of(u + unit_step), next_nidx, nx0, ny0, nn0);
-          next_img = nn0 + (ew * 32) / (p.bw * p.bh);
-        }
-        if (next_img != img_w || next_nidx != n_idx) {
-          if (img_w < p.N) {
+        if (!has_next || nxt.img_w != cur.img_w || nxt.n_idx != cur.n_idx) {
+          if (cur.img_w < p.N) {
 #pragma unroll
-            for (int ch = 0; ch < CW / 32; ++ch) {
-              StatAcc* d = p.stats + ((size_t)img_w * p.st_ld + n_idx * BN + chalf * CW + ch * 32 + lane) * 2;
+            for (int ch = 0; ch < NCH; ++ch) {
+              StatAcc* d = p.stats + ((size_t)cur.img_w * p.st_ld + cur.n_idx * BN + chalf * CW + ch * 32 + lane) * 2;
               stat_add(d, run_s[ch]);        // integer accumulation: the total is independent of the arrival order
               stat_add(d, cmp_s[ch]);
               stat_add(d + 1, run_q[ch]);
@@ -417,7 +429,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
             }
           }
 #pragma unroll
-          for (int ch = 0; ch < CW / 32; ++ch) {
+          for (int ch = 0; ch < NCH; ++ch) {
             run_s[ch] = 0.f;
             run_q[ch] = 0.f;
             cmp_s[ch] = 0.f;
@@ -425,9 +437,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
           }
         }
       }
-      tc_fence_before();
-      if (PAIR) mbar_arrive_leader(tempty_bar(acc));
-      else mbar_arrive(tempty_bar(acc));
+      cur = nxt;
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -597,12 +607,12 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   }
   p.Cout = Cout; p.ldc = out.ld; p.out = out.p;
   p.out_sx = out.ld; p.out_sy = (long long)out.W * out.ld; p.out_sn = (long long)out.H * out.W * out.ld;
-  DDNM_CHECK(out.C == Cout && out.ld % 4 == 0 && ((uintptr_t)out.p & 15) == 0, "output view misaligned");
+  DDNM_CHECK(out.C == Cout && out.ld % 8 == 0 && ((uintptr_t)out.p & 31) == 0, "output view misaligned (rows move as 32-byte vectors)");
   p.chanadd = chanadd; p.ca_ld = ca_ld; p.residual = residual; p.ldr = ldr; p.alpha = alpha; p.res_mode = res_mode;
   p.stats = out.st; p.st_ld = out.st_ld;
   p.terms = g_terms;
   if (out.st) DDNM_CHECK(p.bw * p.bh >= 32, "GroupNorm statistics need >= 32 pixels per image");
-  if (residual) DDNM_CHECK(ldr % 4 == 0 && ((uintptr_t)residual & 15) == 0, "residual misaligned");
+  if (residual) DDNM_CHECK(ldr % 8 == 0 && ((uintptr_t)residual & 31) == 0, "residual misaligned (rows move as 32-byte vectors)");
   // UMMA shared-memory descriptor, high word: SBO = 1024 B (8 rows x 128 B) >> 4 at bits [32,46), version = 1 at
   // [46,48), layout SWIZZLE_128B (= 2) at [61,64).  (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
   p.desc_hi = g_desc_hi_override ? g_desc_hi_override : (64u | (1u << 14) | (2u << 29));
@@ -681,7 +691,7 @@ TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, 
   p.b_batched = 2;
   p.Cout = N; p.ldc = (int)out_sx; p.out = out;
   p.out_sn = out_sn; p.out_sy = out_sy; p.out_sx = out_sx;
-  DDNM_CHECK(out_sx % 4 == 0 && out_sy % 4 == 0 && out_sn % 4 == 0 && ((uintptr_t)out & 15) == 0, "attention GEMM output misaligned");
+  DDNM_CHECK(out_sx % 8 == 0 && out_sy % 8 == 0 && out_sn % 8 == 0 && ((uintptr_t)out & 31) == 0, "attention GEMM output misaligned");
   p.chanadd = nullptr; p.ca_ld = 0; p.residual = nullptr; p.ldr = 0; p.res_mode = 0; p.alpha = alpha;
   p.stats = nullptr; p.st_ld = 0;
   p.terms = g_terms;

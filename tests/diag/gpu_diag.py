@@ -13,6 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from ddnm_b200 import _lib  # noqa: E402
 
+if os.environ.get("DDNM_DIAG_LIB"):      # A/B runs of two builds on one box: point the binding at another .so before it loads
+    _lib.LIB_PATH = os.path.abspath(os.environ["DDNM_DIAG_LIB"])
+
 L = _lib.lib()
 dev = "cuda"
 
