@@ -21,9 +21,12 @@
 //   <128, true, true>   PAIR + DUAL: 256 x 256 A_hi x [B_hi; B_lo] with the two planes held by the two CTAs + 256 x 128 A_lo x B_hi.
 #include "tc_gemm.cuh"
 
+#include <type_traits>
+
 namespace ddnm {
 
 static constexpr int BM = 128;
+static constexpr int kTcThreads = 320;
 static constexpr int BK = 64;                      // fp16 elements = 128 bytes = one swizzle row
 static constexpr int A_PLANE_BYTES = BM * BK * 2;  // 16 KiB
 
@@ -46,14 +49,18 @@ struct TcCfg {
   static constexpr int BY_BYTES = PD ? (BN / 2) * BK * 2 : B_PLANE_BYTES;
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + BX_BYTES + BY_BYTES;
   static constexpr int STAGES = STAGE_BYTES <= 56 * 1024 ? 4 : (STAGE_BYTES <= 64 * 1024 ? 3 : 2);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // the epilogue's cross-warp combine buffer for the GroupNorm sums: 8 warps x BN/2 columns x float4; the PAIR + DUAL form has no
+  // room for it (4 x 56 KiB stages) and does not need it (contiguous tile ranges: one flush per CTA)
+  static constexpr bool COMBINE = !PD;
+  static constexpr int COMBINE_BYTES = COMBINE ? 8 * (BN / 2) * 16 : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COMBINE_BYTES;
   static constexpr int ACC_COLS = DUAL ? 2 * BN : BN;    // TMEM columns of one accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static_assert(TMEM_COLS <= 512 && SMEM_BYTES <= 227 * 1024, "TMEM / shared memory capacity");
 };
 
 template <int BN, bool PAIR, bool DUAL>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant__ CUtensorMap tm_a0l,
                const __grid_constant__ CUtensorMap tm_a1h, const __grid_constant__ CUtensorMap tm_a1l,
                const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bl,
@@ -341,11 +348,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
         for (int j = 0; j < 32; ++j) rv[j] = 0.f;
       }
     };
+    // the tile loop, compiled twice: with a residual (its rows are requested one chunk ahead and live in 2 x 32 registers) and
+    // without (no such registers, no additions of zeros)
+    auto tile_loop = [&](auto res_tag) {
+    constexpr bool HAS_RES = decltype(res_tag)::value;
     Tile cur, nxt;
-    float rvn[32];   // residual of the NEXT chunk to be processed, in flight
+    float rvn[HAS_RES ? 32 : 1];   // residual of the NEXT chunk to be processed, in flight
     if (unit_begin < unit_end) {
       setup(unit_begin, cur);
-      load_res(cur, chalf * CW, rvn);
+      if constexpr (HAS_RES) load_res(cur, chalf * CW, rvn);
     }
     for (int u = unit_begin; u < unit_end; u += unit_step) {
       const bool has_next = u + unit_step < unit_end;
@@ -356,14 +367,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         const int c0 = chalf * CW + ch * 32;
-        float rv[32];
+        float rv[HAS_RES ? 32 : 1];
+        if constexpr (HAS_RES) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) rv[j] = rvn[j];
+          for (int j = 0; j < 32; ++j) rv[j] = rvn[j];
+        }
         uint32_t v[32], v2[32];
         tmem_ld32(t0 + c0, v);
         if (dual_sum) tmem_ld32(t0 + BN + c0, v2);   // the hi*lo partial sums kept in the stage's second half
-        if (ch + 1 < NCH) load_res(cur, c0 + 32, rvn);
-        else if (has_next) load_res(nxt, chalf * CW, rvn);
+        if constexpr (HAS_RES) {
+          if (ch + 1 < NCH) load_res(cur, c0 + 32, rvn);
+          else if (has_next) load_res(nxt, chalf * CW, rvn);
+        }
         tmem_ld_wait();
         if (ch == NCH - 1) {
           // every accumulator column this warp owns is in registers: hand the TMEM stage back before the arithmetic and the stores
@@ -383,10 +398,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
             a2 += __uint_as_float(v2[4 * j + 2]);
             a3 += __uint_as_float(v2[4 * j + 3]);
           }
-          ov[4 * j + 0] = cur.valid ? p.alpha * a0 + cv.x + rv[4 * j + 0] : 0.f;
-          ov[4 * j + 1] = cur.valid ? p.alpha * a1 + cv.y + rv[4 * j + 1] : 0.f;
-          ov[4 * j + 2] = cur.valid ? p.alpha * a2 + cv.z + rv[4 * j + 2] : 0.f;
-          ov[4 * j + 3] = cur.valid ? p.alpha * a3 + cv.w + rv[4 * j + 3] : 0.f;
+          ov[4 * j + 0] = cur.valid ? p.alpha * a0 + cv.x + (HAS_RES ? rv[4 * j + 0] : 0.f) : 0.f;
+          ov[4 * j + 1] = cur.valid ? p.alpha * a1 + cv.y + (HAS_RES ? rv[4 * j + 1] : 0.f) : 0.f;
+          ov[4 * j + 2] = cur.valid ? p.alpha * a2 + cv.z + (HAS_RES ? rv[4 * j + 2] : 0.f) : 0.f;
+          ov[4 * j + 3] = cur.valid ? p.alpha * a3 + cv.w + (HAS_RES ? rv[4 * j + 3] : 0.f) : 0.f;
         }
         if (cur.valid) {
 #pragma unroll
@@ -418,7 +433,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
         // the same image / channel block (the tile -> CTA map is static, so these fp32 partial sums are the same every run),
         // flush with one order-independent fixed-point add pair per column otherwise
         if (!has_next || nxt.img_w != cur.img_w || nxt.n_idx != cur.n_idx) {
-          if (cur.img_w < p.N) {
+          if constexpr (Cfg::COMBINE) {
+            // the warps of this column half whose rows lie in the same image (4, or 2 on 8x8 maps) first add their sums in shared
+            // memory, in a fixed order: 4x fewer same-address reductions reach L2 (with several N tiles the round-robin tile order
+            // changes image or channel block at every tile, so this runs once per tile)
+            const int wpi = min(4, (p.bw * p.bh) >> 5);          // warps per image
+            const int pos = ew % wpi, first = ew - pos;
+            float4* cb = reinterpret_cast<float4*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw))) + (size_t)chalf * 4 * CW;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) cb[ew * CW + ch * 32 + lane] = make_float4(run_s[ch], cmp_s[ch], run_q[ch], cmp_q[ch]);
+            named_bar_sync(1 + chalf, 128);
+            if (cur.img_w < p.N) {
+              for (int slot = pos * 32 + lane; slot < 2 * CW; slot += wpi * 32) {
+                const int which = slot >= CW ? 1 : 0, col = slot - which * CW;
+                float sum = 0.f, comp = 0.f;
+                for (int w = 0; w < wpi; ++w) {
+                  const float4 t = cb[(first + w) * CW + col];
+                  two_sum_acc(sum, comp, which ? t.z : t.x);
+                  two_sum_acc(sum, comp, which ? t.w : t.y);
+                }
+                stat_add(p.stats + ((size_t)cur.img_w * p.st_ld + cur.n_idx * BN + chalf * CW + col) * 2 + which, sum + comp);
+              }
+            }
+            named_bar_sync(1 + chalf, 128);
+          } else if (cur.img_w < p.N) {
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
               StatAcc* d = p.stats + ((size_t)cur.img_w * p.st_ld + cur.n_idx * BN + chalf * CW + ch * 32 + lane) * 2;
@@ -441,6 +479,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
     }
+    };
+    if (p.residual) tile_loop(std::true_type{});
+    else tile_loop(std::false_type{});
   }
 
   tc_fence_before();
@@ -721,7 +762,7 @@ static void launch_bn(const TcLaunch& L, cudaStream_t stream) {
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set))
     CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, PAIR, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  launch_pdl(conv_tc_kernel<BN, PAIR, DUAL>, dim3(L.grid), dim3(320), (size_t)Cfg::SMEM_BYTES, stream, PAIR ? 2 : 1, L.a0h, L.a0l, L.a1h, L.a1l,
+  launch_pdl(conv_tc_kernel<BN, PAIR, DUAL>, dim3(L.grid), dim3(kTcThreads), (size_t)Cfg::SMEM_BYTES, stream, PAIR ? 2 : 1, L.a0h, L.a0l, L.a1h, L.a1l,
              L.bh, L.bl, L.b2, L.p);
   CUDA_CHECK(cudaGetLastError());
 }

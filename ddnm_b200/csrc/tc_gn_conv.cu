@@ -54,7 +54,6 @@ struct GnCfg {
 };
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 // arrive (release, cluster scope) on the LEADER CTA's copy of a barrier: the transform warps of both CTAs publish their operand rows
 __device__ __forceinline__ void mbar_arrive_leader_release(uint32_t bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
