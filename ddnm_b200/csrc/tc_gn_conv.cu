@@ -134,9 +134,12 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
   const int total_tiles = m_tiles * p.n_tiles;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int unit_begin = (int)cluster_id_x();
-  const int unit_end = total_tiles / 2;
-  const int unit_step = (int)(gridDim.x / 2);
+  // p.deal: one contiguous range of tile pairs per cluster (consecutive rows of one image: the output's GroupNorm sums are
+  // flushed once or twice per CTA, the coefficient table is rebuilt as rarely) instead of the round-robin order
+  const int n_units = total_tiles / 2, n_workers = (int)(gridDim.x / 2), worker = (int)cluster_id_x();
+  const int unit_begin = p.deal ? (int)((long long)worker * n_units / n_workers) : worker;
+  const int unit_end = p.deal ? (int)((long long)(worker + 1) * n_units / n_workers) : n_units;
+  const int unit_step = p.deal ? 1 : n_workers;
   auto tile_of = [&](int u) {
     const int mp = u / p.n_tiles;
     return (2 * mp + (int)rank) * p.n_tiles + (u - mp * p.n_tiles);
@@ -292,11 +295,13 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
     const int ew = warp & 3;                 // TMEM lane quarter this warp may read
     const int r = ew * 32 + lane;            // pixel of the tile
     uint32_t acc = 0, acc_phase = 0;
-    float run_s[BN / 32], run_q[BN / 32];
+    float run_s[BN / 32], run_q[BN / 32], cmp_s[BN / 32], cmp_q[BN / 32];   // (value, compensation) pairs: see conv_tc_kernel
 #pragma unroll
     for (int ch = 0; ch < BN / 32; ++ch) {
       run_s[ch] = 0.f;
       run_q[ch] = 0.f;
+      cmp_s[ch] = 0.f;
+      cmp_q[ch] = 0.f;
     }
     for (int u = unit_begin; u < unit_end; u += unit_step) {
       int n_idx, x0, y, n;
@@ -354,8 +359,8 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
               sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, k);
             }
           }
-          run_s[c0 >> 5] += ov[0];
-          run_q[c0 >> 5] += sq[0];
+          two_sum_acc(run_s[c0 >> 5], cmp_s[c0 >> 5], ov[0]);
+          two_sum_acc(run_q[c0 >> 5], cmp_q[c0 >> 5], sq[0]);
         }
       }
       if (p.stats) {
@@ -371,9 +376,13 @@ conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_consta
           for (int ch = 0; ch < BN / 32; ++ch) {
             StatAcc* d = p.stats + ((size_t)n * p.st_ld + n_idx * BN + ch * 32 + lane) * 2;
             stat_add(d, run_s[ch]);
+            stat_add(d, cmp_s[ch]);
             stat_add(d + 1, run_q[ch]);
+            stat_add(d + 1, cmp_q[ch]);
             run_s[ch] = 0.f;
             run_q[ch] = 0.f;
+            cmp_s[ch] = 0.f;
+            cmp_q[ch] = 0.f;
           }
         }
       }
@@ -608,6 +617,7 @@ TcGnLaunch tc_make_gn_launch(const View& x, const GnAffine& gn, const View* side
   L.b2 = pd ? tc_make_weight_map(w_hi, Ktot, Cout, L.BN / 2) : L.bh;
   const int total = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
   L.grid = 2 * std::min(total / 2, num_sms / 2);
+  p.deal = (p.n_tiles == 1 && total / 2 >= L.grid) ? 1 : 0;
   L.flops = 2.0 * (double)out.pixels() * Cout * Ktot;
   return L;
 }
