@@ -271,8 +271,7 @@ void UNetEngine::emit_stem(const std::string& wname, const View& out) {
   const int cin = in_ch_;
   add_op("stem", "stem", 2.0 * B_ * R_ * R_ * (double)out.C * cin * 9, (double)B_ * R_ * R_ * (cin + out.C) * 4,
          [=](cudaStream_t s) { conv3x3_small_cin(xin, cin, w, b, out, s); });
-  // the only GroupNorm input not written by the tensor-core kernel: reduce it separately
-  add_op("stem.gn_stats", "gn_stats", 0, (double)out.pixels() * out.C * 4, [=](cudaStream_t s) { gn_stats(out, s); });
+  // (the GroupNorm sums of the stem output are accumulated by the stem kernel itself: out.st)
 }
 
 // network head: GroupNorm + SiLU + 3x3 conv to out_ch (3 or 6), NCHW result.  The convolution runs on the tensor cores with

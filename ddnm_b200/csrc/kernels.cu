@@ -281,11 +281,12 @@ void gn_apply_f32(const View& x, int groups, const float* gamma, const float* be
 template <int CIN>
 __global__ void __launch_bounds__(256) conv_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ out,
-                                                             int H, int W, int Cout, int ld) {
+                                                             int H, int W, int Cout, int ld, StatAcc* __restrict__ stats, int st_ld) {
   pdl_prologue();
   constexpr int KT = CIN * 9;
   constexpr int TW = 64, TH = 8;  // output tile per CTA: one warp per row
   __shared__ float tile[CIN][TH + 2][TW + 2];
+  __shared__ float red[TH][128][2];   // per-row channel sums of the tile (GroupNorm statistics of the output, when asked for)
   const int slabs = (Cout + 127) / 128;
   const int n = blockIdx.z / slabs;
   const int slab = blockIdx.z % slabs;
@@ -311,9 +312,9 @@ __global__ void __launch_bounds__(256) conv_small_cin_kernel(const float* __rest
   }
   __syncthreads();
   const int y = y0 + warp;
-  if (!active || y >= H) return;
+  float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
   float* orow = out + (((size_t)n * H + y) * W + x0) * ld + co;
-  for (int px = 0; px < TW && x0 + px < W; ++px) {
+  for (int px = 0; active && y < H && px < TW && x0 + px < W; ++px) {
     float acc[4] = {b4[0], b4[1], b4[2], b4[3]};
 #pragma unroll
     for (int c = 0; c < CIN; ++c)
@@ -327,6 +328,26 @@ __global__ void __launch_bounds__(256) conv_small_cin_kernel(const float* __rest
           for (int j = 0; j < 4; ++j) acc[j] = fmaf(v, wr[k][j], acc[j]);
         }
     *reinterpret_cast<float4*>(orow + (size_t)px * ld) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s4[j] += acc[j];
+      q4[j] = fmaf(acc[j], acc[j], q4[j]);
+    }
+  }
+  if (stats == nullptr) return;
+  // the tile's per-channel sums: rows (warps) combined in a fixed order, then one order-independent fixed-point add per statistic
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[warp][lane * 4 + j][0] = s4[j];
+    red[warp][lane * 4 + j][1] = q4[j];
+  }
+  __syncthreads();
+  const int c = threadIdx.x & 127, which = threadIdx.x >> 7;
+  if (slab * 128 + c < Cout) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < TH; ++r) t += red[r][c][which];
+    stat_add(stats + ((size_t)n * st_ld + slab * 128 + c) * 2 + which, t);
   }
 }
 
@@ -334,7 +355,8 @@ void conv3x3_small_cin(const float* x, int Cin, const float* w, const float* bia
   DDNM_CHECK(Cin == 3, "stem convolution expects 3 input channels");
   DDNM_CHECK(out.C % 4 == 0, "stem Cout % 4");
   dim3 grid(cdiv(out.W, 64), cdiv(out.H, 8), out.N * cdiv(out.C, 128));
-  launch_pdl(conv_small_cin_kernel<3>, grid, dim3(256), 0, st, 1, x, w, bias, out.p, out.H, out.W, out.C, out.ld);
+  // the GroupNorm sums of the output come out of the same pass when the view carries accumulators
+  launch_pdl(conv_small_cin_kernel<3>, grid, dim3(256), 0, st, 1, x, w, bias, out.p, out.H, out.W, out.C, out.ld, out.st, out.st_ld);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -344,7 +366,7 @@ void conv3x3_small_cin(const float* x, int Cin, const float* w, const float* bia
 // The activations (N x K, act_in applied once) are staged in shared memory; each warp then produces LIN_OPW output features,
 // reading each weight row exactly once with 16-byte loads and reusing it for every image of the batch.
 constexpr int LIN_NB = 16;    // images per accumulator pass
-constexpr int LIN_OPW = 8;    // output features per warp
+constexpr int LIN_OPW = 2;    // output features per warp (8 left a 512-feature layer with 8 CTAs: 40-50 us of pure latency each)
 constexpr int LIN_WREG = 8;   // float4 weight registers per lane loaded ahead (K <= 1024 in one go)
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, int N, int K, const float* __restrict__ W,
                                                      const float* __restrict__ bias, int O, float* __restrict__ out, int ldo,
@@ -460,31 +482,32 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float a
                                                     long long sb, long long sb2, float* __restrict__ C, int ldc, long long sc,
                                                     long long sc2, int inner_n) {
   pdl_prologue();
-  __shared__ float As[16][64 + 4], Bs[16][64 + 4];
+  constexpr int SK = 32;   // k depth of a shared-memory tile
+  __shared__ float As[SK][64 + 4], Bs[SK][64 + 4];
   const int bo = blockIdx.z / inner_n, bi = blockIdx.z % inner_n;
   A += bo * sa + bi * sa2; B += bo * sb + bi * sb2; C += bo * sc + bi * sc2;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-      const int kk = i % 16, mm = i / 16;
+  for (int k0 = 0; k0 < K; k0 += SK) {
+    for (int i = threadIdx.x; i < 64 * SK; i += 256) {
+      const int kk = i % SK, mm = i / SK;
       As[kk][mm] = (m0 + mm < M && k0 + kk < K) ? A[(long long)(m0 + mm) * lda + k0 + kk] : 0.f;
     }
     if (BT) {
-      for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-        const int kk = i % 16, nn = i / 16;
+      for (int i = threadIdx.x; i < 64 * SK; i += 256) {
+        const int kk = i % SK, nn = i / SK;
         Bs[kk][nn] = (n0 + nn < N && k0 + kk < K) ? B[(long long)(n0 + nn) * ldb + k0 + kk] : 0.f;
       }
     } else {
-      for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      for (int i = threadIdx.x; i < 64 * SK; i += 256) {
         const int nn = i % 64, kk = i / 64;
         Bs[kk][nn] = (n0 + nn < N && k0 + kk < K) ? B[(long long)(k0 + kk) * ldb + n0 + nn] : 0.f;
       }
     }
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
+    for (int kk = 0; kk < SK; ++kk) {
       float a[4], bb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
