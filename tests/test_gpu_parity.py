@@ -310,8 +310,9 @@ def test_unet_fast_fp16_mode_is_close_but_flagged_non_parity(gold):
 
 
 def test_unet_forward_is_bit_reproducible():
-    """GroupNorm sums are accumulated by many CTAs with atomics; they are 128-bit fixed-point integer accumulators (StatAcc), so
-    the arrival order cannot change the result: every replay of a forward is bit-identical (eager and CUDA-graph alike)."""
+    """GroupNorm sums are accumulated by many CTAs with atomics; they are fixed-point integer accumulators (StatAcc: two carry-free
+    64-bit words, 48 fractional bits), so the arrival order cannot change the result: every replay of a forward is bit-identical
+    (eager and CUDA-graph alike)."""
     cfg = U.SimpleUNetConfig.celeba_hq()
     torch.manual_seed(17)
     x = torch.randn(2, 3, 256, 256, device=dev)
@@ -328,6 +329,26 @@ def test_unet_forward_is_bit_reproducible():
     first = m(x, t).clone()
     for _ in range(5):
         assert torch.equal(m(x, t), first)
+
+
+def test_unet_tile_order_does_not_change_the_result():
+    """The tile -> CTA map of the convolutions (round-robin, or one contiguous range per CTA on the layers where that saves the
+    per-tile flush of the GroupNorm sums) only regroups fp32 partial sums: the forward agrees to fp32 rounding of the statistics."""
+    from ddnm_b200 import _lib
+    cfg = U.SimpleUNetConfig.celeba_hq()
+    torch.manual_seed(23)
+    x = torch.randn(2, 3, 256, 256, device=dev)
+    t = torch.tensor([612.0, 87.0], device=dev)
+    outs = []
+    try:
+        for mode in (0, -1):
+            _lib.check(_lib.lib().ddnm_tc_debug_deal(mode))
+            outs.append(_engine_model(cfg)(x, t).clone())
+    finally:
+        _lib.check(_lib.lib().ddnm_tc_debug_deal(-1))
+    scale = outs[0].abs().max().item()
+    err = (outs[0] - outs[1]).abs().max().item()
+    assert err <= 2e-5 * scale, (err, scale)
 
 
 def test_unet_batch_rows_independent():
