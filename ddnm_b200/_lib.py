@@ -100,6 +100,7 @@ _SIGS = {
     "ddnm_tc_debug_override": (C.c_int, [C.c_uint, C.c_uint]),
     "ddnm_tc_debug_force_bn": (C.c_int, [_I]),
     "ddnm_tc_debug_deal": (C.c_int, [_I]),
+    "ddnm_tc_debug_halo": (C.c_int, [_I]),
     "ddnm_tc_debug_pair_dual": (C.c_int, [_I]),
     "ddnm_tc_debug_dual_mode": (C.c_int, [_I]),
     "ddnm_tc_debug_pair_mode": (C.c_int, [_I]),

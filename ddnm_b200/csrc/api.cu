@@ -385,6 +385,11 @@ int ddnm_tc_debug_pair_dual(int on) {
   tc_debug_pair_dual(on);
   DDNM_API_END
 }
+int ddnm_tc_debug_halo(int on) {
+  DDNM_API_BEGIN
+  tc_debug_halo(on);
+  DDNM_API_END
+}
 int ddnm_tc_debug_deal(int mode) {
   DDNM_API_BEGIN
   tc_debug_deal(mode);

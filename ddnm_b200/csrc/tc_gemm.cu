@@ -21,6 +21,7 @@
 //   <128, true, true>   PAIR + DUAL: 256 x 256 A_hi x [B_hi; B_lo] with the two planes held by the two CTAs + 256 x 128 A_lo x B_hi.
 #include "tc_gemm.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace ddnm {
@@ -38,7 +39,13 @@ static constexpr int A_PLANE_BYTES = BM * BK * 2;  // 16 KiB
 // It lets hi*hi and hi*lo ride ONE N = 2*BN instruction (the hi and lo planes of the B tile are adjacent in shared memory, so
 // a single descriptor spans both): per 16-deep k-step the A_hi rows are read once instead of twice and 2 instructions are
 // issued instead of 3.
-template <int BN, bool PAIR, bool DUAL = false>
+// HALO (pairs, 3x3 stride 1 on rows >= 128 pixels wide): the A operand is staged ONCE per (64-channel slice, row offset dy) as a
+// halo row of 130 pixels (x0-1 .. x0+128) and feeds the three taps dx = -1, 0, +1 through UMMA descriptors whose start address is
+// shifted by one 128-byte operand row per tap (the hardware applies the 128B swizzle to the absolute address, so a shifted start
+// reads the right bytes: verified on the B200, profiles/r02_gn_fused_desc_mode.log).  The L2 -> shared-memory fill of A drops
+// 3x (it is 57 % of the 16.9 GB a 256 -> 128 layer pulls through the crossbar per launch, profiles/r02_forward_speedup.md).  A and B
+// then live in separate rings: A units of {hi, lo} x 136 rows, B stages of one tap's weights.
+template <int BN, bool PAIR, bool DUAL = false, bool HALO = false>
 struct TcCfg {
   static constexpr bool PD = PAIR && DUAL;                // both: see conv_tc_kernel's "PAIR + DUAL" note
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;       // B rows staged by one CTA (plain PAIR)
@@ -53,14 +60,20 @@ struct TcCfg {
   // room for it (4 x 56 KiB stages) and does not need it (contiguous tile ranges: one flush per CTA)
   static constexpr bool COMBINE = !PD;
   static constexpr int COMBINE_BYTES = COMBINE ? 8 * (BN / 2) * 16 : 0;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COMBINE_BYTES;
+  static constexpr int HA_PLANE = 136 * 128;              // 130 halo rows padded to 17 KiB (keeps the 1024-byte swizzle alignment)
+  static constexpr int HA_UNIT = 2 * HA_PLANE;            // hi + lo
+  static constexpr int HA_NA = 3;                         // A ring depth (units)
+  static constexpr int HB_STAGE = BX_BYTES + BY_BYTES;
+  static constexpr int HB_NB = PD ? 4 : 3;                // B ring depth (tap stages)
+  static constexpr int RING_BYTES = HALO ? HA_NA * HA_UNIT + HB_NB * HB_STAGE : STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COMBINE_BYTES;
   static constexpr int ACC_COLS = DUAL ? 2 * BN : BN;    // TMEM columns of one accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static_assert(TMEM_COLS <= 512 && SMEM_BYTES <= 227 * 1024, "TMEM / shared memory capacity");
 };
 
-template <int BN, bool PAIR, bool DUAL>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int BN, bool PAIR, bool DUAL, bool HALO>
+__global__ void __launch_bounds__(HALO ? kTcThreads + 32 : kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant__ CUtensorMap tm_a0l,
                const __grid_constant__ CUtensorMap tm_a1h, const __grid_constant__ CUtensorMap tm_a1l,
                const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bl,
@@ -68,17 +81,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
   // PAIR + DUAL (BN = 128: the Cout = 128 layers): A_hi x [B_hi; B_lo] as ONE 256 x 256 cta_group::2 instruction — the leader's
   // smem supplies the B_hi plane (operand rows 0..127), the peer's the B_lo plane (rows 128..255) — then A_lo x B_hi as a 256 x 128
   // instruction whose B halves (B_hi rows 0..63 / 64..127) sit in a third region Y of the stage (tm_b2: B_hi with a BN/2-row box).
-  using Cfg = TcCfg<BN, PAIR, DUAL>;
+  static_assert(!HALO || PAIR, "the halo-row form exists for CTA pairs only");
+  using Cfg = TcCfg<BN, PAIR, DUAL, HALO>;
   constexpr bool PD = Cfg::PD;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int NA = Cfg::HA_NA, NB = Cfg::HB_NB;
+  constexpr int NBAR = HALO ? 2 * NA + 2 * NB : 2 * STAGES;   // ring barriers in front of the accumulator ones
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = smem_base + Cfg::RING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  // HALO: A ring at the base, B ring behind it
+  const uint32_t a_ring = smem_base, b_ring = smem_base + NA * Cfg::HA_UNIT;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (NA + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * NA + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * NA + NB + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (NBAR + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (NBAR + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (NBAR + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   pdl_prologue();
@@ -116,9 +138,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
       tma_prefetch_desc(&tm_a1h);
       tma_prefetch_desc(&tm_a1l);
     }
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < NBAR / 2; ++s) {   // full / empty pairs of the ring(s): one arrival each (expect_tx arrive / tcgen05.commit)
+      mbar_init(bar_base + 8u * (2 * s), 1);
+      mbar_init(bar_base + 8u * (2 * s + 1), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -157,6 +179,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
         if (PAIR) tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
         else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
       };
+      if constexpr (HALO) {
+        // weight (B) stages only: one per (unit, tap dx); the A halo rows come from warp 10
+        const int cb0 = p.cb0, upt = 3 * cb0 + p.kb1;
+        const uint32_t stage_tx = 2u * (uint32_t)Cfg::HB_STAGE;       // both CTAs' bytes land on the leader's barrier
+        for (int u = unit_begin; u < unit_end; u += unit_step) {
+          int n_idx, x0, y0, n0;
+          decode(tile_of(u), n_idx, x0, y0, n0);
+          for (int j = 0; j < upt; ++j) {
+            const bool side = j >= 3 * cb0;
+            const int c = side ? j - 3 * cb0 : j / 3;
+            const int dyi = side ? 0 : j - 3 * c;                     // 0..2 <-> dy = -1..1
+            const int ntap = side ? 1 : 3;
+            for (int dxi = 0; dxi < ntap; ++dxi) {
+              const int kb = side ? p.kb0 + c : ((dyi * 3 + dxi) * cb0 + c);
+              mbar_wait(b_empty(stage), phase ^ 1u);
+              const uint32_t sb = b_ring + stage * Cfg::HB_STAGE;
+              const uint32_t fb = b_full(stage);
+              if (leader) mbar_expect_tx(fb, stage_tx);
+              if (PD) {
+                tma_load_3d_pair(sb, rank == 0 ? &tm_bh : &tm_bl, fb, kb * BK, n_idx * BN, 0);
+                tma_load_3d_pair(sb + Cfg::BX_BYTES, &tm_b2, fb, kb * BK, n_idx * BN + (int)rank * (BN / 2), 0);
+              } else {
+                const int brow = n_idx * BN + (int)rank * Cfg::B_ROWS;
+                tma_load_3d_pair(sb, &tm_bh, fb, kb * BK, brow, 0);
+                tma_load_3d_pair(sb + Cfg::BX_BYTES, &tm_bl, fb, kb * BK, brow, 0);
+              }
+              if (++stage == (uint32_t)NB) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      } else {
       const uint32_t stage_tx = (PAIR ? 2u : 1u) * (uint32_t)(p.terms == 1 ? Cfg::STAGE_BYTES / 2 : Cfg::STAGE_BYTES);
       for (int u = unit_begin; u < unit_end; u += unit_step) {
         const int tile = tile_of(u);
@@ -212,11 +268,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
           }
         }
       }
+      }   // !HALO
+    }
+  } else if (HALO && warp == 10) {
+    // ------------------------------------------------ A halo-row producer (HALO) ----------------------------------
+    if constexpr (HALO) {
+      if (lane == 0) {
+        tma_prefetch_desc(&tm_a0h);
+        tma_prefetch_desc(&tm_a0l);
+        const int cb0 = p.cb0, upt = 3 * cb0 + p.kb1;
+        uint32_t ua = 0, aph = 0;
+        for (int u = unit_begin; u < unit_end; u += unit_step) {
+          int n_idx, x0, y0, n0;
+          decode(tile_of(u), n_idx, x0, y0, n0);
+          for (int j = 0; j < upt; ++j) {
+            const bool side = j >= 3 * cb0;
+            const int c = side ? j - 3 * cb0 : j / 3;
+            const int dyi = side ? 0 : j - 3 * c;
+            mbar_wait(a_empty(ua), aph ^ 1u);
+            const uint32_t sa = a_ring + ua * Cfg::HA_UNIT;
+            const uint32_t fb = a_full(ua);
+            // box bytes count in full even where the box hangs over the image (zero fill): 130 (main) / 128 (side) rows of 128 B,
+            // two planes, two CTAs
+            if (leader) mbar_expect_tx(fb, 4u * (uint32_t)(side ? 128 : 130) * 128u);
+            if (!side) {
+              // pixels x0-1 .. x0+128 of row y0 + dy -> operand rows 0..129; the conv's zero padding is the TMA out-of-bounds fill
+              tma_load_4d_pair(sa, &tm_a0h, fb, c * BK, x0 - 1, y0 + dyi - 1, n0);
+              tma_load_4d_pair(sa + Cfg::HA_PLANE, &tm_a0l, fb, c * BK, x0 - 1, y0 + dyi - 1, n0);
+            } else {
+              tma_load_4d_pair(sa, &tm_a1h, fb, c * BK, x0, y0, n0);
+              tma_load_4d_pair(sa + Cfg::HA_PLANE, &tm_a1l, fb, c * BK, x0, y0, n0);
+            }
+            if (++ua == (uint32_t)NA) {
+              ua = 0;
+              aph ^= 1u;
+            }
+          }
+        }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------ UMMA issuer -------------------------------------------------
     if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      uint32_t h_ua = 0, h_aph = 0;   // HALO: A ring position
       const uint64_t hi = (uint64_t)p.desc_hi << 32;
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
         if (PAIR) umma_f16_pair(d, a, b, p.idesc, accumulate);
@@ -232,6 +327,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
         // DUAL: instruction descriptor of the N = 2*BN product A_hi x [B_hi; B_lo]
         const uint32_t idesc_wide = (p.idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);
+        if constexpr (HALO) {
+          // `stage` / `phase` walk the B ring, ua / aph the A ring
+          const int cb0 = p.cb0, upt = 3 * cb0 + p.kb1;
+          bool first = true;
+          for (int j = 0; j < upt; ++j) {
+            const bool side = j >= 3 * cb0;
+            const int ntap = side ? 1 : 3;
+            mbar_wait(a_full(h_ua), h_aph);
+            tc_fence_after();
+            const uint32_t au = a_ring + h_ua * Cfg::HA_UNIT;
+            for (int dxi = 0; dxi < ntap; ++dxi) {
+              mbar_wait(b_full(stage), phase);
+              tc_fence_after();
+              // main units hold pixels x0-1 .. x0+128 in rows 0..129, tap dx reads rows dx+1 .. dx+128 (start address + dxi rows);
+              // side units hold pixels x0 .. x0+127 in rows 0..127
+              const uint32_t row_off = side ? 0u : (uint32_t)dxi * 128u;
+              const uint32_t ah = (((au + row_off) & 0x3FFFFu) >> 4) | (1u << 16);
+              const uint32_t al = (((au + Cfg::HA_PLANE + row_off) & 0x3FFFFu) >> 4) | (1u << 16);
+              const uint32_t sb = b_ring + stage * Cfg::HB_STAGE;
+              const uint32_t bx = ((sb & 0x3FFFFu) >> 4) | (1u << 16);
+              const uint32_t by = (((sb + Cfg::BX_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint32_t adv = 2u * k;
+                const uint32_t accum = (first && k == 0) ? 0u : 1u;
+                if (PD) {
+                  umma_f16_pair(d_tmem, hi | (ah + adv), hi | (bx + adv), idesc_wide, accum);   // [hi*hi | hi*lo]
+                  umma_f16_pair(d_tmem, hi | (al + adv), hi | (by + adv), p.idesc, 1u);         // lo*hi
+                } else {
+                  umma_f16_pair(d_tmem, hi | (ah + adv), hi | (bx + adv), p.idesc, accum);      // hi*hi
+                  umma_f16_pair(d_tmem, hi | (ah + adv), hi | (by + adv), p.idesc, 1u);         // hi*lo
+                  umma_f16_pair(d_tmem, hi | (al + adv), hi | (bx + adv), p.idesc, 1u);         // lo*hi
+                }
+              }
+              first = false;
+              umma_commit_pair(b_empty(stage));
+              if (++stage == (uint32_t)NB) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+            umma_commit_pair(a_empty(h_ua));   // the unit's rows (in both CTAs) may be overwritten once these MMAs have read them
+            if (++h_ua == (uint32_t)NA) {
+              h_ua = 0;
+              h_aph ^= 1u;
+            }
+          }
+          commit(tfull_bar(acc));
+          acc ^= 1u;
+          if (acc == 0) acc_phase ^= 1u;
+          continue;
+        }
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -564,6 +711,8 @@ void tc_debug_force_bn(int bn) {
   DDNM_CHECK(bn == 0 || bn == 64 || bn == 128 || bn == 256, "BN must be 0 (heuristic), 64, 128 or 256");
   g_force_bn = bn;
 }
+static int g_halo = [] { const char* v = std::getenv("DDNM_HALO"); return v && *v ? std::atoi(v) : 1; }();
+void tc_debug_halo(int on) { g_halo = on; }
 static int g_deal = -1;
 void tc_debug_deal(int mode) {
   DDNM_CHECK(mode >= -1 && mode <= 1, "deal mode must be -1 (default rule), 0 (round-robin) or 1 (contiguous ranges)");
@@ -660,10 +809,14 @@ TcLaunch tc_make_launch(const SplitView& src0, int mode0, const SplitView* src1,
   // Instruction descriptor: D = f32 (1 << 4), A = B = f16 (0), K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
   p.idesc = ((1u << 4) | ((uint32_t)(L.BN >> 3) << 17) | ((uint32_t)((L.pair ? 2 * BM : BM) >> 4) << 24)) ^ g_idesc_xor;
 
+  // halo-row form: pairs, 3x3 stride 1, tiles of 128 pixels of one row (W >= 128), fp32-grade arithmetic
+  L.halo = g_halo != 0 && L.pair && mode0 == TAPS_3X3 && p.bw == 128 && p.bh == 1 && p.bn == 1 && g_terms == 3 && p.b_batched == 0 &&
+           (L.BN == 256 || L.dual);
   const uint64_t ad[4] = {(uint64_t)src0.C, (uint64_t)src0.W, (uint64_t)src0.H, (uint64_t)src0.N};
   const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-  L.a0h = make_map_f16(src0.hi, 4, ad, abox);
-  L.a0l = make_map_f16(src0.lo, 4, ad, abox);
+  const uint32_t hbox[4] = {(uint32_t)BK, 130u, 1u, 1u};   // HALO: pixels x0-1 .. x0+128 of one row
+  L.a0h = make_map_f16(src0.hi, 4, ad, L.halo ? hbox : abox);
+  L.a0l = make_map_f16(src0.lo, 4, ad, L.halo ? hbox : abox);
   if (src1) {
     const uint64_t ad1[4] = {(uint64_t)src1->C, (uint64_t)src1->W, (uint64_t)src1->H, (uint64_t)src1->N};
     L.a1h = make_map_f16(src1->hi, 4, ad1, abox);
@@ -756,25 +909,27 @@ TcLaunch tc_make_gemm_launch(const GemmOperand& A, const GemmOperand& B, int M, 
   return L;
 }
 
-template <int BN, bool PAIR, bool DUAL>
+template <int BN, bool PAIR, bool DUAL, bool HALO = false>
 static void launch_bn(const TcLaunch& L, cudaStream_t stream) {
-  using Cfg = TcCfg<BN, PAIR, DUAL>;
+  using Cfg = TcCfg<BN, PAIR, DUAL, HALO>;
   static bool attr_set[64] = {};
   if (first_use_on_device(attr_set))
-    CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, PAIR, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  launch_pdl(conv_tc_kernel<BN, PAIR, DUAL>, dim3(L.grid), dim3(kTcThreads), (size_t)Cfg::SMEM_BYTES, stream, PAIR ? 2 : 1, L.a0h, L.a0l, L.a1h, L.a1l,
-             L.bh, L.bl, L.b2, L.p);
+    CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, PAIR, DUAL, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  launch_pdl(conv_tc_kernel<BN, PAIR, DUAL, HALO>, dim3(L.grid), dim3(HALO ? kTcThreads + 32 : kTcThreads), (size_t)Cfg::SMEM_BYTES, stream,
+             PAIR ? 2 : 1, L.a0h, L.a0l, L.a1h, L.a1l, L.bh, L.bl, L.b2, L.p);
   CUDA_CHECK(cudaGetLastError());
 }
 
 void tc_run(const TcLaunch& L, cudaStream_t stream) {
   switch (L.BN) {
     case 256:
-      if (L.pair) launch_bn<256, true, false>(L, stream);
+      if (L.pair && L.halo) launch_bn<256, true, false, true>(L, stream);
+      else if (L.pair) launch_bn<256, true, false>(L, stream);
       else launch_bn<256, false, false>(L, stream);
       break;
     case 128:
-      if (L.pair && L.dual) launch_bn<128, true, true>(L, stream);
+      if (L.pair && L.dual && L.halo) launch_bn<128, true, true, true>(L, stream);
+      else if (L.pair && L.dual) launch_bn<128, true, true>(L, stream);
       else if (L.pair) launch_bn<128, true, false>(L, stream);
       else if (L.dual) launch_bn<128, false, true>(L, stream);
       else launch_bn<128, false, false>(L, stream);

@@ -46,6 +46,7 @@ struct TcLaunch {
   TcParams p;
   int BN = 128;
   bool pair = false;           // CTA-pair kernel (cta_group::2, 256-row MMAs, cluster of 2)
+  bool halo = false;           // halo-row form: A staged once per (channel slice, dy) and shared by the three dx taps
   bool dual = false;           // two partial accumulators per stage: hi*hi and hi*lo issued as one N = 2*BN instruction
   int grid = 0;
   double flops = 0;            // algorithmic flops (2*M*N*K, counted once)
@@ -124,6 +125,7 @@ void tc_debug_gn_fused(int on);         // 1: eligible layers use the fused kern
 // debug knobs (tests only): override descriptor words for the NEXT launches built
 void tc_debug_override(uint32_t desc_hi, uint32_t idesc_xor);
 void tc_debug_force_bn(int bn);
+void tc_debug_halo(int on);         // 1 (default, env DDNM_HALO): eligible pair launches use the halo-row form
 void tc_debug_deal(int mode);        // -1 (default): contiguous tile ranges where they pay (one N tile + GroupNorm sums), 0 / 1: force
 void tc_debug_pair_dual(int on);     // 1 (default): CTA pairs at BN = 128 use the PAIR + DUAL form
 void tc_debug_dual_mode(int mode);   // 1: DUAL kernel for single-CTA BN <= 128 launches (default), 0: never

@@ -250,6 +250,9 @@ int ddnm_tc_debug_force_bn(int bn);
 /* tile -> CTA map of conv launches built afterwards: -1 (default) contiguous tile ranges per CTA on layers with one N tile that
  * produce GroupNorm sums, 0 round-robin everywhere, 1 contiguous wherever legal */
 int ddnm_tc_debug_deal(int mode);
+/* 1 (default, also env DDNM_HALO): CTA-pair 3x3 launches on rows >= 128 pixels stage the A operand once per (channel slice, row
+ * offset) as a 130-pixel halo row shared by the three horizontal taps; 0: one TMA box per tap */
+int ddnm_tc_debug_halo(int on);
 /* 1 (default): CTA pairs at BN = 128 (Cout = 128 layers) use the PAIR + DUAL instruction form; 0: the plain pair form */
 int ddnm_tc_debug_pair_dual(int on);
 /* 1 (default): single-CTA launches with BN <= 128 issue hi*hi and hi*lo as one N = 2*BN instruction (two partial accumulators); 0: never */

@@ -109,7 +109,9 @@ def test_tc_conv_cta_pair_vs_fp64_and_single_cta(lib, shape):
         L.ddnm_tc_debug_pair_mode(-1)
         L.ddnm_tc_debug_pair_dual(1)
     torch.cuda.synchronize()
-    assert_close(pair, single, 2e-5, 1e-5, f"pair vs single-CTA {shape}")   # same products, sums re-associated
+    # same products, fp32 sums re-associated (the halo-row form of the pair kernels also walks k in another order): a handful of
+    # the 1e7 outputs differ by up to ~1.5e-5; both forms sit inside the fp64 tolerance below
+    assert_close(pair, single, 3e-5, 2e-5, f"pair vs single-CTA {shape}")
     assert_close(pair, _conv_ref(x, w, b, mode=mode), rtol=1e-4, atol=5e-5, what=f"pair conv {shape}")
 
 
@@ -162,8 +164,41 @@ def test_tc_conv_pair_dual_form(lib, shape):
         L.ddnm_tc_debug_pair_dual(1)
         L.ddnm_tc_debug_force_bn(0)
     torch.cuda.synchronize()
-    assert_close(pd, single, 2e-5, 1e-5, f"pair+dual vs single-CTA {shape}")
+    assert_close(pd, single, 3e-5, 2e-5, f"pair+dual vs single-CTA {shape}")
     assert_close(pd, _conv_ref(x, w, b, mode=mode), rtol=1e-4, atol=5e-5, what=f"pair+dual conv {shape}")
+
+
+@pytest.mark.parametrize("shape", [(2, 128, 128, 64, 128, 0, False, 128), (1, 256, 256, 128, 128, 0, True, 128), (2, 128, 128, 128, 256, 0, False, 256),
+                                   (2, 128, 128, 64, 128, 192, False, 128), (1, 256, 256, 64, 256, 64, True, 256), (3, 128, 128, 192, 128, 0, False, 128)],
+                         ids=str)
+def test_tc_conv_halo_row_form(lib, shape):
+    """HALO form of the CTA-pair kernels (rows >= 128 pixels): the A operand is staged once per (64-channel slice, row offset) as a
+    130-pixel halo row and the three horizontal taps read it through shifted UMMA descriptors.  Same products as the one-box-per-tap
+    form in another k order: must agree with it to fp32 re-association, and with fp64; image borders (TMA zero fill on both sides
+    and above / below), the 1x1 side input and the residual epilogue included."""
+    N, H, W, Cin, Cout, side_c, res, bn = shape
+    torch.manual_seed(11)
+    x = torch.randn(N, Cin, H, W, device=dev)
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    side = torch.randn(N, side_c, H, W, device=dev) if side_c else None
+    sw = torch.randn(Cout, side_c, 1, 1, device=dev) / side_c ** 0.5 if side_c else None
+    r = torch.randn(N, Cout, H, W, device=dev) if res else None
+    L = lib.lib()
+    try:
+        lib.check(L.ddnm_tc_debug_pair_mode(1))
+        lib.check(L.ddnm_tc_debug_force_bn(bn))
+        lib.check(L.ddnm_tc_debug_halo(0))
+        boxes = _conv_tc(lib, x, w, b, side=side, side_w=sw, res=r).clone()
+        lib.check(L.ddnm_tc_debug_halo(1))
+        halo = _conv_tc(lib, x, w, b, side=side, side_w=sw, res=r)
+    finally:
+        L.ddnm_tc_debug_pair_mode(-1)
+        L.ddnm_tc_debug_force_bn(0)
+        L.ddnm_tc_debug_halo(1)
+    torch.cuda.synchronize()
+    assert_close(halo, boxes, 3e-5, 2e-5, f"halo rows vs one box per tap {shape}")
+    assert_close(halo, _conv_ref(x, w, b, side=side, side_w=sw, res=r), rtol=1e-4, atol=5e-5, what=f"halo-row conv {shape}")
 
 
 def test_tc_conv_cta_pair_fusions(lib):
