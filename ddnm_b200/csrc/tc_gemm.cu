@@ -64,7 +64,7 @@ struct TcCfg {
   static constexpr int HA_UNIT = 2 * HA_PLANE;            // hi + lo
   static constexpr int HA_NA = 3;                         // A ring depth (units)
   static constexpr int HB_STAGE = BX_BYTES + BY_BYTES;
-  static constexpr int HB_NB = PD ? 4 : 3;                // B ring depth (tap stages)
+  static constexpr int HB_NB = PD ? 5 : 3;                // B ring depth (tap stages)
   static constexpr int RING_BYTES = HALO ? HA_NA * HA_UNIT + HB_NB * HB_STAGE : STAGES * STAGE_BYTES;
   static constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COMBINE_BYTES;
   static constexpr int ACC_COLS = DUAL ? 2 * BN : BN;    // TMEM columns of one accumulator stage
