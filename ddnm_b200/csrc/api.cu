@@ -289,6 +289,69 @@ int ddnm_conv_tc_bench(int N, int H, int W, int Cin, int Cout, int mode, int ite
   DDNM_API_END
 }
 
+// Probe (tests/diag): GroupNorm+SiLU+split -> 3x3 convolution over N images, run in chunks of `chunk` images that SHARE one
+// chunk-sized scratch for the fp16 planes (so the planes can stay in L2 between the pass that writes them and the convolution that
+// reads them, and are overwritten in place by the next chunk).  chunk == N is the engine's current order.  ms per full pass.
+int ddnm_gnconv_chunk_bench(int N, int chunk, int H, int W, int Cin, int Cout, int iters, float* ms_per_pass) {
+  DDNM_API_BEGIN
+  DDNM_CHECK(chunk >= 1 && N % chunk == 0, "chunk must divide N");
+  Tmp tmp;
+  const size_t pe = (size_t)N * H * W * Cin, ce = (size_t)chunk * H * W * Cin, oe = (size_t)N * H * W * Cout;
+  float* x = tmp.get<float>(pe);
+  bench_fill_f32<<<(unsigned)cdivll((long long)pe, 256), 256>>>(x, (long long)pe, 0x4321u);
+  StatAcc* st = tmp.get<StatAcc>((size_t)N * Cin * 2);
+  CUDA_CHECK(cudaMemset(st, 0, (size_t)N * Cin * 2 * sizeof(StatAcc)));
+  View xv = mkview(x, N, H, W, Cin);
+  xv.st = st; xv.st_ld = Cin;
+  gn_stats(xv, 0);
+  float* gamma = tmp.get<float>(Cin);
+  float* beta = tmp.get<float>(Cin);
+  bench_fill_f32<<<cdiv(Cin, 256), 256>>>(gamma, Cin, 0x11u);
+  bench_fill_f32<<<cdiv(Cin, 256), 256>>>(beta, Cin, 0x22u);
+  SplitView A;
+  A.hi = tmp.get<__half>(ce); A.lo = tmp.get<__half>(ce); A.N = chunk; A.H = H; A.W = W; A.C = Cin;
+  const int ktot = 9 * Cin;
+  __half* wh = tmp.get<__half>((size_t)Cout * ktot);
+  __half* wl = tmp.get<__half>((size_t)Cout * ktot);
+  bench_fill_split<<<(unsigned)cdivll((long long)Cout * ktot, 256), 256>>>(wh, wl, (long long)Cout * ktot, 0x9876u, 1.0f / sqrtf((float)ktot));
+  float* o = tmp.get<float>(oe);
+  StatAcc* ost = tmp.get<StatAcc>((size_t)N * Cout * 2);
+  CUDA_CHECK(cudaMemset(ost, 0, (size_t)N * Cout * 2 * sizeof(StatAcc)));
+  float* ca = tmp.get<float>((size_t)N * Cout);
+  CUDA_CHECK(cudaMemset(ca, 0, (size_t)N * Cout * 4));
+  const int nch = N / chunk;
+  std::vector<View> xs;
+  std::vector<TcLaunch> Ls;
+  for (int c = 0; c < nch; ++c) {
+    View xc = xv;
+    xc.p = x + (size_t)c * chunk * H * W * Cin; xc.N = chunk; xc.st = st + (size_t)c * chunk * Cin * 2;
+    View oc = mkview(o + (size_t)c * chunk * H * W * Cout, chunk, H, W, Cout);
+    oc.st = ost + (size_t)c * chunk * Cout * 2; oc.st_ld = Cout;
+    xs.push_back(xc);
+    Ls.push_back(tc_make_launch(A, TAPS_3X3, nullptr, wh, wl, 1, Cout, oc, ca + (size_t)c * chunk * Cout, Cout, nullptr, 0, 1.0f, sm_count()));
+  }
+  auto pass = [&]() {
+    for (int c = 0; c < nch; ++c) {
+      gn_apply_split(xs[c], 32, true, gamma, beta, 1e-6f, true, SPLIT_SAME, A.hi, A.lo, 0);
+      tc_run(Ls[c], 0);
+    }
+  };
+  for (int i = 0; i < 2; ++i) pass();
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, 0));
+  for (int i = 0; i < iters; ++i) pass();
+  CUDA_CHECK(cudaEventRecord(e1, 0));
+  CUDA_CHECK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_pass = ms / iters;
+  DDNM_API_END
+}
+
 int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const float* gamma, const float* beta, float eps,
                    int silu, float* out, void* stream) {
   DDNM_API_BEGIN

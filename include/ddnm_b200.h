@@ -225,6 +225,8 @@ int ddnm_conv_direct(const float* x, int N, int H, int W, int Cin, const float* 
                      float* out, void* stream);
 /* iters > 0: all-zero operands; iters < 0: |iters| iterations on pseudo-random operands (power-realistic) */
 int ddnm_conv_tc_bench(int N, int H, int W, int Cin, int Cout, int mode, int iters, float* ms_per_iter, double* flops);
+/* diag probe: GroupNorm+SiLU+split -> 3x3 convolution over N images in chunks of `chunk` images sharing one chunk-sized plane scratch */
+int ddnm_gnconv_chunk_bench(int N, int chunk, int H, int W, int Cin, int Cout, int iters, float* ms_per_pass);
 int ddnm_groupnorm(const float* x, int N, int H, int W, int C, int groups, const float* gamma, const float* beta, float eps,
                    int silu, float* out, void* stream);
 /* The fused form the engine uses for the wide layers (rows >= 128 pixels): out = conv3x3(silu?(groupnorm(x))) [+ conv1x1(side_x)] + bias

@@ -433,6 +433,17 @@ def group_epi_bench(iters=-20, deal=-1):
         print(f"[epi_bench] N{N} {H}x{W} {Cin}->{Cout} up-phase: plain {row[0]} | stats {row[1]} | chanadd {row[2]} | stats+chanadd {row[3]} us", flush=True)
 
 
+def group_chunk_bench(iters=10):
+    """GroupNorm pass + convolution over 16 images in chunks sharing a chunk-sized plane scratch: do the planes stay in L2?"""
+    ms = C.c_float()
+    for (N, H, W, Cin, Cout) in [(16, 256, 256, 128, 128), (16, 256, 256, 256, 128), (16, 128, 128, 128, 128), (16, 128, 128, 256, 128)]:
+        row = []
+        for chunk in (16, 8, 4, 2, 1):
+            _lib.check(L.ddnm_gnconv_chunk_bench(N, chunk, H, W, Cin, Cout, int(iters), C.byref(ms)))
+            row.append(f"chunk {chunk:2d}: {ms.value * 1e3:7.1f}")
+        print(f"[chunk_bench] N{N} {H}x{W} {Cin}->{Cout} gn+conv us per 16 images: " + " | ".join(row), flush=True)
+
+
 def group_eager(which="celeba", B=16, iters=3):
     """The competitor SURVEY §8d names: the reference's network as plain PyTorch eager on this GPU (the oracle restatement is
     the reference's op sequence, bit-exact on CPU), with the reference's own settings (main.py:145 cudnn.benchmark = True; TF32
