@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <sstream>
 
 #include "kernels.cuh"
@@ -280,6 +281,18 @@ void UNetEngine::emit_stem(const std::string& wname, const View& out) {
 void UNetEngine::emit_head(const std::string& norm, const std::string& conv, const View& fh) {
   DDNM_CHECK(fh.st != nullptr, "head input without statistics");
   DDNM_CHECK(out_ch_ <= 64, "head convolution: out_ch <= 64");
+  if (head_conv_supported(fh, out_ch_) && std::getenv("DDNM_HEAD_TC") == nullptr) {
+    // one kernel: the activation is read once, normalised on the way into shared memory, convolved in exact fp32 (3 or 6 output
+    // channels are too few for the tensor cores: the padded-N form below streams the A operand for 0.6 ms + a 0.2 ms GroupNorm pass)
+    const float *g = P(norm + ".weight", fh.C), *b = P(norm + ".bias", fh.C);
+    const float *w = P(conv + ".weight", (long long)out_ch_ * fh.C * 9), *cb = P(conv + ".bias", out_ch_);
+    const int groups = groups_, oc = out_ch_;
+    const float eps = eps_;
+    float* o = out_;
+    add_op("head.conv", "head", 2.0 * fh.pixels() * (double)oc * fh.C * 9, (double)fh.pixels() * (fh.C + oc) * 4,
+           [=](cudaStream_t s) { head_conv(fh, groups, g, b, eps, w, cb, oc, o, s); });
+    return;
+  }
   SplitView A{splitA_hi_, splitA_lo_};
   emit_gn_split("head", fh, norm, true, SPLIT_SAME, A);
   const int ktot = 9 * fh.C;

@@ -17,6 +17,14 @@ bool pdl_enabled() {
 }
 
 __device__ __forceinline__ float swishf(float x) { return x / (1.0f + expf(-x)); }
+// x * sigmoid(x) on the special-function unit: 2^(-x log2 e) by ex2.approx, the quotient by rcp.approx (relative error ~2e-7, two
+// orders below the fp16 split that follows it).  The GroupNorm pass is within ~1.4x of being issue-bound with the library expf and
+// the IEEE division (~20 instructions per element); this form is 5.
+__device__ __forceinline__ float swishf_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  return __fdividef(x, 1.0f + e);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Per-channel sums for GroupNorm (torch.nn.GroupNorm(32, C): models.py:32-33 / nn.py:17-19) of a tensor that was NOT
@@ -165,7 +173,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           v[j] = fmaf(v[j], a8[j], b8[j]);
-          if (silu) v[j] = swishf(v[j]);
+          if (silu) v[j] = swishf_fast(v[j]);
           acc[j] += v[j];
         }
       }
@@ -206,7 +214,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       v[j] = fmaf(v[j], a8[j], b8[j]);
-      if (silu) v[j] = swishf(v[j]);
+      if (silu) v[j] = swishf_fast(v[j]);
     }
     if (F32OUT) {
       float* d = out32 + ((size_t)n * HW + p) * C + c;
@@ -314,24 +322,41 @@ __global__ void __launch_bounds__(256) conv_small_cin_kernel(const float* __rest
   const int y = y0 + warp;
   float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
   float* orow = out + (((size_t)n * H + y) * W + x0) * ld + co;
-  for (int px = 0; active && y < H && px < TW && x0 + px < W; ++px) {
-    float acc[4] = {b4[0], b4[1], b4[2], b4[3]};
+  // two pixels per iteration: the 3 x 4 window of each input channel is read once (LDS.64 pairs) for 2 x 27 x 4 FMAs, and the two
+  // accumulator sets give the FMA pipe independent work while the next window loads
+  for (int px = 0; active && y < H && px < TW && x0 + px < W; px += 2) {
+    float acc0[4] = {b4[0], b4[1], b4[2], b4[3]};
+    float acc1[4] = {b4[0], b4[1], b4[2], b4[3]};
 #pragma unroll
     for (int c = 0; c < CIN; ++c)
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 3; ++r) {
+        const float2 v01 = *reinterpret_cast<const float2*>(&tile[c][warp + r][px]);
+        const float2 v23 = *reinterpret_cast<const float2*>(&tile[c][warp + r][px + 2]);
+        const float v[4] = {v01.x, v01.y, v23.x, v23.y};
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const float v = tile[c][warp + r][px + d];
           const int k = c * 9 + r * 3 + d;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = fmaf(v, wr[k][j], acc[j]);
+          for (int j = 0; j < 4; ++j) {
+            acc0[j] = fmaf(v[d], wr[k][j], acc0[j]);
+            acc1[j] = fmaf(v[d + 1], wr[k][j], acc1[j]);
+          }
         }
-    *reinterpret_cast<float4*>(orow + (size_t)px * ld) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      }
+    *reinterpret_cast<float4*>(orow + (size_t)px * ld) = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      s4[j] += acc[j];
-      q4[j] = fmaf(acc[j], acc[j], q4[j]);
+      s4[j] += acc0[j];
+      q4[j] = fmaf(acc0[j], acc0[j], q4[j]);
+    }
+    if (x0 + px + 1 < W) {
+      *reinterpret_cast<float4*>(orow + (size_t)(px + 1) * ld) = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s4[j] += acc1[j];
+        q4[j] = fmaf(acc1[j], acc1[j], q4[j]);
+      }
     }
   }
   if (stats == nullptr) return;
@@ -357,6 +382,140 @@ void conv3x3_small_cin(const float* x, int Cin, const float* w, const float* bia
   dim3 grid(cdiv(out.W, 64), cdiv(out.H, 8), out.N * cdiv(out.C, 128));
   // the GroupNorm sums of the output come out of the same pass when the view carries accumulators
   launch_pdl(conv_small_cin_kernel<3>, grid, dim3(256), 0, st, 1, x, w, bias, out.p, out.H, out.W, out.C, out.ld, out.st, out.st_ld);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Network head in one kernel: h = conv_out(nonlinearity(norm_out(h)))  (models.py:338-340; unet.py:613-617 `out`), NCHW result.
+// Cout is 3 (or 6 with learned sigma): on the tensor cores the N tile has to be padded to 64 columns and the kernel is paced by
+// streaming the A operand (0.6 ms + a 0.2 ms GroupNorm pass + the NCHW copy at 256x256, B = 16).  Here the fp32 activation is read
+// ONCE: a CTA stages an (8 + 2) x (128 + 2) halo tile of 16 channels at a time in shared memory with the GroupNorm affine and SiLU
+// applied on the way in (zero outside the image: the convolution's padding), each thread owns 4 consecutive pixels x COP output
+// channels and per (channel, tap row) reads 6 activations + 3 broadcast weight vectors for 12 * Cout exact fp32 FMAs.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int HD_TW = 128, HD_TH = 8, HD_CH = 16, HD_PITCH = 132, HD_PLANE = (HD_TH + 2) * HD_PITCH + 4;
+template <int COP>
+__global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ x, int H, int W, int C, int ld, int groups,
+                                                        const StatAcc* __restrict__ stats, int st_ld, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, int Cout, float* __restrict__ out) {
+  pdl_prologue();
+  extern __shared__ float hd_smem[];
+  float* act = hd_smem;                           // [HD_CH][HD_PLANE]
+  float* wsm = act + HD_CH * HD_PLANE;            // [HD_CH][3][3][COP]
+  float* sc = wsm + HD_CH * 9 * COP;              // [C] scale, [C] shift
+  float* sh = sc + C;
+  const int n = blockIdx.z, y0 = blockIdx.y * HD_TH, x0 = blockIdx.x * HD_TW;
+  {
+    // per-(image, channel) GroupNorm affine from the producer's sums (same arithmetic as gn_apply_kernel)
+    const int cpg = C / groups;
+    const double cnt = (double)H * W * cpg;
+    const StatAcc* gsrc = stats + (size_t)n * st_ld * 2;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g0 = (c / cpg) * cpg;
+      double s1 = 0, s2 = 0;
+      for (int j = 0; j < cpg; ++j) {
+        s1 += stat_value(gsrc[2 * (g0 + j)]);
+        s2 += stat_value(gsrc[2 * (g0 + j) + 1]);
+      }
+      const double mean = s1 / cnt;
+      double var = s2 / cnt - mean * mean;
+      var = var < 0 ? 0 : var;
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float a = rstd * gamma[c];
+      sc[c] = a;
+      sh[c] = beta[c] - (float)mean * a;
+    }
+  }
+  const int ty = threadIdx.x >> 5, tx4 = (threadIdx.x & 31) * 4;   // 8 rows x 32 groups of 4 pixels
+  float acc[4][COP];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int co = 0; co < COP; ++co) acc[i][co] = 0.f;
+  for (int c0 = 0; c0 < C; c0 += HD_CH) {
+    __syncthreads();   // previous chunk consumed (first pass: the coefficient table is complete)
+    // ---- stage the chunk: activations (normalised, activated, zero-padded) and weights
+    for (int i = threadIdx.x; i < (HD_TH + 2) * (HD_TW + 2) * (HD_CH / 4); i += blockDim.x) {
+      const int q = i % (HD_CH / 4), pix = i / (HD_CH / 4);
+      const int col = pix % (HD_TW + 2), row = pix / (HD_TW + 2);
+      const int gy = y0 + row - 1, gx = x0 + col - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        const int c = c0 + 4 * q;
+        v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + gy) * W + gx) * ld + c));
+        v.x = swishf(fmaf(v.x, sc[c + 0], sh[c + 0]));
+        v.y = swishf(fmaf(v.y, sc[c + 1], sh[c + 1]));
+        v.z = swishf(fmaf(v.z, sc[c + 2], sh[c + 2]));
+        v.w = swishf(fmaf(v.w, sc[c + 3], sh[c + 3]));
+      }
+      float* d = act + (4 * q) * HD_PLANE + row * HD_PITCH + col;
+      d[0] = v.x;
+      d[HD_PLANE] = v.y;
+      d[2 * HD_PLANE] = v.z;
+      d[3 * HD_PLANE] = v.w;
+    }
+    for (int i = threadIdx.x; i < HD_CH * 9 * COP; i += blockDim.x) {
+      const int co = i % COP, t = (i / COP) % 9, ch = i / (9 * COP);
+      wsm[i] = co < Cout ? __ldg(&w[((size_t)co * C + c0 + ch) * 9 + t]) : 0.f;   // OIHW
+    }
+    __syncthreads();
+    // ---- 4 pixels x COP channels per thread
+#pragma unroll 2
+    for (int ch = 0; ch < HD_CH; ++ch) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float* ap = act + ch * HD_PLANE + (ty + r) * HD_PITCH + tx4;
+        const float4 a0 = *reinterpret_cast<const float4*>(ap);
+        const float2 a1 = *reinterpret_cast<const float2*>(ap + 4);
+        const float a[6] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y};
+        const float* wp = wsm + (ch * 9 + r * 3) * COP;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+          for (int co = 0; co < COP; ++co) {
+            const float wv = wp[d * COP + co];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][co] = fmaf(a[i + d], wv, acc[i][co]);
+          }
+      }
+    }
+  }
+  const int y = y0 + ty, xx = x0 + tx4;
+  if (y < H && xx < W) {
+#pragma unroll
+    for (int co = 0; co < COP; ++co) {
+      if (co < Cout) {
+        const float b = bias[co];
+        float* o = out + (((size_t)n * Cout + co) * H + y) * W + xx;
+        if (xx + 3 < W && (W & 3) == 0) {
+          *reinterpret_cast<float4*>(o) = make_float4(acc[0][co] + b, acc[1][co] + b, acc[2][co] + b, acc[3][co] + b);
+        } else {
+          for (int i = 0; i < 4 && xx + i < W; ++i) o[i] = acc[i][co] + b;
+        }
+      }
+    }
+  }
+}
+
+bool head_conv_supported(const View& h, int Cout) { return h.C % HD_CH == 0 && h.C <= 1024 && Cout >= 1 && Cout <= 8 && h.ld % 4 == 0; }
+
+void head_conv(const View& h, int groups, const float* gamma, const float* beta, float eps, const float* w, const float* bias, int Cout,
+               float* out_nchw, cudaStream_t st) {
+  DDNM_CHECK(head_conv_supported(h, Cout) && h.st != nullptr && h.C % groups == 0, "head convolution: unsupported shape");
+  const int cop = Cout <= 4 ? 4 : 8;
+  const size_t smem = ((size_t)HD_CH * HD_PLANE + (size_t)HD_CH * 9 * cop + 2 * (size_t)h.C) * sizeof(float);
+  dim3 grid(cdiv(h.W, HD_TW), cdiv(h.H, HD_TH), h.N);
+  static bool attr4[64] = {}, attr8[64] = {};
+  if (cop == 4) {
+    if (first_use_on_device(attr4)) CUDA_CHECK(cudaFuncSetAttribute(head_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    launch_pdl(head_conv_kernel<4>, grid, dim3(256), smem, st, 1, (const float*)h.p, h.H, h.W, h.C, h.ld, groups, (const StatAcc*)h.st, h.st_ld, gamma,
+               beta, eps, w, bias, Cout, out_nchw);
+  } else {
+    if (first_use_on_device(attr8)) CUDA_CHECK(cudaFuncSetAttribute(head_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    launch_pdl(head_conv_kernel<8>, grid, dim3(256), smem, st, 1, (const float*)h.p, h.H, h.W, h.C, h.ld, groups, (const StatAcc*)h.st, h.st_ld, gamma,
+               beta, eps, w, bias, Cout, out_nchw);
+  }
   CUDA_CHECK(cudaGetLastError());
 }
 

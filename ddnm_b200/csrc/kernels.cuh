@@ -24,6 +24,10 @@ void gn_apply_f32(const View& x, int groups, const float* gamma, const float* be
                   cudaStream_t s);
 
 // 3x3 pad-1 convolution with tiny Cin (the network stem): x NCHW [N,Cin,H,W] fp32, w OIHW, out NHWC view.
+// network head in one pass: GroupNorm + SiLU + 3x3 convolution to Cout <= 8 channels in exact fp32 on the CUDA cores, NCHW output
+bool head_conv_supported(const View& h, int Cout);
+void head_conv(const View& h, int groups, const float* gamma, const float* beta, float eps, const float* w_oihw, const float* bias, int Cout,
+               float* out_nchw, cudaStream_t s);
 void conv3x3_small_cin(const float* x_nchw, int Cin, const float* w_oihw, const float* bias, const View& out, cudaStream_t s);
 // out[n][o] = act_out( sum_k act_in(in[n][k]) * W[o][k] + bias[o] );  act: 0 none, 1 swish
 void linear(const float* in, int N, int K, const float* W, const float* bias, int O, float* out, int ldo, int act_in,
