@@ -360,7 +360,13 @@ def main():
         pk = peaks()
         # roofline of the dominant kernel family (the tcgen05 convolution): per-launch CUDA-event timing of one eager forward
         xt = torch.randn(B, 3, RES, RES, device=dev)
-        prof = model.profile(xt, torch.full((B,), 500.0, device=dev))
+        # three eager passes, per launch the fastest: in the regions of short launches the elapsed time between two events measures the
+        # host's issue rate rather than the kernel (profiles/r02_attn_anomaly.md), and that jitter is one-sided
+        tt = torch.full((B,), 500.0, device=dev)
+        prof = model.profile(xt, tt)
+        for _ in range(2):
+            for a, b in zip(prof, model.profile(xt, tt)):
+                a["ms"] = min(a["ms"], b["ms"])
         tc = [p for p in prof if p["kind"] in ("tc", "tcgn")]
         tc_ms, tc_fl = sum(p["ms"] for p in tc), sum(p["flops"] for p in tc)
         all_ms = sum(p["ms"] for p in prof)

@@ -347,6 +347,14 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(r));
   lo = __ushort_as_half(h);
 }
+// two fp32 values -> packed fp16 hi pair + packed fp16 lo pair (hi = rn(x) saturated to the finite range, lo = rn(x - hi))
+__device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+  const float2 f = __half22float2(h);
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - f.y), "f"(x0 - f.x));
+}
+
 #endif  // __CUDACC__
 
 }  // namespace ddnm

@@ -203,13 +203,14 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
       b = __ldg(reinterpret_cast<const float4*>(src + step + 4));
     }
     if (!F32OUT && raw_hi) {  // second output: the un-normalised tensor (input of the 1x1 shortcut convolution)
-      __align__(16) __half rh[8];
-      __align__(16) __half rl[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) split_f16(v[j], rh[j], rl[j]);
+      uint4 rh, rl;
+      split2_f16(v[0], v[1], rh.x, rl.x);
+      split2_f16(v[2], v[3], rh.y, rl.y);
+      split2_f16(v[4], v[5], rh.z, rl.z);
+      split2_f16(v[6], v[7], rh.w, rl.w);
       const size_t o = ((size_t)n * HW + p) * C + c;
-      *reinterpret_cast<uint4*>(raw_hi + o) = *reinterpret_cast<const uint4*>(rh);
-      *reinterpret_cast<uint4*>(raw_lo + o) = *reinterpret_cast<const uint4*>(rl);
+      *reinterpret_cast<uint4*>(raw_hi + o) = rh;
+      *reinterpret_cast<uint4*>(raw_lo + o) = rl;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -221,12 +222,11 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, int H, int W, int C
       *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
     } else {
-      __align__(16) __half h8[8];
-      __align__(16) __half l8[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) split_f16(v[j], h8[j], l8[j]);
-      const uint4 hv = *reinterpret_cast<const uint4*>(h8);
-      const uint4 lv = *reinterpret_cast<const uint4*>(l8);
+      uint4 hv, lv;   // two values per conversion instruction (same roundings as split_f16)
+      split2_f16(v[0], v[1], hv.x, lv.x);
+      split2_f16(v[2], v[3], hv.y, lv.y);
+      split2_f16(v[4], v[5], hv.z, lv.z);
+      split2_f16(v[6], v[7], hv.w, lv.w);
       if (mode == SPLIT_SAME) {
         const size_t o = ((size_t)n * HW + p) * C + c;
         *reinterpret_cast<uint4*>(hi + o) = hv;
@@ -436,24 +436,43 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
   for (int c0 = 0; c0 < C; c0 += HD_CH) {
     __syncthreads();   // previous chunk consumed (first pass: the coefficient table is complete)
     // ---- stage the chunk: activations (normalised, activated, zero-padded) and weights
-    for (int i = threadIdx.x; i < (HD_TH + 2) * (HD_TW + 2) * (HD_CH / 4); i += blockDim.x) {
-      const int q = i % (HD_CH / 4), pix = i / (HD_CH / 4);
-      const int col = pix % (HD_TW + 2), row = pix / (HD_TW + 2);
-      const int gy = y0 + row - 1, gx = x0 + col - 1;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        const int c = c0 + 4 * q;
-        v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + gy) * W + gx) * ld + c));
-        v.x = swishf(fmaf(v.x, sc[c + 0], sh[c + 0]));
-        v.y = swishf(fmaf(v.y, sc[c + 1], sh[c + 1]));
-        v.z = swishf(fmaf(v.z, sc[c + 2], sh[c + 2]));
-        v.w = swishf(fmaf(v.w, sc[c + 3], sh[c + 3]));
+    // 7 independent 16-byte loads per thread in flight, then their conversion (one load per iteration exposed ~160 memory
+    // latencies per CTA: 0.83 ms for the kernel instead of 0.25)
+    constexpr int NV = (HD_TH + 2) * (HD_TW + 2) * (HD_CH / 4), UNR = 7;
+    for (int base = 0; base < NV; base += 256 * UNR) {
+      float4 v[UNR];
+      int dst[UNR], cc[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int i = base + u * 256 + (int)threadIdx.x;
+        const int q = i % (HD_CH / 4), pix = i / (HD_CH / 4);
+        const int col = pix % (HD_TW + 2), row = pix / (HD_TW + 2);
+        const int gy = y0 + row - 1, gx = x0 + col - 1;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cc[u] = -1;
+        dst[u] = i < NV ? (4 * q) * HD_PLANE + row * HD_PITCH + col : -1;
+        if (i < NV && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          cc[u] = c0 + 4 * q;
+          v[u] = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + gy) * W + gx) * ld + cc[u]));
+        }
       }
-      float* d = act + (4 * q) * HD_PLANE + row * HD_PITCH + col;
-      d[0] = v.x;
-      d[HD_PLANE] = v.y;
-      d[2 * HD_PLANE] = v.z;
-      d[3 * HD_PLANE] = v.w;
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (dst[u] < 0) continue;
+        float4 t = v[u];
+        if (cc[u] >= 0) {
+          const int c = cc[u];
+          t.x = swishf_fast(fmaf(t.x, sc[c + 0], sh[c + 0]));
+          t.y = swishf_fast(fmaf(t.y, sc[c + 1], sh[c + 1]));
+          t.z = swishf_fast(fmaf(t.z, sc[c + 2], sh[c + 2]));
+          t.w = swishf_fast(fmaf(t.w, sc[c + 3], sh[c + 3]));
+        }
+        float* d = act + dst[u];
+        d[0] = t.x;
+        d[HD_PLANE] = t.y;
+        d[2 * HD_PLANE] = t.z;
+        d[3 * HD_PLANE] = t.w;
+      }
     }
     for (int i = threadIdx.x; i < HD_CH * 9 * COP; i += blockDim.x) {
       const int co = i % COP, t = (i / COP) % 9, ch = i / (9 * COP);
@@ -471,13 +490,18 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
         const float a[6] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y};
         const float* wp = wsm + (ch * 9 + r * 3) * COP;
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
+        for (int d = 0; d < 3; ++d) {
+          float wv[COP];   // one broadcast 16-byte read per 4 output channels (scalar reads made the loop LDS-bound)
 #pragma unroll
-          for (int co = 0; co < COP; ++co) {
-            const float wv = wp[d * COP + co];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i][co] = fmaf(a[i + d], wv, acc[i][co]);
+          for (int c4 = 0; c4 < COP / 4; ++c4) {
+            const float4 t = *reinterpret_cast<const float4*>(wp + d * COP + 4 * c4);
+            wv[4 * c4 + 0] = t.x; wv[4 * c4 + 1] = t.y; wv[4 * c4 + 2] = t.z; wv[4 * c4 + 3] = t.w;
           }
+#pragma unroll
+          for (int co = 0; co < COP; ++co)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][co] = fmaf(a[i + d], wv[co], acc[i][co]);
+        }
       }
     }
   }

@@ -93,14 +93,6 @@ __device__ __forceinline__ float exp2f_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// two fp32 values -> packed fp16 hi pair + packed fp16 lo pair (hi = rn(x) saturated to the finite range, lo = rn(x - hi))
-__device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
-  const __half2 h = *reinterpret_cast<const __half2*>(&hi);
-  const float2 f = __half22float2(h);
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - f.y), "f"(x0 - f.x));
-}
-
 template <int BN>
 __global__ void __launch_bounds__(G_THREADS, 1)
 conv_gn_tc_kernel(const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bl,
