@@ -23,6 +23,7 @@ for step in "$@"; do
     ab)      DDNM_GN_FUSED=0 tools/gpu_session.sh ab_unfused_$TAG unet_bench:celeba:16:5 | tail -25; DDNM_GN_FUSED=1 tools/gpu_session.sh ab_fused_$TAG unet_bench:celeba:16:5 openai_bench:8:3 | tail -50 ;;
     abpdl)   DDNM_PDL=0 tools/gpu_session.sh ab_nopdl_$TAG unet_bench:celeba:16:5 | grep "unet bench"; DDNM_PDL=1 tools/gpu_session.sh ab_pdl_$TAG unet_bench:celeba:16:5 openai_bench:8:3 | grep "bench" ;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 1 --profile-steps 2 > gpurun_out/ncu_bench_$TAG.log 2>&1; tail -2 gpurun_out/ncu_bench_$TAG.log ;;
+    ncu_head) timeout 600 ncu --set full --clock-control none -k regex:"head_conv|conv_small_cin" -s 2 -c 2 -o gpurun_out/prof_head_$TAG -f python tools/ncu_fwd.py > gpurun_out/ncu_head_$TAG.log 2>&1; tail -1 gpurun_out/ncu_head_$TAG.log; ncu_export prof_head_$TAG ;;
     ncu_fwd:*) # ncu_fwd:<index among the 112 tensor-core launches of a forward>[:source]
              IFS=: read -ra pp <<< "$step"; idx=${pp[1]}
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel" -s $((112 + idx)) -c 1 -o gpurun_out/prof_fwd${idx}_$TAG -f python tools/ncu_fwd.py > gpurun_out/ncu_fwd${idx}_$TAG.log 2>&1; tail -1 gpurun_out/ncu_fwd${idx}_$TAG.log; ncu_export prof_fwd${idx}_$TAG source ;;
