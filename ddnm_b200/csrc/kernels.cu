@@ -436,42 +436,42 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict_
   for (int c0 = 0; c0 < C; c0 += HD_CH) {
     __syncthreads();   // previous chunk consumed (first pass: the coefficient table is complete)
     // ---- stage the chunk: activations (normalised, activated, zero-padded) and weights
-    // 7 independent 16-byte loads per thread in flight, then their conversion (one load per iteration exposed ~160 memory
-    // latencies per CTA: 0.83 ms for the kernel instead of 0.25)
-    constexpr int NV = (HD_TH + 2) * (HD_TW + 2) * (HD_CH / 4), UNR = 7;
-    for (int base = 0; base < NV; base += 256 * UNR) {
-      float4 v[UNR];
-      int dst[UNR], cc[UNR];
+    // thread <-> (4-channel group q, tile column): its 10 rows are 10 independent 16-byte loads in flight, then their conversion
+    // (one load per iteration exposed ~160 memory latencies per CTA: 0.83 ms for the kernel); addresses advance by a row pitch,
+    // the 8 GroupNorm coefficients of the thread's channels are read once per chunk
+    {
+      const int q = threadIdx.x & 3;
+      const int c = c0 + 4 * q;
+      const float a0 = sc[c], a1 = sc[c + 1], a2 = sc[c + 2], a3 = sc[c + 3];
+      const float b0 = sh[c], b1 = sh[c + 1], b2 = sh[c + 2], b3 = sh[c + 3];
+#pragma unroll 1
+      for (int col = threadIdx.x >> 2; col < HD_TW + 2; col += 64) {
+        const int gx = x0 + col - 1;
+        const bool xin = gx >= 0 && gx < W;
+        const float* src = x + (((size_t)n * H + (y0 - 1)) * W + gx) * ld + c;   // row y0 - 1 (dereferenced only when inside)
+        float4 v[HD_TH + 2];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int i = base + u * 256 + (int)threadIdx.x;
-        const int q = i % (HD_CH / 4), pix = i / (HD_CH / 4);
-        const int col = pix % (HD_TW + 2), row = pix / (HD_TW + 2);
-        const int gy = y0 + row - 1, gx = x0 + col - 1;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        cc[u] = -1;
-        dst[u] = i < NV ? (4 * q) * HD_PLANE + row * HD_PITCH + col : -1;
-        if (i < NV && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-          cc[u] = c0 + 4 * q;
-          v[u] = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + gy) * W + gx) * ld + cc[u]));
+        for (int r = 0; r < HD_TH + 2; ++r) {
+          const int gy = y0 + r - 1;
+          v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (xin && gy >= 0 && gy < H) v[r] = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * W * ld));
         }
-      }
+        float* d = act + (4 * q) * HD_PLANE + col;
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        if (dst[u] < 0) continue;
-        float4 t = v[u];
-        if (cc[u] >= 0) {
-          const int c = cc[u];
-          t.x = swishf_fast(fmaf(t.x, sc[c + 0], sh[c + 0]));
-          t.y = swishf_fast(fmaf(t.y, sc[c + 1], sh[c + 1]));
-          t.z = swishf_fast(fmaf(t.z, sc[c + 2], sh[c + 2]));
-          t.w = swishf_fast(fmaf(t.w, sc[c + 3], sh[c + 3]));
+        for (int r = 0; r < HD_TH + 2; ++r) {
+          const int gy = y0 + r - 1;
+          float4 t = v[r];
+          if (xin && gy >= 0 && gy < H) {   // outside the image the ACTIVATED value is zero (the convolution's padding)
+            t.x = swishf_fast(fmaf(t.x, a0, b0));
+            t.y = swishf_fast(fmaf(t.y, a1, b1));
+            t.z = swishf_fast(fmaf(t.z, a2, b2));
+            t.w = swishf_fast(fmaf(t.w, a3, b3));
+          }
+          d[r * HD_PITCH] = t.x;
+          d[r * HD_PITCH + HD_PLANE] = t.y;
+          d[r * HD_PITCH + 2 * HD_PLANE] = t.z;
+          d[r * HD_PITCH + 3 * HD_PLANE] = t.w;
         }
-        float* d = act + dst[u];
-        d[0] = t.x;
-        d[HD_PLANE] = t.y;
-        d[2 * HD_PLANE] = t.z;
-        d[3 * HD_PLANE] = t.w;
       }
     }
     for (int i = threadIdx.x; i < HD_CH * 9 * COP; i += blockDim.x) {
