@@ -548,8 +548,10 @@ static int g_gn_desc_mode = env_int("DDNM_GN_DESC_MODE", 0);
 static int g_gn_pf_dist = env_int("DDNM_GN_PF_DIST", 0);
 void tc_debug_gn_pf_dist(int d) { g_gn_pf_dist = d; }
 void tc_debug_gn_desc_mode(int mode) { g_gn_desc_mode = mode; }
-// Default OFF until the kernel beats gn_apply + conv_tc on the B200 (profiles/r02_gn_fused_*.md): round-2 measurements put it at
-// parity on the Cout = 256 layers and behind on the Cout = 128 ones (the transform warps, not the tensor pipe, pace it).
+// Default OFF (profiles/r02_forward_speedup.md): per launch it beats gn_apply + conv_tc on wide inputs without a side operand
+// (up.0.*.conv1: 1811 us vs 1353 + 583), loses wherever the 1x1 shortcut's raw input has to be split by the transform warps as well
+// (conv2+nin: 1512 vs 854 + 212) — every wide block of the celeba network; whole forward 27.8-28.0 vs 26.6-27.3 ms (celeba, B = 16),
+// 46.8 vs 47.7 ms (imagenet, B = 8).  The halo-row form of conv_tc_kernel has since taken over its A-operand reuse.
 static int g_gn_enable = env_int("DDNM_GN_FUSED", 0);
 void tc_debug_gn_fused(int on) { g_gn_enable = on; }
 bool tc_gn_enabled() { return g_gn_enable != 0; }
