@@ -158,6 +158,26 @@ void UNetEngine::emit_tc(const std::string& name, const SplitView& a, int mode, 
   TcLaunch L = tc_make_launch(a, mode, side, w.hi, w.lo, 1, Cout, out, chanadd, ca_ld, residual, ldr, 1.0f, num_sms_, res_mode);
   const double bytes = (double)a.N * a.H * a.W * a.C * 4 + (side ? (double)side->N * side->H * side->W * side->C * 4 : 0) +
                        (double)Cout * w.ktot * 4 + (double)out.pixels() * Cout * 4 * (residual ? 2 : 1);
+  // split-K: few tiles walking a long K one k-block after the other (the 8x8 level: 32-64 CTAs, 72-144 k-blocks) are latency-bound;
+  // 2 or 4 CTAs per tile, each over its own k-block range into its own partial buffer, then one small deterministic reduce
+  const int tiles = L.p.tiles_x * L.p.tiles_y * L.p.tiles_n * L.p.n_tiles, kblocks = L.p.kb0 + L.p.kb1;
+  static const bool split_on = std::getenv("DDNM_SPLITK") == nullptr || std::atoi(std::getenv("DDNM_SPLITK")) != 0;
+  if (split_on && !L.pair && !L.halo && res_mode == 0 && 2 * tiles <= num_sms_ && kblocks >= 32) {
+    const int S = 4 * tiles <= num_sms_ ? 4 : 2;
+    const long long stride = out.pixels() * Cout;
+    float* part = (float*)arena_.alloc((size_t)S * stride * sizeof(float));
+    View pv;
+    pv.p = part; pv.N = out.N; pv.H = out.H; pv.W = out.W; pv.C = Cout; pv.ld = Cout;
+    TcLaunch Ls = tc_make_launch(a, mode, side, w.hi, w.lo, 1, Cout, pv, nullptr, 0, nullptr, 0, 1.0f, num_sms_, 0);
+    DDNM_CHECK(!Ls.pair && Ls.BN == L.BN, "split-K: tile shape changed");
+    Ls.p.split_k = S;
+    Ls.p.split_stride = stride;
+    Ls.grid = std::min(tiles * S, num_sms_);
+    add_op(name, "tc", L.flops, bytes, [Ls](cudaStream_t s) { tc_run(Ls, s); });
+    add_op(name + ".splitk_reduce", "reduce", 0, (double)(S + 1 + (residual ? 1 : 0)) * stride * 4,
+           [=](cudaStream_t s) { splitk_reduce(part, S, stride, out, chanadd, ca_ld, residual, ldr, s); });
+    return;
+  }
   add_op(name, "tc", L.flops, bytes, [L](cudaStream_t s) { tc_run(L, s); });
 }
 

@@ -544,6 +544,57 @@ void head_conv(const View& h, int groups, const float* gamma, const float* beta,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Second half of a split-K convolution (tc_gemm.cu, TcParams::split_k): out = sum of the S partial results in a fixed order
+// + per-(image, channel) add + residual, and the GroupNorm sums of the result.  One CTA per (image, few pixels), thread <-> 4 channels.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int S, long long stride, int HW, int C,
+                                                            float* __restrict__ out, int ld, const float* __restrict__ chanadd, int ca_ld,
+                                                            const float* __restrict__ residual, int ldr, StatAcc* __restrict__ stats,
+                                                            int st_ld, int ppc) {
+  pdl_prologue();
+  const int n = blockIdx.y, p0 = blockIdx.x * ppc, p1 = min(HW, p0 + ppc);
+  for (int c4 = threadIdx.x; c4 < (C >> 2); c4 += blockDim.x) {
+    const int c = c4 * 4;
+    const float4 ca = chanadd ? __ldg(reinterpret_cast<const float4*>(chanadd + (size_t)n * ca_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int p = p0; p < p1; ++p) {
+      const size_t pix = (size_t)n * HW + p;
+      float4 a = *reinterpret_cast<const float4*>(part + pix * C + c);
+      for (int k = 1; k < S; ++k) {
+        const float4 b = *reinterpret_cast<const float4*>(part + (size_t)k * stride + pix * C + c);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      a.x += ca.x; a.y += ca.y; a.z += ca.z; a.w += ca.w;
+      if (residual) {
+        const float4 r = *reinterpret_cast<const float4*>(residual + pix * ldr + c);
+        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+      }
+      *reinterpret_cast<float4*>(out + pix * ld + c) = a;
+      s4[0] += a.x; s4[1] += a.y; s4[2] += a.z; s4[3] += a.w;
+      q4[0] = fmaf(a.x, a.x, q4[0]); q4[1] = fmaf(a.y, a.y, q4[1]); q4[2] = fmaf(a.z, a.z, q4[2]); q4[3] = fmaf(a.w, a.w, q4[3]);
+    }
+    if (stats) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        StatAcc* d = stats + ((size_t)n * st_ld + c + j) * 2;
+        stat_add(d, s4[j]);
+        stat_add(d + 1, q4[j]);
+      }
+    }
+  }
+}
+void splitk_reduce(const float* part, int S, long long stride, const View& out, const float* chanadd, int ca_ld, const float* residual,
+                   int ldr, cudaStream_t st) {
+  DDNM_CHECK(out.C % 4 == 0 && out.ld % 4 == 0 && S >= 2, "split-K reduce: unsupported shape");
+  const int HW = out.H * out.W;
+  const int ppc = std::max(1, (int)cdivll((long long)HW * out.N, 296));
+  dim3 grid(cdiv(HW, ppc), out.N);
+  launch_pdl(splitk_reduce_kernel, grid, dim3(std::min(256, out.C / 4)), 0, st, 1, part, S, stride, HW, out.C, out.p, out.ld, chanadd, ca_ld, residual,
+             ldr, out.st, out.st_ld, ppc);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Timestep MLP pieces (models.py:6-24, 305-308, 121).  One warp per output element.
 // ---------------------------------------------------------------------------------------------------------------
 // The activations (N x K, act_in applied once) are staged in shared memory; each warp then produces LIN_OPW output features,

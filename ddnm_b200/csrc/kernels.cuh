@@ -24,6 +24,9 @@ void gn_apply_f32(const View& x, int groups, const float* gamma, const float* be
                   cudaStream_t s);
 
 // 3x3 pad-1 convolution with tiny Cin (the network stem): x NCHW [N,Cin,H,W] fp32, w OIHW, out NHWC view.
+// out = sum_k part[k] (fixed order) + chanadd + residual, with the GroupNorm sums of out (second half of a split-K convolution)
+void splitk_reduce(const float* part, int S, long long stride, const View& out, const float* chanadd, int ca_ld, const float* residual, int ldr,
+                   cudaStream_t s);
 // network head in one pass: GroupNorm + SiLU + 3x3 convolution to Cout <= 8 channels in exact fp32 on the CUDA cores, NCHW output
 bool head_conv_supported(const View& h, int Cout);
 void head_conv(const View& h, int groups, const float* gamma, const float* beta, float eps, const float* w_oihw, const float* bias, int Cout,

@@ -117,14 +117,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
   // PAIR: the scheduling unit is a pair of M-adjacent tiles sharing one N tile; CTA `rank` of the cluster owns tile 2*mp + rank.
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
-  const int n_units = PAIR ? total_tiles / 2 : total_tiles;
+  // split-K (single-CTA launches with few tiles and a long K, i.e. the 8x8 level: 32-64 CTAs walking 72-144 k-blocks one after
+  // the other are latency-bound): p.split_k CTAs share a tile, each accumulates its own range of k-blocks and writes alpha * acc
+  // to its own partial buffer (p.out + ks * p.split_stride); splitk_reduce_kernel adds the partials in a fixed order, applies the
+  // epilogue terms and accumulates the GroupNorm sums — deterministic, no floating-point atomics
+  const int n_units = PAIR ? total_tiles / 2 : total_tiles * p.split_k;
   const int n_workers = PAIR ? (int)(gridDim.x / 2) : (int)gridDim.x;
   const int worker = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
   const int unit_begin = p.deal ? (int)((long long)worker * n_units / n_workers) : worker;
   const int unit_end = p.deal ? (int)((long long)(worker + 1) * n_units / n_workers) : n_units;
   const int unit_step = p.deal ? 1 : n_workers;
+  auto k_lo = [&](int u) { return PAIR ? 0 : (int)((long long)(u % p.split_k) * KB / p.split_k); };
+  auto k_hi = [&](int u) { return PAIR ? KB : (int)((long long)(u % p.split_k + 1) * KB / p.split_k); };
   auto tile_of = [&](int u) {
-    if (!PAIR) return u;
+    if (!PAIR) return u / p.split_k;
     const int mp = u / p.n_tiles;
     return (2 * mp + (int)rank) * p.n_tiles + (u - mp * p.n_tiles);
   };
@@ -220,7 +226,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
         decode(tile, n_idx, x0, y0, n0);
         const int bz = p.b_batched == 1 ? n0 : 0;
         const int brow = n_idx * BN + (int)rank * Cfg::B_ROWS;
-        for (int kb = 0; kb < KB; ++kb) {
+        const int kb_lo = k_lo(u), kb_hi = k_hi(u);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t fb = full_bar(stage);
@@ -379,7 +386,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
           if (acc == 0) acc_phase ^= 1u;
           continue;
         }
-        for (int kb = 0; kb < KB; ++kb) {
+        const int kb_lo = k_lo(u), kb_hi = k_hi(u);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -394,14 +402,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
             if (PD) {
               // region X of the two CTAs forms [B_hi; B_lo]; region Y holds the B_hi halves of the 256 x 128 product
               const uint32_t by = (((sa + 2 * A_PLANE_BYTES + Cfg::BX_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
-              umma_f16_pair(d_tmem, hi | (ah + adv), hi | (bh + adv), idesc_wide, (uint32_t)((kb | k) != 0));
+              umma_f16_pair(d_tmem, hi | (ah + adv), hi | (bh + adv), idesc_wide, (uint32_t)(kb != kb_lo || k != 0));
               umma_f16_pair(d_tmem, hi | (al + adv), hi | (by + adv), p.idesc, 1u);
             } else if (DUAL && p.terms != 1) {
               // columns [0,BN) += A_hi*B_hi, [BN,2BN) += A_hi*B_lo in one instruction; then [0,BN) += A_lo*B_hi
-              umma_f16(d_tmem, hi | (ah + adv), hi | (bh + adv), idesc_wide, (uint32_t)((kb | k) != 0));
+              umma_f16(d_tmem, hi | (ah + adv), hi | (bh + adv), idesc_wide, (uint32_t)(kb != kb_lo || k != 0));
               umma_f16(d_tmem, hi | (al + adv), hi | (bh + adv), p.idesc, 1u);
             } else {
-              mma(d_tmem, hi | (ah + adv), hi | (bh + adv), (uint32_t)((kb | k) != 0));
+              mma(d_tmem, hi | (ah + adv), hi | (bh + adv), (uint32_t)(kb != kb_lo || k != 0));
               if (p.terms != 1) {
                 mma(d_tmem, hi | (ah + adv), hi | (bl + adv), 1u);
                 mma(d_tmem, hi | (al + adv), hi | (bh + adv), 1u);
@@ -460,7 +468,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0h, const __grid_constant
       const int n = n0 + ni;
       t.valid = n < p.N;
       t.img_w = n0 + (ew * 32) / (p.bw * p.bh);
-      t.orow = p.out + (long long)n * p.out_sn + (long long)(y0 + yi) * p.out_sy + (long long)(x0 + xi) * p.out_sx + t.n_idx * BN;
+      t.orow = p.out + (long long)n * p.out_sn + (long long)(y0 + yi) * p.out_sy + (long long)(x0 + xi) * p.out_sx + t.n_idx * BN +
+               (PAIR ? 0ll : (long long)(u % p.split_k) * p.split_stride);
       t.rrow = nullptr;
       if (p.residual) {
         // same pixel, nearest-upsampled (x_upd of ResBlock(up=True), unet.py:240) or the 2x2 average of a twice-as-large map

@@ -35,6 +35,8 @@ struct TcParams {
   float alpha;                 // out = alpha*acc + chanadd + residual
   StatAcc* stats;              // optional GroupNorm sums of the OUTPUT: stats[(image*st_ld + co)*2 + {0,1}] += {sum, sumsq}
   int st_ld;
+  int split_k = 1;             // > 1: this many CTAs per tile, each over its own k-block range, partial sums to out + ks * split_stride
+  long long split_stride = 0;  //      (single-CTA forms only; no chanadd / residual / stats: splitk_reduce applies them)
   int deal = 0;                // tile -> CTA map: 0 round-robin, 1 one contiguous range per CTA (see conv_tc_kernel)
   int terms;                   // 3: hi*hi + hi*lo + lo*hi (fp32-grade, default); 1: hi*hi only (plain fp16 inputs, fast mode)
   uint32_t desc_hi;            // UMMA smem descriptor high word (SW128 K-major), see tc_gemm.cu
